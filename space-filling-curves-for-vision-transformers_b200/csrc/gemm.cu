@@ -1,0 +1,460 @@
+// K3 — tcgen05 / TMEM / TMA GEMM family with fused epilogues (sm_100a).
+//
+// Replaces the cuBLASLt dispatches behind nn.Linear / nn.MultiheadAttention projections /
+// einsum of the reference encoder (/root/reference/src/models/vit.py:197-206, 262-266, 289-292 and
+// torch.nn.TransformerEncoderLayer), forward and backward:
+//   fwd   : Y[M,N]  = X[M,K]  . W[N,K]^T      A K-major,  B K-major
+//   dgrad : dX[M,K] = dY[M,N] . W[N,K]        A K-major,  B MN-major (W read in place, no transpose copy)
+//   wgrad : dW[N,K] = dY[M,N]^T . X[M,K]      A MN-major, B MN-major (+ split-K over the token dimension)
+//
+// Structure: persistent CTAs (one per SM), 128 x BN output tile, BK = 64 (one 128-byte swizzle atom),
+// kStages-deep TMA->smem ring, a single elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a
+// double-buffered TMEM accumulator (2 x BN columns) so that the epilogue warps (TMEM -> registers ->
+// bias / activation / residual / mask -> global) of tile i overlap the main loop of tile i+1.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue.
+#include "common.cuh"
+#include "sfcvit.h"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kNumThreads = 256;
+constexpr int kEpiThreads = 128;
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_tiles, num_n_tiles, splits, kblocks_per_split, num_k_blocks;
+  // epilogue
+  const __nv_bfloat16* bias;      // [N] or null
+  const __nv_bfloat16* residual;  // [M, ld_res] or null (added after activation)
+  const __nv_bfloat16* aux;       // [M, ld_aux] or null
+  void* out;                      // bf16 or fp32 [M, ld_out]
+  __nv_bfloat16* out_pre;         // optional pre-activation copy (bf16, ld_out)
+  long long ld_out, ld_res, ld_aux;
+  long long split_stride;         // elements between split-K partial outputs (fp32)
+  float alpha;
+  int act;                        // SFC_ACT_*
+  int aux_mode;                   // SFC_AUX_*
+  int out_fp32;
+  float drop_p;                   // dropout prob applied after activation (0 = off)
+  unsigned long long drop_seed;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// Counter-based dropout keep decision (same hash used by forward and backward): splitmix64 of (seed, index).
+__device__ __forceinline__ bool drop_keep(unsigned long long seed, unsigned long long idx, float p) {
+  unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  const float u = (float)(unsigned)(z >> 40) * (1.0f / 16777216.0f);
+  return u >= p;
+}
+
+template <int BN, int kStages, bool A_MN, bool B_MN>
+struct SmemLayout {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16 + 1024 /*alignment slack*/;
+};
+
+template <int BN, int kStages, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+  using L = SmemLayout<BN, kStages, A_MN, B_MN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles * p.splits;
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && ptx::elect_one()) {
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tmem_full[s], 1);
+      ptx::mbar_init(&tmem_empty[s], kEpiThreads);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<2 * BN>(tmem_ptr);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int split = t % p.splits;
+        const int tile = t / p.splits;
+        const int n_tile = tile % p.num_n_tiles;
+        const int m_tile = tile / p.num_n_tiles;
+        const int kb0 = split * p.kblocks_per_split;
+        const int kb1 = min(kb0 + p.kblocks_per_split, p.num_k_blocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          if constexpr (!A_MN) {
+            ptx::tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BK, m_tile * BM);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BM / 64; ++a)
+              ptx::tma_load_2d(&tmap_a, &full_bar[stage], sa + a * (BK * 128), m_tile * BM + a * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            ptx::tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * BK, n_tile * BN);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BN / 64; ++a)
+              ptx::tma_load_2d(&tmap_b, &full_bar[stage], sb + a * (BK * 128), n_tile * BN + a * 64, kb * BK);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (ptx::elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      constexpr uint32_t kLboA = A_MN ? BK * 128 : 0, kLboB = B_MN ? BK * 128 : 0;
+      constexpr uint32_t kAdvA = A_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;   // per UMMA_K = 16, in 16-byte units
+      constexpr uint32_t kAdvB = B_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+        const int split = t % p.splits;
+        const int kb0 = split * p.kblocks_per_split;
+        const int kb1 = min(kb0 + p.kblocks_per_split, p.num_k_blocks);
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+          const uint64_t da = umma_smem_desc_sw128(sa, kLboA, 1024);
+          const uint64_t db = umma_smem_desc_sw128(sb, kLboB, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            ptx::umma_f16(tmem_d, da + (uint64_t)(k * kAdvA), db + (uint64_t)(k * kAdvB), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          ptx::umma_commit(&empty_bar[stage]);            // frees the smem slot when these MMAs retire
+          if (kb == kb1 - 1) ptx::umma_commit(&tmem_full[acc]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== epilogue (4 warps, thread <-> accumulator row) =====================
+    const int ewarp = warp - 4;                    // == warp % 4 : TMEM lane quarter
+    const int lane = threadIdx.x & 31;
+    const int row_in_tile = ewarp * 32 + lane;
+    int iter = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+      const int split = t % p.splits;
+      const int tile = t / p.splits;
+      const int n_tile = tile % p.num_n_tiles;
+      const int m_tile = tile / p.num_n_tiles;
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const long long m = (long long)m_tile * BM + row_in_tile;
+      const bool row_ok = m < p.M;
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(ewarp * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = n_tile * BN + c * 32;
+        if (n0 >= p.N) break;                      // warp-uniform
+        uint32_t r[32];
+        ptx::tmem_ld_x32(taddr + c * 32, r);
+        ptx::tmem_ld_wait();
+        if (!row_ok) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+        const bool full = (n0 + 32 <= p.N);
+        if (p.bias) {
+          if (full && ((reinterpret_cast<uintptr_t>(p.bias + n0) & 15) == 0)) {
+            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 b = __ldg(bp + q);
+              v[q * 8 + 0] += ptx::bf16_lo(b.x); v[q * 8 + 1] += ptx::bf16_hi(b.x);
+              v[q * 8 + 2] += ptx::bf16_lo(b.y); v[q * 8 + 3] += ptx::bf16_hi(b.y);
+              v[q * 8 + 4] += ptx::bf16_lo(b.z); v[q * 8 + 5] += ptx::bf16_hi(b.z);
+              v[q * 8 + 6] += ptx::bf16_lo(b.w); v[q * 8 + 7] += ptx::bf16_hi(b.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) v[j] += __bfloat162float(p.bias[n0 + j]);
+          }
+        }
+        const bool out_vec = full && (p.ld_out % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+        if (p.out_pre) {
+          __nv_bfloat16* op = p.out_pre + m * p.ld_out + n0;
+          if (out_vec && ((reinterpret_cast<uintptr_t>(p.out_pre) & 15) == 0)) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              o.x = ptx::pack_bf16(v[q * 8 + 0], v[q * 8 + 1]); o.y = ptx::pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+              o.z = ptx::pack_bf16(v[q * 8 + 4], v[q * 8 + 5]); o.w = ptx::pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+              reinterpret_cast<uint4*>(op)[q] = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) op[j] = __float2bfloat16(v[j]);
+          }
+        }
+        if (p.act == SFC_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        } else if (p.act == SFC_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (p.drop_p > 0.0f) {
+          const float sc = 1.0f / (1.0f - p.drop_p);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = drop_keep(p.drop_seed, (unsigned long long)m * (unsigned long long)p.N + (unsigned long long)(n0 + j), p.drop_p) ? v[j] * sc : 0.0f;
+        }
+        if (p.aux_mode != SFC_AUX_NONE) {
+          const __nv_bfloat16* ap = p.aux + m * p.ld_aux + n0;
+          float a[32];
+          if (full && (p.ld_aux % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0)) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 b = __ldg(reinterpret_cast<const uint4*>(ap) + q);
+              a[q * 8 + 0] = ptx::bf16_lo(b.x); a[q * 8 + 1] = ptx::bf16_hi(b.x);
+              a[q * 8 + 2] = ptx::bf16_lo(b.y); a[q * 8 + 3] = ptx::bf16_hi(b.y);
+              a[q * 8 + 4] = ptx::bf16_lo(b.z); a[q * 8 + 5] = ptx::bf16_hi(b.z);
+              a[q * 8 + 6] = ptx::bf16_lo(b.w); a[q * 8 + 7] = ptx::bf16_hi(b.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a[j] = (n0 + j < p.N) ? __bfloat162float(ap[j]) : 0.0f;
+          }
+          if (p.aux_mode == SFC_AUX_RELU_MASK) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = a[j] > 0.0f ? v[j] : 0.0f;
+          } else {  // SFC_AUX_GELU_GRAD: aux holds the pre-activation
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(a[j]);
+          }
+        }
+        if (p.residual) {
+          const __nv_bfloat16* rp = p.residual + m * p.ld_res + n0;
+          if (full && (p.ld_res % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 b = __ldg(reinterpret_cast<const uint4*>(rp) + q);
+              v[q * 8 + 0] += ptx::bf16_lo(b.x); v[q * 8 + 1] += ptx::bf16_hi(b.x);
+              v[q * 8 + 2] += ptx::bf16_lo(b.y); v[q * 8 + 3] += ptx::bf16_hi(b.y);
+              v[q * 8 + 4] += ptx::bf16_lo(b.z); v[q * 8 + 5] += ptx::bf16_hi(b.z);
+              v[q * 8 + 6] += ptx::bf16_lo(b.w); v[q * 8 + 7] += ptx::bf16_hi(b.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) v[j] += __bfloat162float(rp[j]);
+          }
+        }
+        if (p.out_fp32) {
+          float* op = reinterpret_cast<float*>(p.out) + (long long)split * p.split_stride + m * p.ld_out + n0;
+          if (full && (p.ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && (p.split_stride % 4 == 0)) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              reinterpret_cast<float4*>(op)[q] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) op[j] = v[j];
+          }
+        } else {
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ld_out + n0;
+          if (out_vec) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              o.x = ptx::pack_bf16(v[q * 8 + 0], v[q * 8 + 1]); o.y = ptx::pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+              o.z = ptx::pack_bf16(v[q * 8 + 4], v[q * 8 + 5]); o.w = ptx::pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+              reinterpret_cast<uint4*>(op)[q] = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) op[j] = __float2bfloat16(v[j]);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<2 * BN>(tmem_base);
+  }
+}
+
+// out[m,n] (bf16 or fp32) = (accumulate ? out : 0) + sum_s ws[s,m,n]
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, long long split_stride, int splits, void* __restrict__ out,
+                                     long long ld_out, int M, int N, int out_fp32, int accumulate) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)M * N;
+  if (idx >= total) return;
+  const long long m = idx / N, n = idx % N;
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += ws[k * split_stride + idx];
+  if (out_fp32) {
+    float* o = reinterpret_cast<float*>(out) + m * ld_out + n;
+    *o = accumulate ? (*o + s) : s;
+  } else {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + m * ld_out + n;
+    *o = __float2bfloat16(accumulate ? (__bfloat162float(*o) + s) : s);
+  }
+}
+
+template <int BN, int kStages, bool A_MN, bool B_MN>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using L = SmemLayout<BN, kStages, A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<BN, kStages, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    SFC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles * p.splits;
+  const int grid = total_tiles < sfc_num_sms() ? total_tiles : sfc_num_sms();
+  kern<<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, p);
+  SFC_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" size_t sfc_gemm_workspace_bytes(int M, int N, int K, int splits) {
+  if (splits <= 1) return 0;
+  return (size_t)splits * (size_t)M * (size_t)N * sizeof(float);
+}
+
+// Heuristic split-K factor for reductions over the token dimension (wgrad): enough CTAs for ~2 waves.
+extern "C" int sfc_gemm_suggest_splits(int M, int N, int K) {
+  const int bn = (N >= 256) ? 256 : 128;
+  const long long tiles = (long long)sfc_ceil_div(M, BM) * sfc_ceil_div(N, bn);
+  const int kblocks = sfc_ceil_div(K, BK);
+  const int sms = sfc_num_sms();
+  if (tiles >= sms || kblocks < 16) return 1;
+  long long s = (2ll * sms + tiles - 1) / tiles;
+  const long long max_s = kblocks / 8 > 0 ? kblocks / 8 : 1;   // at least 8 k-blocks per split
+  if (s > max_s) s = max_s;
+  if (s > 64) s = 64;
+  return s < 1 ? 1 : (int)s;
+}
+
+extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major, long long ldb,
+                             int M, int N, int K, const SfcGemmEpilogue* ep, void* workspace, size_t workspace_bytes,
+                             int splits, cudaStream_t stream) {
+  SFC_REQUIRE(A && B && ep && ep->out, "sfc_gemm_bf16: null pointer argument");
+  SFC_REQUIRE(M > 0 && N > 0 && K > 0, "sfc_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
+  SFC_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "sfc_gemm_bf16: leading dimensions must be multiples of 8 elements (lda=%lld ldb=%lld)", lda, ldb);
+  if (splits < 1) splits = 1;
+  const int BN = (N > 128) ? 256 : 128;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.num_m_tiles = sfc_ceil_div(M, BM);
+  p.num_n_tiles = sfc_ceil_div(N, BN);
+  p.num_k_blocks = sfc_ceil_div(K, BK);
+  if (splits > p.num_k_blocks) splits = p.num_k_blocks;
+  p.kblocks_per_split = sfc_ceil_div(p.num_k_blocks, splits);
+  splits = sfc_ceil_div(p.num_k_blocks, p.kblocks_per_split);   // no empty splits
+  p.splits = splits;
+  p.bias = (const __nv_bfloat16*)ep->bias;
+  p.residual = (const __nv_bfloat16*)ep->residual;
+  p.aux = (const __nv_bfloat16*)ep->aux;
+  p.out = ep->out;
+  p.out_pre = (__nv_bfloat16*)ep->out_pre;
+  p.ld_out = ep->ld_out; p.ld_res = ep->ld_res; p.ld_aux = ep->ld_aux;
+  p.alpha = ep->alpha;
+  p.act = ep->act; p.aux_mode = ep->aux_mode; p.out_fp32 = ep->out_fp32;
+  p.drop_p = ep->drop_p; p.drop_seed = ep->drop_seed;
+  p.split_stride = 0;
+  SFC_REQUIRE(p.aux_mode == SFC_AUX_NONE || p.aux != nullptr, "sfc_gemm_bf16: aux_mode set but aux is null");
+  SFC_REQUIRE(p.drop_p >= 0.f && p.drop_p < 1.f, "sfc_gemm_bf16: dropout p out of range");
+
+  GemmParams pk = p;
+  if (splits > 1) {
+    SFC_REQUIRE(!p.bias && !p.residual && p.aux_mode == SFC_AUX_NONE && p.act == SFC_ACT_NONE && !p.out_pre && p.drop_p == 0.f,
+                "sfc_gemm_bf16: split-K supports only a plain (optionally accumulating) epilogue");
+    const size_t need = (size_t)splits * (size_t)M * (size_t)N * sizeof(float);
+    SFC_REQUIRE(workspace && workspace_bytes >= need, "sfc_gemm_bf16: split-K workspace too small (%zu < %zu)", workspace_bytes, need);
+    pk.out = workspace; pk.out_fp32 = 1; pk.ld_out = N; pk.split_stride = (long long)M * N; pk.alpha = p.alpha;
+  } else {
+    SFC_REQUIRE(!ep->accumulate, "sfc_gemm_bf16: accumulate requires split-K (splits > 1)");
+  }
+
+  CUtensorMap ta, tb;
+  // K-major operand: global [rows = M or N][cols = K]; MN-major operand: global [rows = K][cols = M or N].
+  if (!a_mn_major) { if (int e = sfc_make_tmap_2d(&ta, A, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK, BM, true)) return e; }
+  else             { if (int e = sfc_make_tmap_2d(&ta, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, BK, true)) return e; }
+  if (!b_mn_major) { if (int e = sfc_make_tmap_2d(&tb, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, (uint32_t)BN, true)) return e; }
+  else             { if (int e = sfc_make_tmap_2d(&tb, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, BK, true)) return e; }
+
+  int rc = 0;
+#define SFC_DISPATCH(BN_, ST_)                                                              \
+  do {                                                                                      \
+    if (!a_mn_major && !b_mn_major) rc = launch_gemm<BN_, ST_, false, false>(ta, tb, pk, stream); \
+    else if (!a_mn_major && b_mn_major) rc = launch_gemm<BN_, ST_, false, true>(ta, tb, pk, stream); \
+    else if (a_mn_major && b_mn_major) rc = launch_gemm<BN_, ST_, true, true>(ta, tb, pk, stream);  \
+    else rc = launch_gemm<BN_, ST_, true, false>(ta, tb, pk, stream);                        \
+  } while (0)
+  if (BN == 256) SFC_DISPATCH(256, 4); else SFC_DISPATCH(128, 6);
+#undef SFC_DISPATCH
+  if (rc) return rc;
+
+  if (splits > 1) {
+    const long long total = (long long)M * N;
+    const int threads = 256;
+    splitk_reduce_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(
+        (const float*)workspace, (long long)M * N, splits, ep->out, ep->ld_out, M, N, ep->out_fp32, ep->accumulate);
+    SFC_LAUNCH_OK();
+  }
+  return 0;
+}

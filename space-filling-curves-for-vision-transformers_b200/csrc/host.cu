@@ -1,0 +1,70 @@
+// Host-side plumbing of libsfcvit: thread-local error string, TMA descriptor encoding, device info.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "sfcvit.h"
+
+static thread_local char g_err[1024] = "";
+
+void sfc_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* sfc_last_error(void) { return g_err; }
+
+extern "C" int sfc_abi_version(void) { return SFCVIT_ABI_VERSION; }
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+int sfc_make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows,
+                     uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows, bool swizzle128) {
+  PFN_encodeTiled enc = get_encode();
+  SFC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+  SFC_REQUIRE(((uintptr_t)base & 15) == 0, "TMA base pointer must be 16-byte aligned (%p)", base);
+  SFC_REQUIRE((row_stride_bytes & 15) == 0, "TMA row stride must be a multiple of 16 bytes (%llu)",
+              (unsigned long long)row_stride_bytes);
+  SFC_REQUIRE(box_rows >= 1 && box_rows <= 256 && box_cols >= 1 && box_cols <= 256, "TMA box out of range");
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                           : (elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SFC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) cols=%llu rows=%llu stride=%llu box=%ux%u", (int)r,
+              (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)row_stride_bytes, box_cols, box_rows);
+  return 0;
+}
+
+int sfc_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+extern "C" int sfc_device_sm_count(void) { return sfc_num_sms(); }

@@ -1,0 +1,68 @@
+"""ctypes binding of include/sfcvit.h."""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PK = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_PK, "lib", "libsfcvit.so")
+
+_lock = threading.Lock()
+_lib = None
+
+
+class SfcGemmEpilogue(ctypes.Structure):
+    _fields_ = [
+        ("bias", ctypes.c_void_p), ("residual", ctypes.c_void_p), ("aux", ctypes.c_void_p),
+        ("out", ctypes.c_void_p), ("out_pre", ctypes.c_void_p),
+        ("ld_out", ctypes.c_longlong), ("ld_res", ctypes.c_longlong), ("ld_aux", ctypes.c_longlong),
+        ("alpha", ctypes.c_float), ("act", ctypes.c_int), ("aux_mode", ctypes.c_int),
+        ("out_fp32", ctypes.c_int), ("accumulate", ctypes.c_int), ("drop_p", ctypes.c_float),
+        ("drop_seed", ctypes.c_ulonglong),
+    ]
+
+
+_vp, _i, _ll, _sz, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_size_t, ctypes.c_float
+
+# name -> (restype, argtypes); must list every symbol declared in include/sfcvit.h
+SIGNATURES = {
+    "sfc_last_error": (ctypes.c_char_p, []),
+    "sfc_abi_version": (_i, []),
+    "sfc_device_sm_count": (_i, []),
+    "sfc_curve_perm_scratch_bytes": (_sz, [_i, _i, _i]),
+    "sfc_curve_perm": (_i, [_i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "sfc_gemm_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "sfc_gemm_suggest_splits": (_i, [_i, _i, _i]),
+    "sfc_gemm_bf16": (_i, [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, ctypes.POINTER(SfcGemmEpilogue), _vp, _sz, _i, _vp]),
+}
+
+
+def load(build_if_missing: bool = True):
+    """Loads libsfcvit.so (building it with nvcc when absent). Raises if it cannot be loaded."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            if not build_if_missing:
+                raise RuntimeError(f"libsfcvit.so not built: {LIB_PATH}")
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("_sfcvit_build", os.path.join(_PK, "build.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build()
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        if lib.sfc_abi_version() != 1:
+            raise RuntimeError("libsfcvit ABI version mismatch")
+        _lib = lib
+        return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().sfc_last_error()
+        raise RuntimeError(f"libsfcvit {what} failed (rc={rc}): {msg.decode() if msg else '?'}")

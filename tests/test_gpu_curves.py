@@ -1,0 +1,58 @@
+"""K1 parity: CUDA curve permutation vs the C oracle (bit-exact), through the C ABI."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import curves as oc
+
+pytestmark = pytest.mark.gpu
+
+CURVES = ["hilbert", "z", "peano", "moore"]
+# golden hashes generated from the live reference (SURVEY.md §8c / tests/golden/perm_hashes.json)
+GOLD = {("hilbert", 14): "ed85c65cf3da0fef", ("z", 14): "814324e2de38b78d", ("peano", 14): "559705620d5306c3",
+        ("moore", 14): "dac888401a2685b9", ("hilbert", 224): "60518acff2ddbcc5", ("hilbert", 1024): "72d4e368d71bf721"}
+
+
+def _gpu_perm(curve, w, h):
+    from sfcvit import ops
+    perm, inv = ops.curve_perm(curve, w, h)
+    return perm.cpu().numpy().astype(np.int64), inv.cpu().numpy().astype(np.int64)
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_square_grids_bit_exact(cuda_device, curve):
+    for n in list(range(1, 34)) + [64, 81, 96, 224, 243, 384]:
+        perm, inv = _gpu_perm(curve, n, n)
+        ref = oc.flat_perm(curve, n, n)
+        assert np.array_equal(perm, ref), (curve, n)
+        assert np.array_equal(inv[perm], np.arange(n * n)), (curve, n)
+        if (curve, n) in GOLD:
+            assert hashlib.sha256(perm.astype("<i8").tobytes()).hexdigest()[:16] == GOLD[(curve, n)]
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_rectangular_grids(cuda_device, curve):
+    for (w, h) in [(6, 10), (10, 6), (1, 7), (9, 2), (30, 17), (224, 100)]:
+        perm, inv = _gpu_perm(curve, w, h)
+        assert np.array_equal(perm, oc.flat_perm(curve, w, h)), (curve, w, h)
+        assert np.array_equal(np.sort(perm), np.arange(w * h))
+
+
+def test_large_hilbert_1024(cuda_device):
+    perm, inv = _gpu_perm("hilbert", 1024, 1024)
+    assert hashlib.sha256(perm.astype("<i8").tobytes()).hexdigest()[:16] == GOLD[("hilbert", 1024)]
+    assert np.array_equal(inv[perm], np.arange(1024 * 1024))
+
+
+def test_raster_is_identity(cuda_device):
+    perm, inv = _gpu_perm("raster", 14, 14)
+    assert np.array_equal(perm, np.arange(196)) and np.array_equal(inv, np.arange(196))
+
+
+def test_bad_arguments_raise(cuda_device):
+    from sfcvit import ops
+    with pytest.raises(ValueError):
+        ops.curve_perm("onion_curve", 4, 4)
+    with pytest.raises(RuntimeError):
+        ops.curve_perm("hilbert", 0, 4)

@@ -1,0 +1,41 @@
+"""K3 parity: tcgen05 GEMM vs torch fp32 matmul of the same bf16 inputs (tolerance: rel-L2 < 6e-3,
+max-abs < 2% of the output range — bf16 output rounding is 2^-8 relative)."""
+import os
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+
+SHAPES = [(128, 128, 64), (256, 256, 128), (392, 768, 768), (1000, 2304, 768), (200, 192, 48 + 16), (77, 40, 72)]
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_gemm_layouts(cuda_device, shape, a_mn, b_mn):
+    import gemm_selftest
+    M, N, K = shape
+    if (a_mn and M % 8) or (b_mn and N % 8):
+        pytest.skip("MN-major operand needs a 16-byte aligned leading dimension")
+    r = gemm_selftest.run(M, N, K, a_mn, b_mn)
+    assert r["ok"], r
+
+
+@pytest.mark.parametrize("epi", ["bias_relu", "bias_gelu_pre", "bias_res", "relu_mask_res", "gelu_grad", "fp32"])
+def test_gemm_epilogues(cuda_device, epi):
+    import gemm_selftest
+    for (M, N, K) in [(392, 768, 256), (130, 200, 64)]:
+        r = gemm_selftest.run(M, N, K, False, False, epi)
+        assert r["ok"], r
+        if "pre_rel_l2" in r:
+            assert r["pre_rel_l2"] < 6e-3
+
+
+@pytest.mark.parametrize("splits", [2, 5, 0])
+def test_gemm_splitk_wgrad_shape(cuda_device, splits):
+    import gemm_selftest
+    r = gemm_selftest.run(768, 256, 4096, True, True, "fp32", splits)
+    assert r["ok"], r
+    r = gemm_selftest.run(256, 768, 3000 - 3000 % 8, True, True, "none", splits)
+    assert r["ok"], r
