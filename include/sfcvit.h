@@ -74,6 +74,58 @@ int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B, i
                   int N, int K, const SfcGemmEpilogue* ep, void* workspace, size_t workspace_bytes, int splits,
                   sfc_stream_t stream);
 
+/* ---- K5: LayerNorm forward / backward and column sums (nn.LayerNorm in the encoder layers, vit.py:197-206 ->
+ *      torch TransformerEncoderLayer.norm1/norm2; vit.py:253-254, :303; bias gradients of every nn.Linear) ----
+ * x, y, dy, dx, gamma, beta: bf16; mean/rstd: fp32 [rows]; D % 8 == 0, D <= 2048.
+ * dgamma/dbeta: bf16 (param_fp32 = 0) or fp32 (1); accumulate != 0 adds to the existing value. */
+int sfc_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
+                      long long rows, int D, float eps, sfc_stream_t stream);
+size_t sfc_layernorm_bwd_scratch_bytes(long long rows, int D);
+int sfc_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma, void* dx,
+                      void* dgamma, void* dbeta, int param_fp32, int accumulate, void* scratch, size_t scratch_bytes,
+                      long long rows, int D, sfc_stream_t stream);
+size_t sfc_colsum_scratch_bytes(long long rows, int N);
+int sfc_colsum(const void* x, long long ld, long long rows, int N, void* out, int out_fp32, int accumulate,
+               void* scratch, size_t scratch_bytes, sfc_stream_t stream);
+
+/* ---- K2: fused curve-order patch gather + patch-embedding GEMM
+ *      (tokenizers: multiscale/multi_hilbert.py:74-84 SFCEmbedding1D.forward and its morton/peano/moore copies,
+ *       _1D/hilbert_embedding1D.py:30-43, _2D/hilbert_embedding.py:80-91, _2D/zigzag_embedding.py:24-30) ----
+ * img: NCHW fp32 (img_bf16 = 0) or bf16 (1). p = pre-patch size, g = group size, perm = int32 [(H/p)*(W/p)] flat
+ * pre-patch indices r*(W/p)+c in curve order. Wk: bf16 [D, Kpad], K axis ordered (q, c, p1, p2) and zero padded to
+ * Kpad = sfc_patch_embed_kpad(C,p,g). out row of token t of image b: b*rows_per_img + tok_off + t, row stride ld_out
+ * (the caller may pre-offset `out` to write a column slice of a wider matrix). pos: optional bf16 [ntok, ld_pos]. */
+int sfc_patch_embed_kpad(int C, int p, int g);
+int sfc_patch_embed_fwd(const void* img, int img_bf16, int B, int C, int H, int W, int p, int g, const int32_t* perm,
+                        const void* Wk, const void* bias, const void* pos, long long ld_pos, void* out, long long ld_out,
+                        int D, int rows_per_img, int tok_off, sfc_stream_t stream);
+/* backward helper: A[M, Kpad] bf16 = curve-ordered im2col (same K order); dWk = dOut^T . A via sfc_gemm_bf16 */
+int sfc_patch_gather(const void* img, int img_bf16, int B, int C, int H, int W, int p, int g, const int32_t* perm,
+                     void* A, sfc_stream_t stream);
+
+/* ---- K4: flash attention forward / backward, head_dim 64, non-causal
+ *      (F.scaled_dot_product_attention inside nn.MultiheadAttention: vit.py:197-206 -> torch
+ *       TransformerEncoderLayer._sa_block; altvit.py:129-141) ----
+ * qkv: bf16 [B*N, 3*D] packed in-projection output (q | k | v, head h = columns h*64..h*64+63 of each third);
+ * out: bf16 [B*N, D]; lse: fp32 [B, H, N] (natural log of the softmax denominator, for backward);
+ * dqkv: bf16 [B*N, 3*D]; scratch (backward): fp32 [B*N, D] dQ accumulator. drop_p: attention-probability dropout. */
+int sfc_attn_fwd(const void* qkv, void* out, float* lse, int B, int H, int N, int D, float scale, float drop_p,
+                 unsigned long long drop_seed, sfc_stream_t stream);
+size_t sfc_attn_bwd_scratch_bytes(int B, int N, int D);
+int sfc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* scratch,
+                 size_t scratch_bytes, int B, int H, int N, int D, float scale, float drop_p,
+                 unsigned long long drop_seed, sfc_stream_t stream);
+
+/* ---- K6: fused grad-norm / clip / AdamW over flat buckets
+ *      (torch.nn.utils.clip_grad_norm_ + optim.AdamW.step: src/training/train.py:165-166, main.py:288-289) ----
+ * sfc_grad_sumsq: accum[0] += sum(g^2) (caller zeroes accum). sfc_adamw_step: decoupled weight decay Adam on
+ * n elements; gradient used = g * grad_scale * min(1, max_norm / (sqrt(stats[0]) * grad_scale + 1e-6))
+ * (max_norm <= 0 or stats == NULL: no clipping). p/g: bf16 or fp32 (param_fp32); m/v: bf16 or fp32 (state_fp32). */
+int sfc_grad_sumsq(const void* g, int g_fp32, long long n, float* accum, sfc_stream_t stream);
+int sfc_adamw_step(void* p, const void* g, void* m, void* v, long long n, int param_fp32, int state_fp32, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, float max_norm,
+                   const float* stats, sfc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,7 @@
 // bias / activation / residual / mask -> global) of tile i overlap the main loop of tile i+1.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue.
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
 #include "sfcvit.h"
 
 namespace {
@@ -25,38 +26,8 @@ constexpr int kEpiThreads = 128;
 struct GemmParams {
   int M, N, K;
   int num_m_tiles, num_n_tiles, splits, kblocks_per_split, num_k_blocks;
-  // epilogue
-  const __nv_bfloat16* bias;      // [N] or null
-  const __nv_bfloat16* residual;  // [M, ld_res] or null (added after activation)
-  const __nv_bfloat16* aux;       // [M, ld_aux] or null
-  void* out;                      // bf16 or fp32 [M, ld_out]
-  __nv_bfloat16* out_pre;         // optional pre-activation copy (bf16, ld_out)
-  long long ld_out, ld_res, ld_aux;
-  long long split_stride;         // elements between split-K partial outputs (fp32)
-  float alpha;
-  int act;                        // SFC_ACT_*
-  int aux_mode;                   // SFC_AUX_*
-  int out_fp32;
-  float drop_p;                   // dropout prob applied after activation (0 = off)
-  unsigned long long drop_seed;
+  EpiParams epi;
 };
-
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
-}
-
-// Counter-based dropout keep decision (same hash used by forward and backward): splitmix64 of (seed, index).
-__device__ __forceinline__ bool drop_keep(unsigned long long seed, unsigned long long idx, float p) {
-  unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  const float u = (float)(unsigned)(z >> 40) * (1.0f / 16777216.0f);
-  return u >= p;
-}
 
 template <int BN, int kStages, bool A_MN, bool B_MN>
 struct SmemLayout {
@@ -203,123 +174,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (!row_ok) continue;
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-        const bool full = (n0 + 32 <= p.N);
-        if (p.bias) {
-          if (full && ((reinterpret_cast<uintptr_t>(p.bias + n0) & 15) == 0)) {
-            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 b = __ldg(bp + q);
-              v[q * 8 + 0] += ptx::bf16_lo(b.x); v[q * 8 + 1] += ptx::bf16_hi(b.x);
-              v[q * 8 + 2] += ptx::bf16_lo(b.y); v[q * 8 + 3] += ptx::bf16_hi(b.y);
-              v[q * 8 + 4] += ptx::bf16_lo(b.z); v[q * 8 + 5] += ptx::bf16_hi(b.z);
-              v[q * 8 + 6] += ptx::bf16_lo(b.w); v[q * 8 + 7] += ptx::bf16_hi(b.w);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) v[j] += __bfloat162float(p.bias[n0 + j]);
-          }
-        }
-        const bool out_vec = full && (p.ld_out % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
-        if (p.out_pre) {
-          __nv_bfloat16* op = p.out_pre + m * p.ld_out + n0;
-          if (out_vec && ((reinterpret_cast<uintptr_t>(p.out_pre) & 15) == 0)) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 o;
-              o.x = ptx::pack_bf16(v[q * 8 + 0], v[q * 8 + 1]); o.y = ptx::pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-              o.z = ptx::pack_bf16(v[q * 8 + 4], v[q * 8 + 5]); o.w = ptx::pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-              reinterpret_cast<uint4*>(op)[q] = o;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) op[j] = __float2bfloat16(v[j]);
-          }
-        }
-        if (p.act == SFC_ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-        } else if (p.act == SFC_ACT_GELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        }
-        if (p.drop_p > 0.0f) {
-          const float sc = 1.0f / (1.0f - p.drop_p);
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = drop_keep(p.drop_seed, (unsigned long long)m * (unsigned long long)p.N + (unsigned long long)(n0 + j), p.drop_p) ? v[j] * sc : 0.0f;
-        }
-        if (p.aux_mode != SFC_AUX_NONE) {
-          const __nv_bfloat16* ap = p.aux + m * p.ld_aux + n0;
-          float a[32];
-          if (full && (p.ld_aux % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0)) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 b = __ldg(reinterpret_cast<const uint4*>(ap) + q);
-              a[q * 8 + 0] = ptx::bf16_lo(b.x); a[q * 8 + 1] = ptx::bf16_hi(b.x);
-              a[q * 8 + 2] = ptx::bf16_lo(b.y); a[q * 8 + 3] = ptx::bf16_hi(b.y);
-              a[q * 8 + 4] = ptx::bf16_lo(b.z); a[q * 8 + 5] = ptx::bf16_hi(b.z);
-              a[q * 8 + 6] = ptx::bf16_lo(b.w); a[q * 8 + 7] = ptx::bf16_hi(b.w);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) a[j] = (n0 + j < p.N) ? __bfloat162float(ap[j]) : 0.0f;
-          }
-          if (p.aux_mode == SFC_AUX_RELU_MASK) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = a[j] > 0.0f ? v[j] : 0.0f;
-          } else {  // SFC_AUX_GELU_GRAD: aux holds the pre-activation
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(a[j]);
-          }
-        }
-        if (p.residual) {
-          const __nv_bfloat16* rp = p.residual + m * p.ld_res + n0;
-          if (full && (p.ld_res % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 b = __ldg(reinterpret_cast<const uint4*>(rp) + q);
-              v[q * 8 + 0] += ptx::bf16_lo(b.x); v[q * 8 + 1] += ptx::bf16_hi(b.x);
-              v[q * 8 + 2] += ptx::bf16_lo(b.y); v[q * 8 + 3] += ptx::bf16_hi(b.y);
-              v[q * 8 + 4] += ptx::bf16_lo(b.z); v[q * 8 + 5] += ptx::bf16_hi(b.z);
-              v[q * 8 + 6] += ptx::bf16_lo(b.w); v[q * 8 + 7] += ptx::bf16_hi(b.w);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) v[j] += __bfloat162float(rp[j]);
-          }
-        }
-        if (p.out_fp32) {
-          float* op = reinterpret_cast<float*>(p.out) + (long long)split * p.split_stride + m * p.ld_out + n0;
-          if (full && (p.ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && (p.split_stride % 4 == 0)) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              reinterpret_cast<float4*>(op)[q] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) op[j] = v[j];
-          }
-        } else {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ld_out + n0;
-          if (out_vec) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 o;
-              o.x = ptx::pack_bf16(v[q * 8 + 0], v[q * 8 + 1]); o.y = ptx::pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-              o.z = ptx::pack_bf16(v[q * 8 + 4], v[q * 8 + 5]); o.w = ptx::pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-              reinterpret_cast<uint4*>(op)[q] = o;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) op[j] = __float2bfloat16(v[j]);
-          }
-        }
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        epi_apply_store(p.epi, v, m, m, n0, split);
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
@@ -406,26 +262,28 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
   p.kblocks_per_split = sfc_ceil_div(p.num_k_blocks, splits);
   splits = sfc_ceil_div(p.num_k_blocks, p.kblocks_per_split);   // no empty splits
   p.splits = splits;
-  p.bias = (const __nv_bfloat16*)ep->bias;
-  p.residual = (const __nv_bfloat16*)ep->residual;
-  p.aux = (const __nv_bfloat16*)ep->aux;
-  p.out = ep->out;
-  p.out_pre = (__nv_bfloat16*)ep->out_pre;
-  p.ld_out = ep->ld_out; p.ld_res = ep->ld_res; p.ld_aux = ep->ld_aux;
-  p.alpha = ep->alpha;
-  p.act = ep->act; p.aux_mode = ep->aux_mode; p.out_fp32 = ep->out_fp32;
-  p.drop_p = ep->drop_p; p.drop_seed = ep->drop_seed;
-  p.split_stride = 0;
-  SFC_REQUIRE(p.aux_mode == SFC_AUX_NONE || p.aux != nullptr, "sfc_gemm_bf16: aux_mode set but aux is null");
-  SFC_REQUIRE(p.drop_p >= 0.f && p.drop_p < 1.f, "sfc_gemm_bf16: dropout p out of range");
+  EpiParams& e = p.epi;
+  e.N = N;
+  e.bias = (const __nv_bfloat16*)ep->bias;
+  e.residual = (const __nv_bfloat16*)ep->residual;
+  e.aux = (const __nv_bfloat16*)ep->aux;
+  e.out = ep->out;
+  e.out_pre = (__nv_bfloat16*)ep->out_pre;
+  e.ld_out = ep->ld_out; e.ld_res = ep->ld_res; e.ld_aux = ep->ld_aux;
+  e.alpha = ep->alpha;
+  e.act = ep->act; e.aux_mode = ep->aux_mode; e.out_fp32 = ep->out_fp32;
+  e.drop_p = ep->drop_p; e.drop_seed = ep->drop_seed;
+  e.split_stride = 0;
+  SFC_REQUIRE(e.aux_mode == SFC_AUX_NONE || e.aux != nullptr, "sfc_gemm_bf16: aux_mode set but aux is null");
+  SFC_REQUIRE(e.drop_p >= 0.f && e.drop_p < 1.f, "sfc_gemm_bf16: dropout p out of range");
 
   GemmParams pk = p;
   if (splits > 1) {
-    SFC_REQUIRE(!p.bias && !p.residual && p.aux_mode == SFC_AUX_NONE && p.act == SFC_ACT_NONE && !p.out_pre && p.drop_p == 0.f,
+    SFC_REQUIRE(!e.bias && !e.residual && e.aux_mode == SFC_AUX_NONE && e.act == SFC_ACT_NONE && !e.out_pre && e.drop_p == 0.f,
                 "sfc_gemm_bf16: split-K supports only a plain (optionally accumulating) epilogue");
     const size_t need = (size_t)splits * (size_t)M * (size_t)N * sizeof(float);
     SFC_REQUIRE(workspace && workspace_bytes >= need, "sfc_gemm_bf16: split-K workspace too small (%zu < %zu)", workspace_bytes, need);
-    pk.out = workspace; pk.out_fp32 = 1; pk.ld_out = N; pk.split_stride = (long long)M * N; pk.alpha = p.alpha;
+    pk.epi.out = workspace; pk.epi.out_fp32 = 1; pk.epi.ld_out = N; pk.epi.split_stride = (long long)M * N;
   } else {
     SFC_REQUIRE(!ep->accumulate, "sfc_gemm_bf16: accumulate requires split-K (splits > 1)");
   }

@@ -1,0 +1,298 @@
+// K5 — memory-bound row/column kernels (sm_100a): LayerNorm forward/backward with warp-shuffle
+// reductions, and column sums for bias gradients. These replace the ATen LayerNorm / reduction kernels
+// behind nn.LayerNorm and the bias gradients of nn.Linear in the reference encoder
+// (/root/reference/src/models/vit.py:197-206 -> torch TransformerEncoderLayer norm1/norm2; :253-254, :303).
+// Residual adds, bias, ReLU/GELU and their derivatives are fused into the GEMM epilogues (gemm.cu).
+//
+// Layout: activations are bf16 [rows, D] row-major; one warp owns one row; each lane moves 16-byte
+// vectors (8 bf16) so a warp reads/writes 512 contiguous bytes per instruction. Statistics are fp32.
+#include "common.cuh"
+#include "sfcvit.h"
+
+namespace {
+
+constexpr int kMaxVec = 8;        // per-lane 16-byte vectors: D <= 8 * 256 = 2048
+constexpr int kLnWarps = 4;       // rows per CTA
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  f[0] = ptx::bf16_lo(u.x); f[1] = ptx::bf16_hi(u.x); f[2] = ptx::bf16_lo(u.y); f[3] = ptx::bf16_hi(u.y);
+  f[4] = ptx::bf16_lo(u.z); f[5] = ptx::bf16_hi(u.z); f[6] = ptx::bf16_lo(u.w); f[7] = ptx::bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = ptx::pack_bf16(f[0], f[1]); u.y = ptx::pack_bf16(f[2], f[3]);
+  u.z = ptx::pack_bf16(f[4], f[5]); u.w = ptx::pack_bf16(f[6], f[7]);
+  return u;
+}
+
+// y = (x - mean) * rstd * gamma + beta ; saves mean/rstd (fp32) for the backward pass
+template <int NV>
+__global__ void __launch_bounds__(kLnWarps * 32)
+layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+                     const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out, long long rows, int D, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = D >> 3;                   // 16-byte vectors per row
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * D);
+  float v[NV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      unpack8(__ldg(xr + vi), v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+  }
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+  uint4* yr = reinterpret_cast<uint4*>(y + row * D);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      float g[8], b[8], o[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + vi), g);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(beta) + vi), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
+      yr[vi] = pack8(o);
+    }
+  }
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma,  xhat = (x - mean) * rstd
+// per-CTA partial sums of dgamma = sum dy * xhat and dbeta = sum dy go to part[blockIdx.x][2][D] (fp32).
+template <int NV>
+__global__ void __launch_bounds__(kLnWarps * 32)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                     const __nv_bfloat16* __restrict__ gamma, __nv_bfloat16* __restrict__ dx, float* __restrict__ part,
+                     long long rows, int D) {
+  extern __shared__ float sred[];            // [kLnWarps][2][D]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nvec = D >> 3;
+  float dg[NV][8], db[NV][8], gm[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; gm[i][j] = 0.f; }
+    if (vi < nvec) unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + vi), gm[i]);
+  }
+  for (long long row = (long long)blockIdx.x * kLnWarps + wid; row < rows; row += (long long)gridDim.x * kLnWarps) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * D);
+    const uint4* dyr = reinterpret_cast<const uint4*>(dy + row * D);
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float xh[NV][8], g[NV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        float xv[8], dv[8];
+        unpack8(__ldg(xr + vi), xv);
+        unpack8(__ldg(dyr + vi), dv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = (xv[j] - mean) * rstd;
+          g[i][j] = dv[j] * gm[i][j];
+          s1 += g[i][j];
+          s2 += g[i][j] * xh[i][j];
+          dg[i][j] += dv[j] * xh[i][j];
+          db[i][j] += dv[j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)D;
+    s2 = warp_sum(s2) / (float)D;
+    uint4* dxr = reinterpret_cast<uint4*>(dx + row * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - s1 - xh[i][j] * s2);
+        dxr[vi] = pack8(o);
+      }
+    }
+  }
+  // cross-warp reduction of the column partials
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sred[(wid * 2 + 0) * D + vi * 8 + j] = dg[i][j];
+        sred[(wid * 2 + 1) * D + vi * 8 + j] = db[i][j];
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+    const int which = c / D, col = c % D;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kLnWarps; ++w) s += sred[(w * 2 + which) * D + col];
+    part[((long long)blockIdx.x * 2 + which) * D + col] = s;
+  }
+}
+
+// column sums: x bf16 [rows, N] (ld) -> part[blockIdx.y][N] fp32. block (32 x 8): 32 lanes x 8 columns, 8 row lanes.
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long long rows, int N, float* __restrict__ part,
+                      long long rows_per_block) {
+  __shared__ float sred[8][256 + 8];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col0 = (blockIdx.x * 32 + tx) * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(r0 + rows_per_block, rows);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (col0 < N) {
+    const bool vec = (col0 + 8 <= N) && (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    for (long long r = r0 + ty; r < r1; r += 8) {
+      const __nv_bfloat16* p = x + r * ld + col0;
+      if (vec) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p)), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (col0 + j < N) acc[j] += __bfloat162float(p[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sred[ty][tx * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = threadIdx.x;          // 256 columns per block
+  const int col = blockIdx.x * 256 + c;
+  if (col < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sred[w][c];
+    part[(long long)blockIdx.y * N + col] = s;
+  }
+}
+
+// out[c] = (accumulate ? out[c] : 0) + sum_b part[b * stride + c]
+__global__ void partial_finalize_kernel(const float* __restrict__ part, int nparts, long long stride, int N, void* __restrict__ out,
+                                        int out_fp32, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  float s = 0.f;
+  for (int b = 0; b < nparts; ++b) s += part[(long long)b * stride + c];
+  if (out_fp32) {
+    float* o = reinterpret_cast<float*>(out) + c;
+    *o = accumulate ? *o + s : s;
+  } else {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + c;
+    *o = __float2bfloat16(accumulate ? __bfloat162float(*o) + s : s);
+  }
+}
+
+int ln_bwd_blocks(long long rows) {
+  long long b = sfc_ceil_div64(rows, kLnWarps);
+  const long long cap = 2ll * sfc_num_sms();
+  return (int)(b < cap ? b : cap);
+}
+
+}  // namespace
+
+extern "C" int sfc_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
+                                 long long rows, int D, float eps, cudaStream_t stream) {
+  SFC_REQUIRE(x && gamma && beta && y, "sfc_layernorm_fwd: null pointer");
+  SFC_REQUIRE(D % 8 == 0 && D >= 8 && D <= kMaxVec * 256, "sfc_layernorm_fwd: D=%d must be a multiple of 8 and <= %d", D, kMaxVec * 256);
+  if (rows == 0) return 0;
+  const unsigned grid = (unsigned)sfc_ceil_div64(rows, kLnWarps);
+  const int nv = sfc_ceil_div(D / 8, 32);
+#define LN_FWD(NV) layernorm_fwd_kernel<NV><<<grid, kLnWarps * 32, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, \
+      (const __nv_bfloat16*)beta, (__nv_bfloat16*)y, mean, rstd, rows, D, eps)
+  if (nv <= 1) LN_FWD(1); else if (nv <= 2) LN_FWD(2); else if (nv <= 3) LN_FWD(3); else if (nv <= 4) LN_FWD(4); else LN_FWD(8);
+#undef LN_FWD
+  SFC_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" size_t sfc_layernorm_bwd_scratch_bytes(long long rows, int D) {
+  return (size_t)ln_bwd_blocks(rows) * 2 * (size_t)D * sizeof(float);
+}
+
+extern "C" int sfc_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
+                                 void* dx, void* dgamma, void* dbeta, int param_fp32, int accumulate, void* scratch,
+                                 size_t scratch_bytes, long long rows, int D, cudaStream_t stream) {
+  SFC_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta, "sfc_layernorm_bwd: null pointer");
+  SFC_REQUIRE(D % 8 == 0 && D >= 8 && D <= kMaxVec * 256, "sfc_layernorm_bwd: D=%d unsupported", D);
+  SFC_REQUIRE(rows > 0, "sfc_layernorm_bwd: rows must be positive");
+  const int blocks = ln_bwd_blocks(rows);
+  SFC_REQUIRE(scratch && scratch_bytes >= (size_t)blocks * 2 * D * sizeof(float), "sfc_layernorm_bwd: scratch too small");
+  const size_t smem = (size_t)kLnWarps * 2 * D * sizeof(float);
+  const int nv = sfc_ceil_div(D / 8, 32);
+#define LN_BWD(NV)                                                                                                  \
+  do {                                                                                                              \
+    auto k = layernorm_bwd_kernel<NV>;                                                                              \
+    if (smem > 48 * 1024) SFC_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k<<<blocks, kLnWarps * 32, smem, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd,       \
+                                               (const __nv_bfloat16*)gamma, (__nv_bfloat16*)dx, (float*)scratch, rows, D); \
+  } while (0)
+  if (nv <= 1) LN_BWD(1); else if (nv <= 2) LN_BWD(2); else if (nv <= 3) LN_BWD(3); else if (nv <= 4) LN_BWD(4); else LN_BWD(8);
+#undef LN_BWD
+  SFC_LAUNCH_OK();
+  const int threads = 256;
+  // part layout: [block][2][D] -> dgamma uses offset 0, dbeta offset D, stride 2*D
+  partial_finalize_kernel<<<sfc_ceil_div(D, threads), threads, 0, stream>>>((const float*)scratch, blocks, 2ll * D, D, dgamma, param_fp32, accumulate);
+  SFC_LAUNCH_OK();
+  partial_finalize_kernel<<<sfc_ceil_div(D, threads), threads, 0, stream>>>((const float*)scratch + D, blocks, 2ll * D, D, dbeta, param_fp32, accumulate);
+  SFC_LAUNCH_OK();
+  return 0;
+}
+
+static int colsum_row_blocks(long long rows) {
+  long long b = sfc_ceil_div64(rows, 256);
+  if (b > 128) b = 128;
+  return (int)(b < 1 ? 1 : b);
+}
+
+extern "C" size_t sfc_colsum_scratch_bytes(long long rows, int N) { return (size_t)colsum_row_blocks(rows) * (size_t)N * sizeof(float); }
+
+// out[n] = sum_m x[m, n]   (bias gradients)
+extern "C" int sfc_colsum(const void* x, long long ld, long long rows, int N, void* out, int out_fp32, int accumulate, void* scratch,
+                          size_t scratch_bytes, cudaStream_t stream) {
+  SFC_REQUIRE(x && out && rows > 0 && N > 0, "sfc_colsum: bad arguments");
+  const int rb = colsum_row_blocks(rows);
+  SFC_REQUIRE(scratch && scratch_bytes >= (size_t)rb * N * sizeof(float), "sfc_colsum: scratch too small");
+  dim3 grid(sfc_ceil_div(N, 256), rb);
+  colsum_partial_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, ld, rows, N, (float*)scratch, sfc_ceil_div64(rows, rb));
+  SFC_LAUNCH_OK();
+  partial_finalize_kernel<<<sfc_ceil_div(N, 256), 256, 0, stream>>>((const float*)scratch, rb, (long long)N, N, out, out_fp32, accumulate);
+  SFC_LAUNCH_OK();
+  return 0;
+}

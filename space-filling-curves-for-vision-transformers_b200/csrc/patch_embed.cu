@@ -1,0 +1,411 @@
+// K2 — fused curve-order patch gather + patch-embedding GEMM (sm_100a).
+//
+// Replaces, for every tokenizer of the reference,
+//     rearrange 'b c (h p1)(w p2) -> b (h w)(p1 p2 c)'  ->  x[:, sfc_indices]  ->  'b (n g) d -> b n (g d)'  ->  Linear
+// (/root/reference/src/tokenizers/multiscale/multi_hilbert.py:74-84, _1D/hilbert_embedding1D.py:30-43,
+//  _2D/hilbert_embedding.py:80-91 Conv2d(k=s=p) + reorder) by ONE kernel: no permuted im2col tensor is written.
+//
+//   out[b, t, :] = W . concat_{q<g} patchvec(b, perm[t*g+q]) + bias (+ pos[t, :])
+//
+// A operand (tokens x K): gathered straight from the NCHW image by 8 producer warps (two groups that
+// alternate pipeline stages), converted fp32->bf16 in registers and written to shared memory in the
+// 128-byte-swizzled K-major layout that tcgen05.mma reads. K is ordered (q, c, p1, p2) — the image's own
+// memory order, so every gathered run is a contiguous row segment of a patch — and the weight's K axis is
+// permuted once on the host to match (never the data).
+// B operand (D x Kpad weights): TMA, K-major. Accumulators: double-buffered TMEM. Epilogue: shared with gemm.cu.
+#include "common.cuh"
+#include "gemm_epilogue.cuh"
+#include "sfcvit.h"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 512;      // warps 0-3 control, 4-7 epilogue, 8-15 gather producers
+constexpr int kEpiThreads = 128;
+constexpr int kProdWarpsPerGroup = 4;
+
+struct PatchParams {
+  const void* img;
+  const int* perm;       // [ntok * g] flat pre-patch index r*gw + c in curve order
+  int B, C, H, W, p, g, gw;
+  int ntok, K, Kpad;
+  long long M;           // B * ntok
+  int num_m_tiles, num_n_tiles, num_k_blocks;
+  int rows_per_img, tok_off;
+  EpiParams epi;         // epi.residual = position embedding rows (indexed by token), may be null
+};
+
+template <int BN, int kStages>
+struct PeSmem {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16 + 1024;
+};
+
+__device__ __forceinline__ uint4 pack8f(const float* f) {
+  uint4 u;
+  u.x = ptx::pack_bf16(f[0], f[1]); u.y = ptx::pack_bf16(f[2], f[3]);
+  u.z = ptx::pack_bf16(f[4], f[5]); u.w = ptx::pack_bf16(f[6], f[7]);
+  return u;
+}
+
+// Gathers the 64 K-elements [kb*64, kb*64+64) of token row m into its 128-byte swizzled smem row.
+template <bool VEC, bool BF16IN>
+__device__ __forceinline__ void gather_row(const PatchParams& pp, long long m, int row, int kb, uint8_t* smem_a) {
+  uint8_t* srow = smem_a + row * 128;
+  const int sw = row & 7;
+  if (m >= pp.M) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const int b = (int)(m / pp.ntok);
+  const int t = (int)(m % pp.ntok);
+  const int p = pp.p;
+  const long long plane = (long long)pp.H * pp.W;
+  if constexpr (VEC) {
+    // p % 8 == 0: each 8-element chunk is one contiguous run inside a patch row
+    uint4 raw[8][BF16IN ? 1 : 2];
+    bool valid[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k0 = kb * 64 + j * 8;
+      valid[j] = k0 < pp.K;
+      if (valid[j]) {
+        const int p2 = k0 % p;
+        const int t1 = k0 / p;
+        const int p1 = t1 % p;
+        const int t2 = t1 / p;
+        const int c = t2 % pp.C;
+        const int q = t2 / pp.C;
+        const int idx = __ldg(pp.perm + t * pp.g + q);
+        const int r = idx / pp.gw, cc = idx % pp.gw;
+        const long long off = ((long long)b * pp.C + c) * plane + (long long)(r * p + p1) * pp.W + cc * p + p2;
+        if constexpr (BF16IN) {
+          raw[j][0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(pp.img) + off));
+        } else {
+          const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(pp.img) + off);
+          raw[j][0] = __ldg(src);
+          raw[j][1] = __ldg(src + 1);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint4 o = make_uint4(0, 0, 0, 0);
+      if (valid[j]) {
+        if constexpr (BF16IN) {
+          o = raw[j][0];
+        } else {
+          o.x = ptx::pack_bf16(__uint_as_float(raw[j][0].x), __uint_as_float(raw[j][0].y));
+          o.y = ptx::pack_bf16(__uint_as_float(raw[j][0].z), __uint_as_float(raw[j][0].w));
+          o.z = ptx::pack_bf16(__uint_as_float(raw[j][1].x), __uint_as_float(raw[j][1].y));
+          o.w = ptx::pack_bf16(__uint_as_float(raw[j][1].z), __uint_as_float(raw[j][1].w));
+        }
+      }
+      *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = o;
+    }
+  } else {
+    // generic element-wise gather (any p, g): pixel-level tokenizers (p = 1) and small pre-patches
+    const int k_begin = kb * 64;
+    int p2 = k_begin % p;
+    int t1 = k_begin / p;
+    int p1 = t1 % p;
+    int t2 = t1 / p;
+    int c = t2 % pp.C;
+    int q = t2 / pp.C;
+    int idx = (k_begin < pp.K) ? __ldg(pp.perm + t * pp.g + q) : 0;
+    int r = idx / pp.gw, cc = idx % pp.gw;
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = k_begin + j * 8 + e;
+        f[e] = 0.f;
+        if (k < pp.K) {
+          const long long off = ((long long)b * pp.C + c) * plane + (long long)(r * p + p1) * pp.W + cc * p + p2;
+          if constexpr (BF16IN) f[e] = __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(pp.img) + off));
+          else f[e] = __ldg(reinterpret_cast<const float*>(pp.img) + off);
+          if (++p2 == p) {
+            p2 = 0;
+            if (++p1 == p) {
+              p1 = 0;
+              if (++c == pp.C) {
+                c = 0;
+                ++q;
+                if (k + 1 < pp.K) {
+                  idx = __ldg(pp.perm + t * pp.g + q);
+                  r = idx / pp.gw; cc = idx % pp.gw;
+                }
+              }
+            }
+          }
+        }
+      }
+      *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = pack8f(f);
+    }
+  }
+}
+
+template <int BN, int kStages, bool VEC, bool BF16IN>
+__global__ void __launch_bounds__(kThreads, 1)
+patch_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchParams pp) {
+  static_assert(kStages % 2 == 0, "producer groups alternate stages by parity");
+  using L = PeSmem<BN, kStages>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int total_tiles = pp.num_m_tiles * pp.num_n_tiles;
+
+  if (warp == 0 && ptx::elect_one()) ptx::prefetch_tmap(&tmap_w);
+  if (warp == 1 && ptx::elect_one()) {
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1 + kProdWarpsPerGroup);   // TMA expect_tx arrive + one arrive per producer warp
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tmem_full[s], 1);
+      ptx::mbar_init(&tmem_empty[s], kEpiThreads);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<2 * BN>(tmem_ptr);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer: weights =====================
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % pp.num_n_tiles;
+        for (int kb = 0; kb < pp.num_k_blocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sb = smem + stage * L::kStageBytes + L::kABytes;
+          ptx::mbar_expect_tx(&full_bar[stage], L::kBBytes);
+          ptx::tma_load_2d(&tmap_w, &full_bar[stage], sb, kb * BK, n_tile * BN);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (ptx::elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(BM, BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < pp.num_k_blocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+          const uint64_t da = umma_smem_desc_sw128(sa, 0, 1024);
+          const uint64_t db = umma_smem_desc_sw128(sb, 0, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            ptx::umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          ptx::umma_commit(&empty_bar[stage]);
+          if (kb == pp.num_k_blocks - 1) ptx::umma_commit(&tmem_full[acc]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== epilogue =====================
+    const int ewarp = warp - 4;
+    const int lane = threadIdx.x & 31;
+    const int row_in_tile = ewarp * 32 + lane;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const int n_tile = tile % pp.num_n_tiles;
+      const int m_tile = tile / pp.num_n_tiles;
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const long long m = (long long)m_tile * BM + row_in_tile;
+      const bool row_ok = m < pp.M;
+      const long long bimg = row_ok ? m / pp.ntok : 0;
+      const long long tok = row_ok ? m % pp.ntok : 0;
+      const long long out_row = bimg * pp.rows_per_img + pp.tok_off + tok;
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(ewarp * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = n_tile * BN + c * 32;
+        if (n0 >= pp.epi.N) break;
+        uint32_t r[32];
+        ptx::tmem_ld_x32(taddr + c * 32, r);
+        ptx::tmem_ld_wait();
+        if (!row_ok) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        epi_apply_store(pp.epi, v, out_row, tok, n0, 0);
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tmem_empty[acc]);
+    }
+  } else if (warp >= 8) {
+    // ===================== gather producers (2 groups x 4 warps, alternate stages) =====================
+    const int pw = warp - 8;
+    const int group = pw / kProdWarpsPerGroup;
+    const int row = (pw % kProdWarpsPerGroup) * 32 + (threadIdx.x & 31);
+    int it = 0;                                   // running k-block counter of this CTA
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / pp.num_n_tiles;
+      const long long m = (long long)m_tile * BM + row;
+      for (int kb = 0; kb < pp.num_k_blocks; ++kb, ++it) {
+        if ((it & 1) != group) continue;
+        const int stage = it % kStages;
+        const uint32_t phase = (it / kStages) & 1;
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        gather_row<VEC, BF16IN>(pp, m, row, kb, smem + stage * L::kStageBytes);
+        ptx::fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (ptx::elect_one()) ptx::mbar_arrive(&full_bar[stage]);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<2 * BN>(tmem_base);
+  }
+}
+
+// A-only gather: writes the curve-ordered im2col matrix A[M, Kpad] (bf16). Used by the backward pass
+// (weight gradient) only; the forward never materialises it.
+template <bool BF16IN>
+__global__ void __launch_bounds__(256) patch_gather_kernel(const PatchParams pp, __nv_bfloat16* __restrict__ A) {
+  const long long total = pp.M * (long long)(pp.Kpad / 8);
+  const int p = pp.p;
+  const long long plane = (long long)pp.H * pp.W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / (pp.Kpad / 8);
+    const int k0 = (int)(i % (pp.Kpad / 8)) * 8;
+    const int b = (int)(m / pp.ntok), t = (int)(m % pp.ntok);
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = k0 + e;
+      f[e] = 0.f;
+      if (k < pp.K) {
+        const int p2 = k % p, t1 = k / p, p1 = t1 % p, t2 = t1 / p, c = t2 % pp.C, q = t2 / pp.C;
+        const int idx = __ldg(pp.perm + t * pp.g + q);
+        const int r = idx / pp.gw, cc = idx % pp.gw;
+        const long long off = ((long long)b * pp.C + c) * plane + (long long)(r * p + p1) * pp.W + cc * p + p2;
+        if constexpr (BF16IN) f[e] = __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(pp.img) + off));
+        else f[e] = __ldg(reinterpret_cast<const float*>(pp.img) + off);
+      }
+    }
+    *reinterpret_cast<uint4*>(A + m * pp.Kpad + k0) = pack8f(f);
+  }
+}
+
+int fill_params(PatchParams& pp, const void* img, int img_bf16, int B, int C, int H, int W, int p, int g, const int32_t* perm,
+                int D) {
+  SFC_REQUIRE(img && perm, "patch_embed: null pointer");
+  SFC_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && p > 0 && g > 0 && D > 0, "patch_embed: bad shape");
+  SFC_REQUIRE(H % p == 0 && W % p == 0, "patch_embed: image %dx%d not divisible by pre-patch size %d", H, W, p);
+  const int gh = H / p, gw = W / p;
+  SFC_REQUIRE((gh * gw) % g == 0, "patch_embed: %d pre-patches not divisible by group size %d", gh * gw, g);
+  pp.img = img; pp.perm = perm;
+  pp.B = B; pp.C = C; pp.H = H; pp.W = W; pp.p = p; pp.g = g; pp.gw = gw;
+  pp.ntok = gh * gw / g;
+  pp.K = g * C * p * p;
+  pp.Kpad = sfc_ceil_div(pp.K, BK) * BK;
+  pp.M = (long long)B * pp.ntok;
+  pp.num_m_tiles = (int)sfc_ceil_div64(pp.M, BM);
+  pp.num_k_blocks = pp.Kpad / BK;
+  pp.rows_per_img = pp.ntok; pp.tok_off = 0;
+  (void)img_bf16;
+  return 0;
+}
+
+template <int BN, int kStages, bool VEC, bool BF16IN>
+int launch_pe(const CUtensorMap& tw, const PatchParams& pp, cudaStream_t stream) {
+  using L = PeSmem<BN, kStages>;
+  auto kern = patch_embed_fwd_kernel<BN, kStages, VEC, BF16IN>;
+  static bool configured = false;
+  if (!configured) {
+    SFC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  const int total_tiles = pp.num_m_tiles * pp.num_n_tiles;
+  const int grid = total_tiles < sfc_num_sms() ? total_tiles : sfc_num_sms();
+  kern<<<grid, kThreads, L::kTotal, stream>>>(tw, pp);
+  SFC_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int sfc_patch_embed_kpad(int C, int p, int g) { return sfc_ceil_div(g * C * p * p, BK) * BK; }
+
+extern "C" int sfc_patch_embed_fwd(const void* img, int img_bf16, int B, int C, int H, int W, int p, int g, const int32_t* perm,
+                                   const void* Wk, const void* bias, const void* pos, long long ld_pos, void* out,
+                                   long long ld_out, int D, int rows_per_img, int tok_off, cudaStream_t stream) {
+  PatchParams pp;
+  if (int e = fill_params(pp, img, img_bf16, B, C, H, W, p, g, perm, D)) return e;
+  SFC_REQUIRE(Wk && out, "sfc_patch_embed_fwd: null pointer");
+  SFC_REQUIRE(rows_per_img >= pp.ntok + tok_off && tok_off >= 0, "sfc_patch_embed_fwd: rows_per_img/tok_off inconsistent");
+  pp.rows_per_img = rows_per_img; pp.tok_off = tok_off;
+  const int BN = (D > 128) ? 256 : 128;
+  pp.num_n_tiles = sfc_ceil_div(D, BN);
+  EpiParams& e = pp.epi;
+  e.N = D; e.bias = (const __nv_bfloat16*)bias; e.residual = (const __nv_bfloat16*)pos; e.aux = nullptr;
+  e.out = out; e.out_pre = nullptr; e.ld_out = ld_out; e.ld_res = ld_pos; e.ld_aux = 0; e.split_stride = 0;
+  e.alpha = 1.0f; e.act = SFC_ACT_NONE; e.aux_mode = SFC_AUX_NONE; e.out_fp32 = 0; e.drop_p = 0.f; e.drop_seed = 0;
+  CUtensorMap tw;
+  if (int err = sfc_make_tmap_2d(&tw, Wk, 2, (uint64_t)pp.Kpad, (uint64_t)D, (uint64_t)pp.Kpad * 2, BK, (uint32_t)BN, true)) return err;
+  const bool vec = (p % 8 == 0) && (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0) && (((long long)H * W) % 8 == 0);
+#define PE_DISPATCH(BN_, ST_)                                                                   \
+  do {                                                                                          \
+    if (vec && img_bf16) return launch_pe<BN_, ST_, true, true>(tw, pp, stream);                \
+    if (vec && !img_bf16) return launch_pe<BN_, ST_, true, false>(tw, pp, stream);              \
+    if (!vec && img_bf16) return launch_pe<BN_, ST_, false, true>(tw, pp, stream);              \
+    return launch_pe<BN_, ST_, false, false>(tw, pp, stream);                                   \
+  } while (0)
+  if (BN == 256) PE_DISPATCH(256, 4); else PE_DISPATCH(128, 6);
+#undef PE_DISPATCH
+}
+
+// A[M, Kpad] = curve-ordered im2col (bf16), K order (q, c, p1, p2), zero padded to Kpad. Backward only.
+extern "C" int sfc_patch_gather(const void* img, int img_bf16, int B, int C, int H, int W, int p, int g, const int32_t* perm,
+                                void* A, cudaStream_t stream) {
+  PatchParams pp;
+  if (int e = fill_params(pp, img, img_bf16, B, C, H, W, p, g, perm, 8)) return e;
+  SFC_REQUIRE(A, "sfc_patch_gather: null output");
+  const long long total = pp.M * (long long)(pp.Kpad / 8);
+  long long blocks = sfc_ceil_div64(total, 256);
+  const long long cap = 16ll * sfc_num_sms();
+  if (blocks > cap) blocks = cap;
+  if (img_bf16) patch_gather_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(pp, (__nv_bfloat16*)A);
+  else patch_gather_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(pp, (__nv_bfloat16*)A);
+  SFC_LAUNCH_OK();
+  return 0;
+}

@@ -33,6 +33,19 @@ SIGNATURES = {
     "sfc_curve_perm": (_i, [_i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "sfc_gemm_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "sfc_gemm_suggest_splits": (_i, [_i, _i, _i]),
+    "sfc_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _vp]),
+    "sfc_layernorm_bwd_scratch_bytes": (_sz, [_ll, _i]),
+    "sfc_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _ll, _i, _vp]),
+    "sfc_colsum_scratch_bytes": (_sz, [_ll, _i]),
+    "sfc_colsum": (_i, [_vp, _ll, _ll, _i, _vp, _i, _i, _vp, _sz, _vp]),
+    "sfc_patch_embed_kpad": (_i, [_i, _i, _i]),
+    "sfc_patch_embed_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _vp]),
+    "sfc_patch_gather": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "sfc_attn_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, ctypes.c_ulonglong, _vp]),
+    "sfc_attn_bwd_scratch_bytes": (_sz, [_i, _i, _i]),
+    "sfc_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _f, _f, ctypes.c_ulonglong, _vp]),
+    "sfc_grad_sumsq": (_i, [_vp, _i, _ll, _vp, _vp]),
+    "sfc_adamw_step": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _f, _f, _f, _f, _f, _i, _f, _f, _vp, _vp]),
     "sfc_gemm_bf16": (_i, [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, ctypes.POINTER(SfcGemmEpilogue), _vp, _sz, _i, _vp]),
 }
 
