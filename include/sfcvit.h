@@ -84,6 +84,8 @@ size_t sfc_layernorm_bwd_scratch_bytes(long long rows, int D);
 int sfc_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma, void* dx,
                       void* dgamma, void* dbeta, int param_fp32, int accumulate, void* scratch, size_t scratch_bytes,
                       long long rows, int D, sfc_stream_t stream);
+/* out = alpha * dy * f'(aux): aux_mode SFC_AUX_RELU_MASK (aux > 0) or SFC_AUX_GELU_GRAD (aux = pre-activation); bf16, n % 8 == 0 */
+int sfc_act_bwd(const void* dy, const void* aux, void* out, long long n, int aux_mode, float alpha, sfc_stream_t stream);
 size_t sfc_colsum_scratch_bytes(long long rows, int N);
 int sfc_colsum(const void* x, long long ld, long long rows, int N, void* out, int out_fp32, int accumulate,
                void* scratch, size_t scratch_bytes, sfc_stream_t stream);
@@ -91,17 +93,17 @@ int sfc_colsum(const void* x, long long ld, long long rows, int N, void* out, in
 /* ---- K2: fused curve-order patch gather + patch-embedding GEMM
  *      (tokenizers: multiscale/multi_hilbert.py:74-84 SFCEmbedding1D.forward and its morton/peano/moore copies,
  *       _1D/hilbert_embedding1D.py:30-43, _2D/hilbert_embedding.py:80-91, _2D/zigzag_embedding.py:24-30) ----
- * img: NCHW fp32 (img_bf16 = 0) or bf16 (1). p = pre-patch size, g = group size, perm = int32 [(H/p)*(W/p)] flat
- * pre-patch indices r*(W/p)+c in curve order. Wk: bf16 [D, Kpad], K axis ordered (q, c, p1, p2) and zero padded to
+ * img: NCHW fp32 (img_bf16 = 0) or bf16 (1). p = pre-patch size, g = group size, perm = int32 [n_perm] flat
+ * pre-patch indices r*(W/p)+c in curve order (n_perm <= (H/p)*(W/p), tokens per image = n_perm / g). Wk: bf16 [D, Kpad], K axis ordered (q, c, p1, p2) and zero padded to
  * Kpad = sfc_patch_embed_kpad(C,p,g). out row of token t of image b: b*rows_per_img + tok_off + t, row stride ld_out
  * (the caller may pre-offset `out` to write a column slice of a wider matrix). pos: optional bf16 [ntok, ld_pos]. */
 int sfc_patch_embed_kpad(int C, int p, int g);
 int sfc_patch_embed_fwd(const void* img, int img_bf16, int B, int C, int H, int W, int p, int g, const int32_t* perm,
-                        const void* Wk, const void* bias, const void* pos, long long ld_pos, void* out, long long ld_out,
+                        int n_perm, const void* Wk, const void* bias, const void* pos, long long ld_pos, void* out, long long ld_out,
                         int D, int rows_per_img, int tok_off, sfc_stream_t stream);
 /* backward helper: A[M, Kpad] bf16 = curve-ordered im2col (same K order); dWk = dOut^T . A via sfc_gemm_bf16 */
 int sfc_patch_gather(const void* img, int img_bf16, int B, int C, int H, int W, int p, int g, const int32_t* perm,
-                     void* A, sfc_stream_t stream);
+                     int n_perm, void* A, sfc_stream_t stream);
 
 /* ---- K4: flash attention forward / backward, head_dim 64, non-causal
  *      (F.scaled_dot_product_attention inside nn.MultiheadAttention: vit.py:197-206 -> torch

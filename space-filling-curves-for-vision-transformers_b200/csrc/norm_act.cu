@@ -219,6 +219,26 @@ __global__ void partial_finalize_kernel(const float* __restrict__ part, int npar
   }
 }
 
+// out = dy * f'(aux): relu mask (aux > 0) or exact-GELU derivative (aux = pre-activation); 8 elements per thread
+__global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ aux,
+                                                      __nv_bfloat16* __restrict__ out, long long nvec, int mode, float alpha) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float d[8], a[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy) + i), d);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(aux) + i), a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (mode == SFC_AUX_RELU_MASK) o[j] = a[j] > 0.f ? d[j] * alpha : 0.f;
+      else {
+        const float cdf = 0.5f * (1.0f + erff(a[j] * 0.70710678118654752f));
+        const float pdf = 0.3989422804014327f * __expf(-0.5f * a[j] * a[j]);
+        o[j] = d[j] * alpha * (cdf + a[j] * pdf);
+      }
+    }
+    reinterpret_cast<uint4*>(out)[i] = pack8(o);
+  }
+}
+
 int ln_bwd_blocks(long long rows) {
   long long b = sfc_ceil_div64(rows, kLnWarps);
   const long long cap = 2ll * sfc_num_sms();
@@ -293,6 +313,19 @@ extern "C" int sfc_colsum(const void* x, long long ld, long long rows, int N, vo
   colsum_partial_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, ld, rows, N, (float*)scratch, sfc_ceil_div64(rows, rb));
   SFC_LAUNCH_OK();
   partial_finalize_kernel<<<sfc_ceil_div(N, 256), 256, 0, stream>>>((const float*)scratch, rb, (long long)N, N, out, out_fp32, accumulate);
+  SFC_LAUNCH_OK();
+  return 0;
+}
+
+// out[i] = alpha * dy[i] * f'(aux[i])   (n % 8 == 0, contiguous bf16)
+extern "C" int sfc_act_bwd(const void* dy, const void* aux, void* out, long long n, int aux_mode, float alpha, cudaStream_t stream) {
+  SFC_REQUIRE(dy && aux && out && n >= 0 && n % 8 == 0, "sfc_act_bwd: bad arguments (n must be a multiple of 8)");
+  SFC_REQUIRE(aux_mode == SFC_AUX_RELU_MASK || aux_mode == SFC_AUX_GELU_GRAD, "sfc_act_bwd: bad mode");
+  if (n == 0) return 0;
+  long long blocks = sfc_ceil_div64(n / 8, 256);
+  const long long cap = 16ll * sfc_num_sms();
+  if (blocks > cap) blocks = cap;
+  act_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)aux, (__nv_bfloat16*)out, n / 8, aux_mode, alpha);
   SFC_LAUNCH_OK();
   return 0;
 }

@@ -327,15 +327,15 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const PatchParams pp,
 }
 
 int fill_params(PatchParams& pp, const void* img, int img_bf16, int B, int C, int H, int W, int p, int g, const int32_t* perm,
-                int D) {
+                int n_perm, int D) {
   SFC_REQUIRE(img && perm, "patch_embed: null pointer");
   SFC_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && p > 0 && g > 0 && D > 0, "patch_embed: bad shape");
   SFC_REQUIRE(H % p == 0 && W % p == 0, "patch_embed: image %dx%d not divisible by pre-patch size %d", H, W, p);
   const int gh = H / p, gw = W / p;
-  SFC_REQUIRE((gh * gw) % g == 0, "patch_embed: %d pre-patches not divisible by group size %d", gh * gw, g);
+  SFC_REQUIRE(n_perm > 0 && n_perm <= gh * gw && n_perm % g == 0, "patch_embed: permutation length %d must be in (0, %d] and divisible by group size %d", n_perm, gh * gw, g);
   pp.img = img; pp.perm = perm;
   pp.B = B; pp.C = C; pp.H = H; pp.W = W; pp.p = p; pp.g = g; pp.gw = gw;
-  pp.ntok = gh * gw / g;
+  pp.ntok = n_perm / g;
   pp.K = g * C * p * p;
   pp.Kpad = sfc_ceil_div(pp.K, BK) * BK;
   pp.M = (long long)B * pp.ntok;
@@ -367,10 +367,10 @@ int launch_pe(const CUtensorMap& tw, const PatchParams& pp, cudaStream_t stream)
 extern "C" int sfc_patch_embed_kpad(int C, int p, int g) { return sfc_ceil_div(g * C * p * p, BK) * BK; }
 
 extern "C" int sfc_patch_embed_fwd(const void* img, int img_bf16, int B, int C, int H, int W, int p, int g, const int32_t* perm,
-                                   const void* Wk, const void* bias, const void* pos, long long ld_pos, void* out,
+                                   int n_perm, const void* Wk, const void* bias, const void* pos, long long ld_pos, void* out,
                                    long long ld_out, int D, int rows_per_img, int tok_off, cudaStream_t stream) {
   PatchParams pp;
-  if (int e = fill_params(pp, img, img_bf16, B, C, H, W, p, g, perm, D)) return e;
+  if (int e = fill_params(pp, img, img_bf16, B, C, H, W, p, g, perm, n_perm, D)) return e;
   SFC_REQUIRE(Wk && out, "sfc_patch_embed_fwd: null pointer");
   SFC_REQUIRE(rows_per_img >= pp.ntok + tok_off && tok_off >= 0, "sfc_patch_embed_fwd: rows_per_img/tok_off inconsistent");
   pp.rows_per_img = rows_per_img; pp.tok_off = tok_off;
@@ -396,9 +396,9 @@ extern "C" int sfc_patch_embed_fwd(const void* img, int img_bf16, int B, int C, 
 
 // A[M, Kpad] = curve-ordered im2col (bf16), K order (q, c, p1, p2), zero padded to Kpad. Backward only.
 extern "C" int sfc_patch_gather(const void* img, int img_bf16, int B, int C, int H, int W, int p, int g, const int32_t* perm,
-                                void* A, cudaStream_t stream) {
+                                int n_perm, void* A, cudaStream_t stream) {
   PatchParams pp;
-  if (int e = fill_params(pp, img, img_bf16, B, C, H, W, p, g, perm, 8)) return e;
+  if (int e = fill_params(pp, img, img_bf16, B, C, H, W, p, g, perm, n_perm, 8)) return e;
   SFC_REQUIRE(A, "sfc_patch_gather: null output");
   const long long total = pp.M * (long long)(pp.Kpad / 8);
   long long blocks = sfc_ceil_div64(total, 256);

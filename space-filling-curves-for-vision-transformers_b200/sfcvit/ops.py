@@ -112,3 +112,167 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=None, au
                                ctypes.byref(ep), _ptr(ws), ws_bytes, int(splits), _stream())
     _lib.check(rc, "sfc_gemm_bf16")
     return (out, pre) if want_pre else out
+
+
+# ------------------------------------------------------------------ K5: LayerNorm / column sums
+def layernorm_fwd(x, gamma, beta, eps=1e-5, want_stats=True):
+    """x: bf16 [rows, D] contiguous. Returns (y, mean, rstd)."""
+    lib = _lib.load()
+    _require_cuda(x, gamma, beta)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and gamma.dtype == torch.bfloat16 and beta.dtype == torch.bfloat16
+    D = x.shape[-1]
+    rows = x.numel() // D
+    y = torch.empty_like(x)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device) if want_stats else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if want_stats else None
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sfc_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean), _ptr(rstd), rows, D,
+                                         float(eps), _stream()), "sfc_layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, param_dtype=torch.bfloat16):
+    """Returns (dx bf16, dgamma, dbeta) with dgamma/dbeta in param_dtype (bf16 or fp32)."""
+    lib = _lib.load()
+    _require_cuda(dy, x, mean, rstd, gamma)
+    assert dy.dtype == torch.bfloat16 and dy.is_contiguous() and x.is_contiguous()
+    D = x.shape[-1]
+    rows = x.numel() // D
+    dx = torch.empty_like(x)
+    dgamma = torch.empty(D, dtype=param_dtype, device=x.device)
+    dbeta = torch.empty(D, dtype=param_dtype, device=x.device)
+    nbytes = lib.sfc_layernorm_bwd_scratch_bytes(rows, D)
+    scratch = _workspace(nbytes, x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sfc_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dx), _ptr(dgamma),
+                                         _ptr(dbeta), 1 if param_dtype == torch.float32 else 0, 0, _ptr(scratch), nbytes,
+                                         rows, D, _stream()), "sfc_layernorm_bwd")
+    return dx, dgamma, dbeta
+
+
+def colsum(x, out_dtype=torch.bfloat16):
+    """x: bf16 [rows, N] (row stride arbitrary, inner contiguous) -> [N] column sums (bias gradient)."""
+    lib = _lib.load()
+    _require_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    rows, N = x.shape
+    out = torch.empty(N, dtype=out_dtype, device=x.device)
+    nbytes = lib.sfc_colsum_scratch_bytes(rows, N)
+    scratch = _workspace(nbytes, x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sfc_colsum(_ptr(x), x.stride(0), rows, N, _ptr(out), 1 if out_dtype == torch.float32 else 0, 0,
+                                  _ptr(scratch), nbytes, _stream()), "sfc_colsum")
+    return out
+
+
+# ------------------------------------------------------------------ K2: fused patch embed
+def patch_embed_kpad(C, p, g):
+    return _lib.load().sfc_patch_embed_kpad(C, p, g)
+
+
+def patch_embed_fwd(img, perm, wk, bias, p, g, *, pos=None, out=None, col_off=0, rows_per_img=None, tok_off=0):
+    """img: [B,C,H,W] fp32/bf16 contiguous; perm int32 [(H/p)*(W/p)]; wk bf16 [D, Kpad] (K order q,c,p1,p2).
+    Writes out[b, tok_off + t, col_off : col_off + D]; returns out ([B, rows_per_img, ld] bf16)."""
+    lib = _lib.load()
+    _require_cuda(img, perm, wk, bias, pos, out)
+    assert img.dim() == 4 and img.is_contiguous() and img.dtype in (torch.float32, torch.bfloat16)
+    assert perm.dtype == torch.int32 and wk.dtype == torch.bfloat16 and wk.is_contiguous()
+    B, C, H, W = img.shape
+    D, Kpad = wk.shape
+    assert Kpad == lib.sfc_patch_embed_kpad(C, p, g)
+    ntok = perm.numel() // g
+    if rows_per_img is None:
+        rows_per_img = ntok + tok_off
+    if out is None:
+        out = torch.empty((B, rows_per_img, D), dtype=torch.bfloat16, device=img.device)
+    assert out.dtype == torch.bfloat16 and out.stride(-1) == 1 and out.shape[0] == B and out.shape[1] == rows_per_img
+    assert out.stride(0) == rows_per_img * out.stride(1)
+    out_ptr = ctypes.c_void_p(out.data_ptr() + 2 * col_off)
+    with torch.cuda.device(img.device):
+        rc = lib.sfc_patch_embed_fwd(_ptr(img), 1 if img.dtype == torch.bfloat16 else 0, B, C, H, W, p, g, _ptr(perm),
+                                     perm.numel(), _ptr(wk), _ptr(bias), _ptr(pos), pos.stride(0) if pos is not None else 0, out_ptr,
+                                     out.stride(1), D, rows_per_img, tok_off, _stream())
+    _lib.check(rc, "sfc_patch_embed_fwd")
+    return out
+
+
+def patch_gather(img, perm, p, g):
+    """Curve-ordered im2col A[B*ntok, Kpad] bf16 (backward helper)."""
+    lib = _lib.load()
+    _require_cuda(img, perm)
+    B, C, H, W = img.shape
+    Kpad = lib.sfc_patch_embed_kpad(C, p, g)
+    ntok = perm.numel() // g
+    A = torch.empty((B * ntok, Kpad), dtype=torch.bfloat16, device=img.device)
+    with torch.cuda.device(img.device):
+        _lib.check(lib.sfc_patch_gather(_ptr(img), 1 if img.dtype == torch.bfloat16 else 0, B, C, H, W, p, g, _ptr(perm),
+                                        perm.numel(), _ptr(A), _stream()), "sfc_patch_gather")
+    return A
+
+
+# ------------------------------------------------------------------ K4: attention
+def attn_fwd(qkv, B, H, N, *, scale=None, drop_p=0.0, drop_seed=0):
+    """qkv bf16 [B*N, 3D] contiguous -> (out bf16 [B*N, D], lse fp32 [B, H, N])."""
+    lib = _lib.load()
+    _require_cuda(qkv)
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.dim() == 2
+    D = qkv.shape[1] // 3
+    assert qkv.shape[0] == B * N
+    if scale is None:
+        scale = (D // H) ** -0.5
+    out = torch.empty((B * N, D), dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        _lib.check(lib.sfc_attn_fwd(_ptr(qkv), _ptr(out), _ptr(lse), B, H, N, D, float(scale), float(drop_p),
+                                    int(drop_seed) & 0xFFFFFFFFFFFFFFFF, _stream()), "sfc_attn_fwd")
+    return out, lse
+
+
+def attn_bwd(qkv, out, dout, lse, B, H, N, *, scale=None, drop_p=0.0, drop_seed=0):
+    lib = _lib.load()
+    _require_cuda(qkv, out, dout, lse)
+    assert dout.dtype == torch.bfloat16 and dout.is_contiguous() and out.is_contiguous() and qkv.is_contiguous()
+    D = qkv.shape[1] // 3
+    if scale is None:
+        scale = (D // H) ** -0.5
+    dqkv = torch.empty_like(qkv)
+    nbytes = lib.sfc_attn_bwd_scratch_bytes(B, N, D)
+    scratch = _workspace(nbytes, qkv.device)
+    with torch.cuda.device(qkv.device):
+        _lib.check(lib.sfc_attn_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), _ptr(scratch), nbytes, B, H, N,
+                                    D, float(scale), float(drop_p), int(drop_seed) & 0xFFFFFFFFFFFFFFFF, _stream()),
+                   "sfc_attn_bwd")
+    return dqkv
+
+
+# ------------------------------------------------------------------ K6: optimizer
+def grad_sumsq(g, accum):
+    lib = _lib.load()
+    _require_cuda(g, accum)
+    assert g.is_contiguous() and accum.dtype == torch.float32
+    with torch.cuda.device(g.device):
+        _lib.check(lib.sfc_grad_sumsq(_ptr(g), 1 if g.dtype == torch.float32 else 0, g.numel(), _ptr(accum), _stream()),
+                   "sfc_grad_sumsq")
+
+
+def adamw_step(p, g, m, v, *, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, max_norm=0.0, stats=None):
+    lib = _lib.load()
+    _require_cuda(p, g, m, v, stats)
+    assert p.is_contiguous() and g.is_contiguous() and m.is_contiguous() and v.is_contiguous()
+    assert p.dtype == g.dtype and m.dtype == v.dtype
+    with torch.cuda.device(p.device):
+        _lib.check(lib.sfc_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), 1 if p.dtype == torch.float32 else 0,
+                                      1 if m.dtype == torch.float32 else 0, float(lr), float(beta1), float(beta2), float(eps),
+                                      float(weight_decay), int(step), float(grad_scale), float(max_norm), _ptr(stats),
+                                      _stream()), "sfc_adamw_step")
+
+
+def act_bwd(dy, aux, mode, alpha=1.0):
+    """dy * f'(aux) (bf16, contiguous, numel % 8 == 0)."""
+    lib = _lib.load()
+    _require_cuda(dy, aux)
+    assert dy.is_contiguous() and aux.is_contiguous() and dy.dtype == torch.bfloat16 and aux.dtype == torch.bfloat16
+    out = torch.empty_like(dy)
+    with torch.cuda.device(dy.device):
+        _lib.check(lib.sfc_act_bwd(_ptr(dy), _ptr(aux), _ptr(out), dy.numel(), int(mode), float(alpha), _stream()), "sfc_act_bwd")
+    return out

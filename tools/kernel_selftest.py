@@ -1,0 +1,151 @@
+"""Stand-alone checks of K2/K4/K5/K6 against torch fp32 math on the same bf16 inputs (one check per process).
+usage: python tools/kernel_selftest.py <check> [args...]"""
+import json
+import math
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "space-filling-curves-for-vision-transformers_b200"))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from sfcvit import ops  # noqa: E402
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
+
+
+def check_attn(B=2, H=3, N=196, drop_p=0.0, bwd=True, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    D = H * 64
+    qkv = (torch.randn(B * N, 3 * D, generator=g, device="cuda")).bfloat16()
+    out, lse = ops.attn_fwd(qkv, B, H, N, drop_p=drop_p, drop_seed=123)
+    q, k, v = [t.reshape(B, N, H, 64).permute(0, 2, 1, 3).float().requires_grad_(True) for t in qkv.float().split(D, dim=1)]
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    ref_lse = torch.logsumexp(s, dim=-1)
+    pr = torch.softmax(s, dim=-1)
+    res = dict(check="attn", B=B, H=H, N=N, drop_p=drop_p)
+    res["lse_max_err"] = (lse - ref_lse).abs().max().item()
+    if drop_p == 0.0:
+        ref = (pr @ v).permute(0, 2, 1, 3).reshape(B * N, D)
+        res["out_rel"] = rel(out, ref)
+        ok = res["out_rel"] < 1e-2 and res["lse_max_err"] < 2e-3
+        if bwd:
+            dout = torch.randn(B * N, D, generator=g, device="cuda").bfloat16()
+            dqkv = ops.attn_bwd(qkv, out, dout, lse, B, H, N)
+            ref.backward(dout.float())
+            ref_d = torch.cat([t.grad.permute(0, 2, 1, 3).reshape(B * N, D) for t in (q, k, v)], dim=1)
+            res["dq_rel"] = rel(dqkv[:, :D], ref_d[:, :D])
+            res["dk_rel"] = rel(dqkv[:, D:2 * D], ref_d[:, D:2 * D])
+            res["dv_rel"] = rel(dqkv[:, 2 * D:], ref_d[:, 2 * D:])
+            ok = ok and max(res["dq_rel"], res["dk_rel"], res["dv_rel"]) < 2e-2
+    else:
+        # dropout: statistical check (mean preserved) + fwd/bwd mask consistency via finite differences of a linear loss
+        ref = (pr @ v).permute(0, 2, 1, 3).reshape(B * N, D)
+        res["out_rel_vs_nodrop"] = rel(out, ref)
+        out2, _ = ops.attn_fwd(qkv, B, H, N, drop_p=drop_p, drop_seed=123)
+        res["deterministic"] = bool(torch.equal(out, out2))
+        # directional derivative check along v: out is linear in v for a fixed mask
+        dout = torch.randn(B * N, D, generator=g, device="cuda").bfloat16()
+        dqkv = ops.attn_bwd(qkv, out, dout, lse, B, H, N, drop_p=drop_p, drop_seed=123)
+        dv_dir = torch.randn(B * N, D, generator=g, device="cuda").bfloat16()
+        qkv2 = qkv.clone()
+        qkv2[:, 2 * D:] = dv_dir
+        qkv2[:, :2 * D] = qkv[:, :2 * D]
+        out_dir, _ = ops.attn_fwd(qkv2, B, H, N, drop_p=drop_p, drop_seed=123)   # = P_drop @ dv_dir (same q,k -> same P, mask)
+        lhs = (out_dir.float() * dout.float()).sum().item()
+        rhs = (dqkv[:, 2 * D:].float() * dv_dir.float()).sum().item()
+        res["dv_adjoint_rel"] = abs(lhs - rhs) / max(abs(lhs), 1e-6)
+        ok = res["deterministic"] and res["dv_adjoint_rel"] < 3e-2 and 0.05 < res["out_rel_vs_nodrop"] < 2.0
+    res["ok"] = bool(ok)
+    return res
+
+
+def check_patch(B=3, C=3, HW=224, p=16, g=1, D=768, curve="hilbert", dtype="fp32", seed=0):
+    import numpy as np
+    from oracle import curves as oc
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    img = torch.randn(B, C, HW, HW, generator=gen, device="cuda")
+    if dtype == "bf16":
+        img = img.bfloat16()
+    n = HW // p
+    perm_ref = torch.from_numpy(oc.flat_perm(curve, n, n)).cuda()
+    perm, _ = ops.curve_perm(curve, n, n)
+    assert torch.equal(perm.long(), perm_ref)
+    K = g * p * p * C
+    W = (torch.randn(D, K, generator=gen, device="cuda") * 0.05).bfloat16()     # reference layout: (g, p1, p2, c)
+    bias = torch.randn(D, generator=gen, device="cuda").bfloat16()
+    # reference math (multi_hilbert.py:74-84) in fp32 on the bf16-rounded operands
+    x = img.float().bfloat16().float()
+    xr = x.reshape(B, C, n, p, n, p).permute(0, 2, 4, 3, 5, 1).reshape(B, n * n, p * p * C)
+    xr = xr[:, perm_ref].reshape(B, n * n // g, g * p * p * C)
+    ref = xr @ W.float().t() + bias.float()
+    # kernel layout: K order (q, c, p1, p2), zero padded
+    Kpad = ops.patch_embed_kpad(C, p, g)
+    wk = torch.zeros(D, Kpad, dtype=torch.bfloat16, device="cuda")
+    wk[:, :K] = W.reshape(D, g, p, p, C).permute(0, 1, 4, 2, 3).reshape(D, K)
+    out = ops.patch_embed_fwd(img, perm, wk, bias, p, g)
+    A = ops.patch_gather(img, perm, p, g)
+    A_ref = x.reshape(B, C, n, p, n, p).permute(0, 2, 4, 1, 3, 5).reshape(B, n * n, C * p * p)[:, perm_ref].reshape(B * (n * n // g), K)
+    res = dict(check="patch", B=B, HW=HW, p=p, g=g, D=D, curve=curve, dtype=dtype)
+    res["out_rel"] = rel(out.reshape(-1, D), ref.reshape(-1, D))
+    res["gather_exact"] = bool(torch.equal(A[:, :K].float(), A_ref.bfloat16().float())) and bool((A[:, K:] == 0).all())
+    res["ok"] = bool(res["out_rel"] < 6e-3 and res["gather_exact"])
+    return res
+
+
+def check_ln(rows=1000, D=768, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = (torch.randn(rows, D, generator=g, device="cuda") * 2 + 0.5).bfloat16()
+    gamma = (1 + 0.1 * torch.randn(D, generator=g, device="cuda")).bfloat16()
+    beta = (0.1 * torch.randn(D, generator=g, device="cuda")).bfloat16()
+    dy = torch.randn(rows, D, generator=g, device="cuda").bfloat16()
+    y, mean, rstd = ops.layernorm_fwd(x, gamma, beta)
+    xf = x.float().requires_grad_(True)
+    gf = gamma.float().requires_grad_(True)
+    bf = beta.float().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xf, (D,), gf, bf, 1e-5)
+    ref.backward(dy.float())
+    dx, dg, db = ops.layernorm_bwd(dy, x, mean, rstd, gamma, torch.float32)
+    cs = ops.colsum(dy, torch.float32)
+    res = dict(check="ln", rows=rows, D=D, y_rel=rel(y, ref), dx_rel=rel(dx, xf.grad), dg_rel=rel(dg, gf.grad), db_rel=rel(db, bf.grad),
+               colsum_rel=rel(cs, dy.float().sum(0)))
+    res["ok"] = bool(res["y_rel"] < 5e-3 and res["dx_rel"] < 6e-3 and res["dg_rel"] < 1e-3 and res["db_rel"] < 1e-3 and res["colsum_rel"] < 1e-4)
+    return res
+
+
+def check_adamw(n=100003, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    p0 = torch.randn(n, generator=g, device="cuda")
+    grads = [torch.randn(n, generator=g, device="cuda") * 3 for _ in range(3)]
+    pref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([pref], lr=3e-3, weight_decay=0.05)
+    p = p0.clone(); m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    stats = torch.zeros(1, device="cuda")
+    for step, gr in enumerate(grads, 1):
+        pref.grad = gr.clone()
+        torch.nn.utils.clip_grad_norm_([pref], 1.0)
+        opt.step()
+        stats.zero_()
+        ops.grad_sumsq(gr, stats)
+        ops.adamw_step(p, gr, m, v, lr=3e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.05, step=step, max_norm=1.0, stats=stats)
+    res = dict(check="adamw", n=n, p_rel=rel(p, pref.detach()), max_abs=(p - pref.detach()).abs().max().item())
+    res["ok"] = bool(res["p_rel"] < 1e-5)
+    return res
+
+
+if __name__ == "__main__":
+    name = sys.argv[1]
+    args = [a for a in sys.argv[2:]]
+
+    def conv(a):
+        try:
+            return int(a)
+        except ValueError:
+            try:
+                return float(a)
+            except ValueError:
+                return a
+    fn = {"attn": check_attn, "patch": check_patch, "ln": check_ln, "adamw": check_adamw}[name]
+    print(json.dumps(fn(*[conv(a) for a in args])))
