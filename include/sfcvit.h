@@ -84,8 +84,11 @@ size_t sfc_layernorm_bwd_scratch_bytes(long long rows, int D);
 int sfc_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma, void* dx,
                       void* dgamma, void* dbeta, int param_fp32, int accumulate, void* scratch, size_t scratch_bytes,
                       long long rows, int D, sfc_stream_t stream);
-/* out = alpha * dy * f'(aux): aux_mode SFC_AUX_RELU_MASK (aux > 0) or SFC_AUX_GELU_GRAD (aux = pre-activation); bf16, n % 8 == 0 */
-int sfc_act_bwd(const void* dy, const void* aux, void* out, long long n, int aux_mode, float alpha, sfc_stream_t stream);
+/* out = alpha * dy * f'(aux) * keep(seed, i) / (1 - drop_p): aux_mode SFC_AUX_NONE, SFC_AUX_RELU_MASK (aux > 0) or
+ * SFC_AUX_GELU_GRAD (aux = pre-activation); the dropout mask is the one the GEMM epilogue drew for a contiguous
+ * [M, N] output with the same seed. bf16, n % 8 == 0. */
+int sfc_act_bwd(const void* dy, const void* aux, void* out, long long n, int aux_mode, float alpha, float drop_p,
+                unsigned long long drop_seed, sfc_stream_t stream);
 size_t sfc_colsum_scratch_bytes(long long rows, int N);
 int sfc_colsum(const void* x, long long ld, long long rows, int N, void* out, int out_fp32, int accumulate,
                void* scratch, size_t scratch_bytes, sfc_stream_t stream);

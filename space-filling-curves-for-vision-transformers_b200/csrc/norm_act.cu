@@ -7,6 +7,7 @@
 // Layout: activations are bf16 [rows, D] row-major; one warp owns one row; each lane moves 16-byte
 // vectors (8 bf16) so a warp reads/writes 512 contiguous bytes per instruction. Statistics are fp32.
 #include "common.cuh"
+#include "gemm_epilogue.cuh"   // drop_keep
 #include "sfcvit.h"
 
 namespace {
@@ -219,21 +220,27 @@ __global__ void partial_finalize_kernel(const float* __restrict__ part, int npar
   }
 }
 
-// out = dy * f'(aux): relu mask (aux > 0) or exact-GELU derivative (aux = pre-activation); 8 elements per thread
+// out = alpha * dy * f'(aux) * dropout_mask: relu mask (aux > 0), exact-GELU derivative (aux = pre-activation) or
+// identity; the dropout keep decision is re-derived from (seed, element index) exactly as in the GEMM epilogue.
 __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ aux,
-                                                      __nv_bfloat16* __restrict__ out, long long nvec, int mode, float alpha) {
+                                                      __nv_bfloat16* __restrict__ out, long long nvec, int mode, float alpha,
+                                                      float drop_p, unsigned long long seed) {
+  const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     float d[8], a[8], o[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(dy) + i), d);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(aux) + i), a);
+    if (mode != SFC_AUX_NONE) unpack8(__ldg(reinterpret_cast<const uint4*>(aux) + i), a);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      if (mode == SFC_AUX_RELU_MASK) o[j] = a[j] > 0.f ? d[j] * alpha : 0.f;
-      else {
+      float v = d[j] * alpha;
+      if (mode == SFC_AUX_RELU_MASK) v = a[j] > 0.f ? v : 0.f;
+      else if (mode == SFC_AUX_GELU_GRAD) {
         const float cdf = 0.5f * (1.0f + erff(a[j] * 0.70710678118654752f));
         const float pdf = 0.3989422804014327f * __expf(-0.5f * a[j] * a[j]);
-        o[j] = d[j] * alpha * (cdf + a[j] * pdf);
+        v *= (cdf + a[j] * pdf);
       }
+      if (drop_p > 0.f) v = drop_keep(seed, (unsigned long long)(i * 8 + j), drop_p) ? v * inv_keep : 0.f;
+      o[j] = v;
     }
     reinterpret_cast<uint4*>(out)[i] = pack8(o);
   }
@@ -317,15 +324,18 @@ extern "C" int sfc_colsum(const void* x, long long ld, long long rows, int N, vo
   return 0;
 }
 
-// out[i] = alpha * dy[i] * f'(aux[i])   (n % 8 == 0, contiguous bf16)
-extern "C" int sfc_act_bwd(const void* dy, const void* aux, void* out, long long n, int aux_mode, float alpha, cudaStream_t stream) {
-  SFC_REQUIRE(dy && aux && out && n >= 0 && n % 8 == 0, "sfc_act_bwd: bad arguments (n must be a multiple of 8)");
-  SFC_REQUIRE(aux_mode == SFC_AUX_RELU_MASK || aux_mode == SFC_AUX_GELU_GRAD, "sfc_act_bwd: bad mode");
+// out[i] = alpha * dy[i] * f'(aux[i]) * keep(seed, i) / (1 - drop_p)   (n % 8 == 0, contiguous bf16)
+extern "C" int sfc_act_bwd(const void* dy, const void* aux, void* out, long long n, int aux_mode, float alpha, float drop_p,
+                           unsigned long long drop_seed, cudaStream_t stream) {
+  SFC_REQUIRE(dy && out && n >= 0 && n % 8 == 0, "sfc_act_bwd: bad arguments (n must be a multiple of 8)");
+  SFC_REQUIRE(aux_mode == SFC_AUX_NONE || aux != nullptr, "sfc_act_bwd: aux is null");
+  SFC_REQUIRE(aux_mode >= SFC_AUX_NONE && aux_mode <= SFC_AUX_GELU_GRAD, "sfc_act_bwd: bad mode");
   if (n == 0) return 0;
   long long blocks = sfc_ceil_div64(n / 8, 256);
   const long long cap = 16ll * sfc_num_sms();
   if (blocks > cap) blocks = cap;
-  act_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)aux, (__nv_bfloat16*)out, n / 8, aux_mode, alpha);
+  act_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)aux, (__nv_bfloat16*)out, n / 8,
+                                                       aux_mode, alpha, drop_p, drop_seed);
   SFC_LAUNCH_OK();
   return 0;
 }

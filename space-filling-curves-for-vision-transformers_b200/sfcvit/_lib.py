@@ -41,7 +41,7 @@ SIGNATURES = {
     "sfc_patch_embed_kpad": (_i, [_i, _i, _i]),
     "sfc_patch_embed_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _vp]),
     "sfc_patch_gather": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
-    "sfc_act_bwd": (_i, [_vp, _vp, _vp, _ll, _i, _f, _vp]),
+    "sfc_act_bwd": (_i, [_vp, _vp, _vp, _ll, _i, _f, _f, ctypes.c_ulonglong, _vp]),
     "sfc_attn_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, ctypes.c_ulonglong, _vp]),
     "sfc_attn_bwd_scratch_bytes": (_sz, [_i, _i, _i]),
     "sfc_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _f, _f, ctypes.c_ulonglong, _vp]),

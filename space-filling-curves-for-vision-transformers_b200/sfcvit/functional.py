@@ -1,0 +1,311 @@
+"""Autograd functions over the libsfcvit kernels.
+
+Activations are bf16 (as under the reference's bf16 autocast, src/training/train.py:90,113,155); parameters may be
+fp32 or bf16 (main.py:157 sets the default dtype to bf16) — a bf16 shadow is cached per parameter version, and
+gradients are produced directly in the parameter's dtype by the GEMM / reduction epilogues.
+"""
+import weakref
+
+import torch
+from torch.autograd import Function
+
+from . import ops
+
+ACT_NONE, ACT_RELU, ACT_GELU = ops.ACT_NONE, ops.ACT_RELU, ops.ACT_GELU
+
+_shadow = {}
+
+
+def as_bf16(t):
+    """bf16 view/shadow of a parameter (no copy when it already is bf16). Cached on (storage, version)."""
+    if t is None:
+        return None
+    if t.dtype == torch.bfloat16:
+        return t.detach()
+    key = id(t)
+    ent = _shadow.get(key)
+    ver = t._version
+    if ent is not None and ent[0]() is t and ent[1] == ver and ent[2].device == t.device:
+        return ent[2]
+    sh = t.detach().to(torch.bfloat16)
+    _shadow[key] = (weakref.ref(t), ver, sh)
+    if len(_shadow) > 4096:
+        for k in [k for k, e in _shadow.items() if e[0]() is None]:
+            del _shadow[k]
+    return sh
+
+
+def new_seed():
+    """64-bit dropout seed from torch's CPU generator (reproducible under torch.manual_seed; no device sync)."""
+    return int(torch.empty((), dtype=torch.int64).random_().item())
+
+
+def _bf16_act(x):
+    if not x.is_cuda:
+        raise RuntimeError("sfcvit: CUDA tensors only (the B200 path has no CPU fallback)")
+    return x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+
+
+def _pad_cols(t, mult=8):
+    n = t.shape[1]
+    if n % mult == 0 and t.stride(1) == 1 and t.stride(0) % mult == 0:
+        return t
+    npad = (n + mult - 1) // mult * mult
+    out = t.new_zeros((t.shape[0], npad))
+    out[:, :n] = t
+    return out
+
+
+def linear_backward(dy2, x2, wb, w_dtype, need_dx, need_dw, need_db, *, dx_aux=None, dx_aux_mode=ops.AUX_NONE,
+                    dx_alpha=1.0, dx_residual=None):
+    """Gradients of y = x W^T + b for dy2 [M,N], x2 [M,K], wb bf16 [N,K].
+    dX = epilogue(dY.W) (optionally * relu-mask / gelu' of dx_aux, + dx_residual), dW = dY^T.X, db = colsum(dY)."""
+    N = wb.shape[0]
+    dyp = _pad_cols(dy2)                     # TMA needs 16-byte row strides (e.g. num_classes = 10)
+    dx = dw = db = None
+    if need_dx:
+        wbp = wb
+        if dyp.shape[1] != N:
+            wbp = wb.new_zeros((dyp.shape[1], wb.shape[1]))
+            wbp[:N] = wb
+        dx = ops.gemm(dyp, wbp, b_mn=True, aux=dx_aux, aux_mode=dx_aux_mode, alpha=dx_alpha, residual=dx_residual)
+    if need_dw:
+        dwp = ops.gemm(dyp, x2, a_mn=True, b_mn=True, out_dtype=w_dtype, splits=0)
+        dw = dwp[:N] if dwp.shape[0] != N else dwp
+    if need_db:
+        db = ops.colsum(dy2, w_dtype)
+    return dx, dw, db
+
+
+class LinearFn(Function):
+    """y = dropout(act(x W^T + b)) (+ residual). Generic building block (mixer, head, fusion layers)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act, residual, drop_p, seed):
+        xs = x.shape
+        K = xs[-1]
+        x2 = _bf16_act(x).reshape(-1, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        wb, bb = as_bf16(w), as_bf16(b)
+        N = wb.shape[0]
+        res2 = None
+        if residual is not None:
+            res2 = _bf16_act(residual).reshape(-1, N)
+            if not res2.is_contiguous():
+                res2 = res2.contiguous()
+        need_grad = any(ctx.needs_input_grad)
+        want_pre = act == ACT_GELU and need_grad
+        r = ops.gemm(x2, wb, bias=bb, act=act, residual=res2, want_pre=want_pre, drop_p=drop_p, drop_seed=seed)
+        out, pre = r if want_pre else (r, None)
+        ctx.act, ctx.drop_p, ctx.seed, ctx.xs = act, drop_p, seed, xs
+        ctx.has_res = residual is not None
+        ctx.has_bias = b is not None
+        ctx.w_dtype = w.dtype
+        # relu: the (post-dropout) output itself is the mask source, but only when no residual was added on top
+        aux = pre if act == ACT_GELU else (out if (act == ACT_RELU and residual is None) else None)
+        if act == ACT_RELU and residual is not None and need_grad:
+            raise RuntimeError("LinearFn: relu + residual needs the pre-residual output; not used by any reference module")
+        ctx.save_for_backward(x2, wb, aux)
+        return out.reshape(*xs[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wb, aux = ctx.saved_tensors
+        N = wb.shape[0]
+        dy2 = _bf16_act(dy).reshape(-1, N)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        d_res = dy if ctx.has_res else None
+        g = dy2
+        if ctx.act == ACT_RELU:
+            g = ops.act_bwd(dy2, aux, ops.AUX_RELU_MASK, alpha=1.0 / (1.0 - ctx.drop_p) if ctx.drop_p > 0 else 1.0)
+        elif ctx.act == ACT_GELU:
+            g = ops.act_bwd(dy2, aux, ops.AUX_GELU_GRAD, drop_p=ctx.drop_p, drop_seed=ctx.seed)
+        elif ctx.drop_p > 0:
+            g = ops.act_bwd(dy2, None, ops.AUX_NONE, drop_p=ctx.drop_p, drop_seed=ctx.seed)
+        dx, dw, db = linear_backward(g, x2, wb, ctx.w_dtype, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                     ctx.has_bias and ctx.needs_input_grad[2])
+        if dx is not None:
+            dx = dx.reshape(ctx.xs)
+        return dx, dw, db, None, d_res, None, None
+
+
+def linear(x, w, b=None, act=ACT_NONE, residual=None, drop_p=0.0, seed=0):
+    return LinearFn.apply(x, w, b, act, residual, float(drop_p), int(seed))
+
+
+class LayerNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        xs = x.shape
+        x2 = _bf16_act(x).reshape(-1, xs[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        gb = as_bf16(gamma)
+        y, mean, rstd = ops.layernorm_fwd(x2, gb, as_bf16(beta), eps)
+        ctx.save_for_backward(x2, mean, rstd, gb)
+        ctx.xs, ctx.p_dtype = xs, gamma.dtype
+        return y.reshape(xs)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, mean, rstd, gb = ctx.saved_tensors
+        dy2 = _bf16_act(dy).reshape(x2.shape)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dx, dg, db = ops.layernorm_bwd(dy2, x2, mean, rstd, gb, ctx.p_dtype)
+        return dx.reshape(ctx.xs), dg, db, None
+
+
+def layer_norm(x, gamma, beta, eps=1e-5):
+    return LayerNormFn.apply(x, gamma, beta, float(eps))
+
+
+class PatchEmbedFn(Function):
+    """K2: tokens = Linear(curve-ordered patches) without materialising the im2col tensor (forward).
+    w_ref is the reference-layout weight: 'p1p2c' -> [D, g*p*p*C] Linear weight (multi_hilbert.py:66,78-84),
+    'cp1p2' -> Conv2d weight [D, C, p, p] (_2D/hilbert_embedding.py:18-23)."""
+
+    @staticmethod
+    def forward(ctx, img, w_ref, bias, perm32, p, g, k_order, pos):
+        if not img.is_cuda:
+            raise RuntimeError("sfcvit: CUDA tensors only (the B200 path has no CPU fallback)")
+        if img.dtype not in (torch.float32, torch.bfloat16):
+            img = img.float()
+        img = img.contiguous()
+        B, C, H, W = img.shape
+        D = w_ref.shape[0]
+        K = g * p * p * C
+        wk = kernel_weight(w_ref, C, p, g, k_order)
+        out = ops.patch_embed_fwd(img, perm32, wk, as_bf16(bias), p, g, pos=as_bf16(pos))
+        ctx.save_for_backward(img, perm32)
+        ctx.cfg = (p, g, k_order, C, D, K, w_ref.dtype, tuple(w_ref.shape), bias is not None, pos is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        img, perm32 = ctx.saved_tensors
+        p, g, k_order, C, D, K, w_dtype, w_shape, has_bias, has_pos = ctx.cfg
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("PatchEmbedFn: gradient w.r.t. the input image is not implemented")
+        d2 = _bf16_act(dout).reshape(-1, D)
+        if not d2.is_contiguous():
+            d2 = d2.contiguous()
+        dw = db = dpos = None
+        if ctx.needs_input_grad[1]:
+            A = ops.patch_gather(img, perm32, p, g)                       # [M, Kpad] curve-ordered im2col (backward only)
+            dwk = ops.gemm(d2, A, a_mn=True, b_mn=True, out_dtype=w_dtype, splits=0)[:, :K]
+            if k_order == "p1p2c":
+                dw = dwk.reshape(D, g, C, p, p).permute(0, 1, 3, 4, 2).reshape(w_shape)
+            else:
+                dw = dwk.reshape(w_shape)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = ops.colsum(d2, w_dtype)
+        if has_pos and ctx.needs_input_grad[7]:
+            dpos = dout.sum(0)
+        return None, dw, db, None, None, None, None, dpos
+
+
+_wk_cache = {}
+
+
+def kernel_weight(w_ref, C, p, g, k_order):
+    """Reference-layout projection weight -> kernel layout bf16 [D, Kpad] with K ordered (q, c, p1, p2), zero padded.
+    The permutation is applied to the WEIGHT once per parameter version, never to the image data."""
+    key = id(w_ref)
+    ent = _wk_cache.get(key)
+    if ent is not None and ent[0]() is w_ref and ent[1] == w_ref._version and ent[2].device == w_ref.device:
+        return ent[2]
+    D = w_ref.shape[0]
+    K = g * p * p * C
+    Kpad = ops.patch_embed_kpad(C, p, g)
+    w = w_ref.detach()
+    if k_order == "p1p2c":
+        w = w.reshape(D, g, p, p, C).permute(0, 1, 4, 2, 3).reshape(D, K)
+    else:
+        assert g == 1
+        w = w.reshape(D, K)
+    wk = torch.zeros((D, Kpad), dtype=torch.bfloat16, device=w_ref.device)
+    wk[:, :K] = w
+    _wk_cache[key] = (weakref.ref(w_ref), w_ref._version, wk)
+    return wk
+
+
+def patch_embed(img, w_ref, bias, perm32, p, g, k_order="p1p2c", pos=None):
+    return PatchEmbedFn.apply(img, w_ref, bias, perm32, int(p), int(g), k_order, pos)
+
+
+class EncoderLayerFn(Function):
+    """One post-norm ReLU transformer encoder layer (torch.nn.TransformerEncoderLayer defaults used by the reference,
+    vit.py:197-206): x1 = LN1(x + drop(out_proj(MHA(x)))), x2 = LN2(x1 + drop(W2 drop(relu(W1 x1 + b1)) + b2)).
+    Forward: 4 tcgen05 GEMMs with fused bias/ReLU/dropout/residual epilogues + flash attention + 2 LayerNorm kernels.
+    Backward: dgrad GEMMs with fused ReLU-mask / residual epilogues, split-K wgrad GEMMs, column-sum bias gradients."""
+
+    @staticmethod
+    def forward(ctx, x, in_w, in_b, out_w, out_b, w1, b1, w2, b2, g1, be1, g2, be2, heads, eps, drops, seed):
+        B, N, D = x.shape
+        x2 = _bf16_act(x).reshape(B * N, D)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        wi, wo, wf1, wf2 = as_bf16(in_w), as_bf16(out_w), as_bf16(w1), as_bf16(w2)
+        g1b, g2b = as_bf16(g1), as_bf16(g2)
+        s_attn, s_d1, s_ff, s_d2 = seed, seed + 1, seed + 2, seed + 3
+        p_attn, p_d1, p_ff, p_d2 = drops      # attention-prob dropout, dropout1, FFN dropout, dropout2
+        qkv = ops.gemm(x2, wi, bias=as_bf16(in_b))
+        attn, lse = ops.attn_fwd(qkv, B, heads, N, drop_p=p_attn, drop_seed=s_attn)
+        y1 = ops.gemm(attn, wo, bias=as_bf16(out_b), residual=x2, drop_p=p_d1, drop_seed=s_d1)
+        x1, mean1, rstd1 = ops.layernorm_fwd(y1, g1b, as_bf16(be1), eps)
+        h = ops.gemm(x1, wf1, bias=as_bf16(b1), act=ACT_RELU, drop_p=p_ff, drop_seed=s_ff)
+        y2 = ops.gemm(h, wf2, bias=as_bf16(b2), residual=x1, drop_p=p_d2, drop_seed=s_d2)
+        out, mean2, rstd2 = ops.layernorm_fwd(y2, g2b, as_bf16(be2), eps)
+        ctx.save_for_backward(x2, qkv, attn, lse, y1, mean1, rstd1, x1, h, y2, mean2, rstd2, wi, wo, wf1, wf2, g1b, g2b)
+        ctx.cfg = (B, N, D, heads, drops, seed, in_w.dtype)
+        return out.reshape(B, N, D)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x2, qkv, attn, lse, y1, mean1, rstd1, x1, h, y2, mean2, rstd2, wi, wo, wf1, wf2, g1b, g2b) = ctx.saved_tensors
+        B, N, D, heads, drops, seed, pdt = ctx.cfg
+        p_attn, p_d1, p_ff, p_d2 = drops
+        s_attn, s_d1, s_ff, s_d2 = seed, seed + 1, seed + 2, seed + 3
+        inv_keep = 1.0 / (1.0 - p_ff) if p_ff > 0 else 1.0
+        d2 = _bf16_act(dout).reshape(B * N, D)
+        if not d2.is_contiguous():
+            d2 = d2.contiguous()
+        # LN2
+        dy2, dg2, dbe2 = ops.layernorm_bwd(d2, y2, mean2, rstd2, g2b, pdt)
+        dy2d = ops.act_bwd(dy2, None, ops.AUX_NONE, drop_p=p_d2, drop_seed=s_d2) if p_d2 > 0 else dy2
+        # linear2 (+ReLU/dropout mask fused into the dgrad epilogue)
+        dh = ops.gemm(dy2d, wf2, b_mn=True, aux=h, aux_mode=ops.AUX_RELU_MASK, alpha=inv_keep)
+        dw2 = ops.gemm(dy2d, h, a_mn=True, b_mn=True, out_dtype=pdt, splits=0)
+        db2 = ops.colsum(dy2d, pdt)
+        # linear1 (+ residual gradient of x1 fused)
+        dx1 = ops.gemm(dh, wf1, b_mn=True, residual=dy2)
+        dw1 = ops.gemm(dh, x1, a_mn=True, b_mn=True, out_dtype=pdt, splits=0)
+        db1 = ops.colsum(dh, pdt)
+        # LN1
+        dy1, dg1, dbe1 = ops.layernorm_bwd(dx1, y1, mean1, rstd1, g1b, pdt)
+        dy1d = ops.act_bwd(dy1, None, ops.AUX_NONE, drop_p=p_d1, drop_seed=s_d1) if p_d1 > 0 else dy1
+        # out_proj
+        dattn = ops.gemm(dy1d, wo, b_mn=True)
+        dwo = ops.gemm(dy1d, attn, a_mn=True, b_mn=True, out_dtype=pdt, splits=0)
+        dbo = ops.colsum(dy1d, pdt)
+        # attention
+        dqkv = ops.attn_bwd(qkv, attn, dattn, lse, B, heads, N, drop_p=p_attn, drop_seed=s_attn)
+        # in_proj (+ residual gradient of x fused)
+        dx = ops.gemm(dqkv, wi, b_mn=True, residual=dy1) if ctx.needs_input_grad[0] else None
+        dwi = ops.gemm(dqkv, x2, a_mn=True, b_mn=True, out_dtype=pdt, splits=0)
+        dbi = ops.colsum(dqkv, pdt)
+        if dx is not None:
+            dx = dx.reshape(B, N, D)
+        return (dx, dwi, dbi, dwo, dbo, dw1, db1, dw2, db2, dg1, dbe1, dg2, dbe2, None, None, None, None)
+
+
+def encoder_layer(x, layer, heads, eps, drops, seed):
+    """drops = (attention-prob dropout, dropout1, FFN dropout, dropout2) probabilities (all 0 in eval mode)."""
+    a = layer.self_attn
+    return EncoderLayerFn.apply(x, a.in_proj_weight, a.in_proj_bias, a.out_proj.weight, a.out_proj.bias,
+                                layer.linear1.weight, layer.linear1.bias, layer.linear2.weight, layer.linear2.bias,
+                                layer.norm1.weight, layer.norm1.bias, layer.norm2.weight, layer.norm2.bias,
+                                int(heads), float(eps), tuple(float(d) for d in drops), int(seed))

@@ -267,12 +267,14 @@ def adamw_step(p, g, m, v, *, lr, beta1, beta2, eps, weight_decay, step, grad_sc
                                       _stream()), "sfc_adamw_step")
 
 
-def act_bwd(dy, aux, mode, alpha=1.0):
-    """dy * f'(aux) (bf16, contiguous, numel % 8 == 0)."""
+def act_bwd(dy, aux, mode, alpha=1.0, drop_p=0.0, drop_seed=0):
+    """alpha * dy * f'(aux) * dropout_mask (bf16, contiguous, numel % 8 == 0)."""
     lib = _lib.load()
     _require_cuda(dy, aux)
-    assert dy.is_contiguous() and aux.is_contiguous() and dy.dtype == torch.bfloat16 and aux.dtype == torch.bfloat16
+    assert dy.is_contiguous() and dy.dtype == torch.bfloat16
+    assert aux is None or (aux.is_contiguous() and aux.dtype == torch.bfloat16)
     out = torch.empty_like(dy)
     with torch.cuda.device(dy.device):
-        _lib.check(lib.sfc_act_bwd(_ptr(dy), _ptr(aux), _ptr(out), dy.numel(), int(mode), float(alpha), _stream()), "sfc_act_bwd")
+        _lib.check(lib.sfc_act_bwd(_ptr(dy), _ptr(aux), _ptr(out), dy.numel(), int(mode), float(alpha), float(drop_p),
+                                   int(drop_seed) & 0xFFFFFFFFFFFFFFFF, _stream()), "sfc_act_bwd")
     return out

@@ -16,7 +16,8 @@ _REF_MODULES = [
     "src.tokenizers._2D.zigzag_embedding", "src.tokenizers._2D.hilbert_embedding",
     "src.tokenizers._1D.zigzag_embedding1D", "src.tokenizers._1D.hilbert_embedding1D",
     "src.tokenizers._1D.peano_embedding1D", "src.tokenizers._1D.moore_embedding1D",
-    "src.tokenizers._1D.morton_embedding1D",
+    "src.tokenizers._1D.morton_embedding1D", "src.tokenizers._1D.onion_embedding1D",
+    "src.tokenizers._2D.random_embedding", "src.tokenizers.multiscale.multi_onion",
     "src.tokenizers.multiscale.multi_morton", "src.tokenizers.multiscale.multi_zigzag",
     "src.tokenizers.multiscale.multi_hilbert", "src.tokenizers.multiscale.multi_peano",
     "src.tokenizers.multiscale.multi_moore",

@@ -1,0 +1,86 @@
+"""Model parity (src.models.vit on the libsfcvit kernels) vs the fp32 CPU oracle on the same seeded weights/inputs.
+Stated tolerance (measured drift of the reference's own bf16-autocast path): logits rel-L2 <= 2e-2,
+per-parameter gradient rel-L2 <= 1e-1, global gradient cosine >= 0.999. Dropout is zeroed on both sides."""
+import pytest
+import torch
+
+import cases
+from oracle import model as om
+
+pytestmark = pytest.mark.gpu
+
+
+def _build_pair(name):
+    from src.models.vit import VisionTransformer, VisionTransformer1D
+    vk, tcase, mkw, batch = cases.MODEL_CASES[name]
+    kind, kw, shape = cases.TOKENIZER_CASES[tcase]
+    torch.manual_seed(cases.INIT_SEED)
+    o = om.zero_dropout(om.build_vit(vk, cases.build_oracle_tokenizer(kind, kw), **mkw))
+    torch.manual_seed(cases.INIT_SEED)
+    cls = VisionTransformer1D if vk == "vit1d" else VisionTransformer
+    s = om.zero_dropout(cls(patch_embed=cases.build_src_tokenizer(kind, kw), **mkw))
+    x = cases.make_input((batch,) + tuple(shape[1:]))
+    tgt = cases.make_soft_targets(batch, mkw["num_classes"])
+    return o, s, x, tgt
+
+
+@pytest.mark.parametrize("name", sorted(cases.MODEL_CASES))
+def test_model_forward_backward_parity(cuda_device, name):
+    o, s, x, tgt = _build_pair(name)
+    sd_o, sd_s = o.state_dict(), s.state_dict()
+    assert list(sd_o) == list(sd_s)                                  # same keys, same order as the reference layout
+    for k in sd_o:
+        assert torch.equal(sd_o[k], sd_s[k]), k                     # identical init under seed 42
+    s = s.to(cuda_device)
+    o.train(); s.train()
+    lo = o(x)
+    loss_o = om.soft_target_cross_entropy(lo, tgt)
+    loss_o.backward()
+    ls = s(x.to(cuda_device))
+    assert ls.dtype == torch.float32 and tuple(ls.shape) == tuple(lo.shape)
+    loss_s = om.soft_target_cross_entropy(ls.float(), tgt.to(cuda_device))
+    loss_s.backward()
+    assert cases.rel_l2(ls, lo) < 2e-2
+    assert abs(float(loss_s) - float(loss_o)) < 2e-2
+    po, ps = dict(o.named_parameters()), dict(s.named_parameters())
+    dot = no = ns = 0.0
+    for n, p in po.items():
+        if p.grad is None:
+            assert ps[n].grad is None, n                              # e.g. mlp_mixer.token_mix* never get gradients
+            continue
+        g = ps[n].grad
+        assert g is not None and g.dtype == ps[n].dtype, n
+        assert cases.rel_l2(g, p.grad) < 1e-1, (n, cases.rel_l2(g, p.grad))
+        gd, pd = g.detach().double().cpu().flatten(), p.grad.double().flatten()
+        dot += float(gd @ pd); no += float(pd @ pd); ns += float(gd @ gd)
+    assert dot / (no ** 0.5 * ns ** 0.5) > 0.999
+
+
+def test_eval_autocast_bf16_params_and_checkpoint(cuda_device):
+    """main.py's regime: default dtype bf16 parameters, bf16 autocast, eval(): logits are bf16 and match the oracle."""
+    o, s, x, _ = _build_pair("vit1d_hier_morton")
+    s.load_state_dict(o.state_dict())
+    s = s.to(cuda_device).to(torch.bfloat16).eval()
+    o.eval()
+    with torch.no_grad(), torch.amp.autocast(device_type="cuda", dtype=torch.bfloat16):
+        ls = s(x.to(cuda_device))
+    with torch.no_grad():
+        lo = o(x)
+    assert ls.dtype == torch.bfloat16
+    assert cases.rel_l2(ls, lo) < 4e-2                                # bf16 weights + bf16 logits
+
+
+def test_training_mode_dropout_runs_and_is_seeded(cuda_device):
+    from src.models.vit import VisionTransformer
+    kind, kw, shape = cases.TOKENIZER_CASES["conv_hilbert_32_p4_d192"]
+    torch.manual_seed(0)
+    m = VisionTransformer(patch_embed=cases.build_src_tokenizer(kind, kw), depth=2, n_heads=3, mlp_dim=384,
+                          num_classes=10).to(cuda_device).train()
+    x = cases.make_input(shape).to(cuda_device)
+    torch.manual_seed(5); a = m(x)
+    torch.manual_seed(5); b = m(x)
+    torch.manual_seed(6); c = m(x)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    a.float().square().mean().backward()
+    for n, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n

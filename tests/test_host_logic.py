@@ -1,0 +1,101 @@
+"""CPU tests of the host logic: the integer curve routines the kernel runs (host build of csrc/curve_index.h) against
+the oracle, the C-ABI surface, the spiral permutation, the schedule, and the DP bucket/shard helpers."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import curves as oc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PK = os.path.join(ROOT, "space-filling-curves-for-vision-transformers_b200")
+
+
+@pytest.fixture(scope="module")
+def host_curve_lib(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("hostlib") / "libcurve_host.so")
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-I", os.path.join(PK, "csrc"), "-o", out,
+                           os.path.join(ROOT, "tests", "host", "curve_index_host.cpp")])
+    lib = ctypes.CDLL(out)
+    lib.sfc_host_perm.restype = ctypes.c_longlong
+    lib.sfc_host_perm.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p]
+    return lib
+
+
+@pytest.mark.parametrize("cid,curve", [(0, "hilbert"), (1, "z"), (2, "peano"), (3, "moore")])
+def test_kernel_index_math_matches_oracle(host_curve_lib, cid, curve):
+    shapes = [(n, n) for n in cases.PERM_SIZES] + cases.PERM_RECTS
+    for (w, h) in shapes:
+        out = np.empty(w * h, dtype=np.int64)
+        n = host_curve_lib.sfc_host_perm(cid, w, h, out.ctypes.data)
+        ij = oc.embed_and_prune(curve, w, h)
+        assert n == w * h and np.array_equal(out, ij[:, 0] * h + ij[:, 1]), (curve, w, h)
+
+
+def test_kernel_index_math_random_grids(host_curve_lib):
+    rng = np.random.default_rng(0)
+    for _ in range(40):
+        w, h, cid = int(rng.integers(1, 70)), int(rng.integers(1, 70)), int(rng.integers(0, 4))
+        curve = ["hilbert", "z", "peano", "moore"][cid]
+        out = np.empty(w * h, dtype=np.int64)
+        assert host_curve_lib.sfc_host_perm(cid, w, h, out.ctypes.data) == w * h
+        assert np.array_equal(out, oc.flat_perm(curve, w, h)), (curve, w, h)
+        assert np.array_equal(np.sort(out), np.arange(w * h))
+
+
+def test_abi_exports_every_declared_symbol():
+    """The shared library must load without a GPU and export exactly what include/sfcvit.h declares."""
+    from sfcvit import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "sfcvit.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(sfc_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in sfcvit.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.sfc_abi_version() == 1
+    assert lib.sfc_patch_embed_kpad(3, 16, 1) == 768 and lib.sfc_patch_embed_kpad(3, 1, 16) == 64
+
+
+def test_ops_refuse_cpu_tensors():
+    from sfcvit import ops
+    a = torch.zeros(8, 8, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        ops.gemm(a, a)
+    with pytest.raises(RuntimeError):
+        ops.curve_perm("hilbert", 4, 4, device="cpu")
+
+
+def test_spiral_is_a_permutation():
+    from src.tokenizers._spiral import spiral_cells
+    for (h, w) in [(1, 1), (2, 2), (3, 5), (8, 8), (14, 14), (7, 4)]:
+        c = spiral_cells(h, w)
+        assert np.array_equal(np.sort(c[:, 0] * w + c[:, 1]), np.arange(h * w))
+        assert tuple(c[0]) == (h - 1, 0)
+        assert np.all(np.abs(np.diff(c, axis=0)).sum(1) == 1)       # unit steps
+
+
+def test_warmup_cosine_schedule():
+    from src.training.scheduler import WarmupCosineScheduler
+    opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1.0)
+    s = WarmupCosineScheduler(opt, warmup_steps=4, total_steps=12, min_lr=0.0)
+    lrs = [s.step() for _ in range(14)]
+    assert lrs[:4] == [0.0, 0.25, 0.5, 0.75] and lrs[4] == 1.0
+    assert abs(lrs[8] - 0.5) < 1e-12 and lrs[12] == 0.0 and lrs[13] == 0.0
+    assert opt.param_groups[0]["lr"] == lrs[-1]
+
+
+def test_bucketing_and_sharding():
+    from src.training import distributed as D
+    ts = [torch.zeros(10), torch.zeros(30), torch.zeros(5, dtype=torch.bfloat16), torch.zeros(100)]
+    b = D.build_buckets(ts, bucket_bytes=160)
+    assert [len(x) for x in b] == [2, 1, 1]
+    x = torch.arange(10)
+    assert D.shard(x, 1, 2).tolist() == [1, 3, 5, 7, 9] and D.shard(x, 0, 3).tolist() == [0, 3, 6]
+    assert D.world() == (0, 1)
