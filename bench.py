@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: ViT-B/16 224 px, patches serialised along the generalised Hilbert curve (14 x 14 grid),
+one TRAINING step = forward + soft-target CE + backward + (DP gradient all-reduce) + grad-norm clip + AdamW, bf16
+parameters/activations (main.py:157), dropout active, synthetic images and random-init weights.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B] [--config vit_b16_224]
+
+N > 1: launched by the driver as `python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...`.
+Prints ONE JSON line on rank 0 (contract in the task statement): `value` = images/s over all GPUs with inputs resident
+in HBM; `e2e` = same metric through the public API with pinned-host inputs copied H2D (and the loss read back) inside
+the timed region; `roofline` for the dominant kernel family (tcgen05 GEMM), timed live with CUDA events;
+`cpu_baseline` = the CPU oracle port of the reference path on this box's host cores (N = 1 only).
+`--impl reference` times that CPU port alone (all host threads, a bounded batch per step).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PK = os.path.join(ROOT, "space-filling-curves-for-vision-transformers_b200")
+for p in (ROOT, PK):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+CONFIGS = {
+    # name: img, patch, D, depth, heads, mlp, classes, default per-GPU batch
+    "vit_b16_224": dict(img=224, patch=16, D=768, depth=12, heads=12, mlp=3072, classes=1000, batch=256),
+    "vit_s16_224": dict(img=224, patch=16, D=384, depth=12, heads=6, mlp=1536, classes=1000, batch=256),
+    "vit_l16_384": dict(img=384, patch=16, D=1024, depth=24, heads=16, mlp=4096, classes=1000, batch=64),
+    "vit_tiny4_32": dict(img=32, patch=4, D=192, depth=12, heads=3, mlp=768, classes=10, batch=1024),
+}
+METRIC = "ViT-B/16 224px Hilbert images/sec fwd+bwd"
+
+
+def fwd_flops_per_image(c):
+    """Algorithmic forward FLOPs (2mnk per GEMM, 4 N^2 D attention per layer) — SURVEY.md §8d / BASELINE.md §3."""
+    N = (c["img"] // c["patch"]) ** 2
+    D, M, K = c["D"], c["mlp"], 3 * c["patch"] ** 2
+    pe = 2 * N * K * D
+    layer = 2 * N * D * 3 * D + 4 * N * N * D + 2 * N * D * D + 2 * 2 * N * D * M
+    head = 2 * N * D * 64 + 2 * (N * 64) * 2 * D + 2 * 2 * D * c["classes"]
+    return pe + c["depth"] * layer + head
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm_gbs=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_b200_model(c, device):
+    from src.models.vit import VisionTransformer
+    from src.tokenizers.multiscale.multi_hilbert import SFCEmbedding1D
+    torch.manual_seed(42)                                    # main.py:151-152
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)                  # main.py:157: parameters, buffers and optimizer state in bf16
+    try:
+        tok = SFCEmbedding1D(c["img"], c["patch"], 1, 3, c["D"])          # embed-and-prune Hilbert on the patch grid
+        model = VisionTransformer(patch_embed=tok, depth=c["depth"], n_heads=c["heads"], mlp_dim=c["mlp"],
+                                  num_classes=c["classes"]).to(device)
+    finally:
+        torch.set_default_dtype(prev)
+    return model.train()
+
+
+def build_oracle_model(c):
+    from oracle import model as om
+    torch.manual_seed(42)
+    tok = om.SFCEmbedding1D(c["img"], c["patch"], 1, 3, c["D"], "hilbert")
+    tok.n_patches = (c["img"] // c["patch"]) ** 2
+    return om.VisionTransformer(tok, depth=c["depth"], n_heads=c["heads"], mlp_dim=c["mlp"], num_classes=c["classes"]).train()
+
+
+def soft_targets(labels_a, labels_b, lam, classes):
+    oh = torch.nn.functional.one_hot
+    return lam * oh(labels_a, classes).float() + (1 - lam) * oh(labels_b, classes).float()
+
+
+def cpu_reference_throughput(c, steps, warmup, batch):
+    """The reference path on the host CPU (oracle port: stock torch fp32 modules + C-oracle curve indices)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = build_oracle_model(c)
+    opt = torch.optim.AdamW(model.parameters(), lr=3e-4, weight_decay=5e-5)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(batch, 3, c["img"], c["img"], generator=g)
+    tgt = soft_targets(torch.randint(0, c["classes"], (batch,), generator=g), torch.randint(0, c["classes"], (batch,), generator=g), 0.3, c["classes"])
+    from oracle.model import soft_target_cross_entropy
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss = soft_target_cross_entropy(model(x), tgt)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return batch / sec, sec, torch.get_num_threads()
+
+
+def run_reference_arm(args, c):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = args.cpu_batch
+    ips, sec, threads = cpu_reference_throughput(c, max(1, args.steps), max(0, min(args.warmup, 1)), batch)
+    line = {
+        "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": f"{args.config} Hilbert(embed-and-prune) train step fwd+bwd+clip+AdamW, CPU oracle port of the reference path",
+                   "batch_per_step": batch},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps of batch {batch} (fp32, {threads} threads)"},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="vit_b16_224", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: config)")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dropout", action="store_true")
+    args = ap.parse_args()
+    c = dict(CONFIGS[args.config])
+    if args.impl == "reference":
+        return run_reference_arm(args, c)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+    from sfcvit import ops
+    from src.training import distributed as D
+    from src.training.losses import SoftTargetCrossEntropy
+    from src.training.optim import FusedAdamW
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (B200); there is no CPU fallback")
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    rank, world = D.init_from_env("nccl")
+    B = args.batch or c["batch"]
+    classes = c["classes"]
+
+    model = build_b200_model(c, device)
+    if args.no_dropout:
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+            if isinstance(m, torch.nn.MultiheadAttention):
+                m.dropout = 0.0
+    opt = FusedAdamW(model.parameters(), lr=3e-4, weight_decay=5e-5, max_grad_norm=1.0)   # main.py:288-289 + train.py:165
+    crit = SoftTargetCrossEntropy()
+
+    g = torch.Generator(device=device).manual_seed(1234 + rank)
+    n_bufs = 4                                                        # distinct input batches: 4 x 154 MB > L2 (126 MB)
+    dev_imgs = [torch.randn(B, 3, c["img"], c["img"], generator=g, device=device) for _ in range(n_bufs)]
+    la = torch.randint(0, classes, (B,), generator=g, device=device)
+    lb = torch.randint(0, classes, (B,), generator=g, device=device)
+    tgt = soft_targets(la, lb, 0.3, classes)
+
+    def step(images):
+        opt.zero_grad(set_to_none=True)
+        logits = model(images)
+        loss = crit(logits, tgt)
+        loss.backward()
+        opt.step()                                                    # all-reduce (N > 1) + clip + AdamW, fused
+        return loss
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(dev_imgs[i % n_bufs])
+    sync_all()
+
+    # ---------------- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.GEMM_PROFILE = []
+    launches0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for i in range(args.steps):
+        loss = step(dev_imgs[i % n_bufs])
+    e1.record()
+    sync_all()
+    ms_local = e0.elapsed_time(e1)
+    launches = ops.LAUNCHES - launches0
+    prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_local], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
+    gemm_flops = sum(f for _, _, f in prof)
+    peaks = load_peaks()
+    gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    step_flops = 3.0 * fwd_flops_per_image(c) * B
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all fwd/dgrad/wgrad launches)",
+        "achieved": gemm_tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+        "frac": gemm_tflops / peaks["tf_sustained"], "peak_source": peaks["source"] + " (sustained; kernels timed inside a long step)",
+        "traffic": None, "launches_per_step": len(prof) / max(1, args.steps),
+        "avg_launch_ms": gemm_ms / max(1, len(prof)), "gemm_share_of_step": gemm_ms / ms_local,
+        "whole_step_tflops": step_flops / (ms_total / args.steps * 1e-3) / 1e12,
+        "whole_step_frac_of_peak": step_flops / (ms_total / args.steps * 1e-3) / 1e12 / peaks["tf_sustained"],
+    }
+
+    # ---------------- timed region 2: end to end (pinned host inputs -> H2D every step, loss read back)
+    host_imgs = [torch.randn(B, 3, c["img"], c["img"]).pin_memory() for _ in range(2)]
+    stage = [torch.empty(B, 3, c["img"], c["img"], device=device) for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            stage[s].copy_(host_imgs[s], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    for s in range(2):
+        consumed[s].record()
+    e2e_steps = max(3, args.steps)
+    sync_all()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    prefetch(0)
+    loss_host = 0.0
+    for i in range(e2e_steps):
+        if i + 1 < e2e_steps:
+            prefetch(i + 1)
+        s = i % 2
+        torch.cuda.current_stream().wait_event(ready[s])
+        loss = step(stage[s])
+        consumed[s].record()
+        loss_host = float(loss.item())                                # device -> host read of the step's result
+    t1.record()
+    sync_all()
+    tt = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / (float(tt.item()) * 1e-3)
+    e2e = {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * c["img"] * c["img"] * 4,
+           "d2h_bytes_per_step": 4, "steps": e2e_steps, "last_loss": loss_host}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ips, sec, threads = cpu_reference_throughput(c, 2, 1, args.cpu_batch)
+        cpu_baseline = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                        "sample": f"2 timed steps (+1 warm-up) of batch {args.cpu_batch}, fp32, {threads} threads, same model/step as the GPU arm"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.config} generalised-Hilbert (embed-and-prune) tokens, training step fwd+bwd+clip+AdamW",
+                       "batch_per_gpu": B, "global_batch": B * world, "tokens": (c["img"] // c["patch"]) ** 2,
+                       "dropout": not args.no_dropout, "params_dtype": "bf16", "parallelism": f"dp{world}",
+                       "l2_policy": f"{n_bufs} rotating input batches of {B * 3 * c['img'] ** 2 * 4 / 1e6:.0f} MB (> 126 MB L2); activations per step ~GBs"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
+            "gpu_launches_per_step": launches / args.steps, "clocks": clocks, "loss": float(loss.item()),
+            "allreduce_buckets_per_step": opt.last_num_buckets,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

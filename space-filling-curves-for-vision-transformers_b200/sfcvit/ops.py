@@ -11,6 +11,16 @@ CURVE_IDS = {"hilbert_curve": 0, "z_curve": 1, "peano_curve": 2, "moore_curve": 
              "hilbert": 0, "z": 1, "morton": 1, "peano": 2, "moore": 3, "raster": 4}
 
 
+# ---- instrumentation (bench.py): kernel-launch counter and optional per-GEMM CUDA-event timing -------------
+LAUNCHES = 0            # kernels launched through the C ABI by this process
+GEMM_PROFILE = None     # when a list: (start_event, end_event, flops) appended per sfc_gemm_bf16 call
+
+
+def _count(n):
+    global LAUNCHES
+    LAUNCHES += n
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -57,6 +67,7 @@ def curve_perm(curve, w: int, h: int, device="cuda"):
         nbytes = lib.sfc_curve_perm_scratch_bytes(cid, w, h)
         scratch = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=device)
         _lib.check(lib.sfc_curve_perm(cid, w, h, _ptr(perm), _ptr(inv), _ptr(scratch), nbytes, _stream()), "sfc_curve_perm")
+    _count(2)
     return perm, inv
 
 
@@ -107,10 +118,18 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=None, au
     if splits > 1:
         ws_bytes = lib.sfc_gemm_workspace_bytes(M, N, K, splits)
         ws = _workspace(ws_bytes, a.device)
+    prof = GEMM_PROFILE
     with torch.cuda.device(a.device):
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         rc = lib.sfc_gemm_bf16(_ptr(a), int(a_mn), a.stride(0), _ptr(b), int(b_mn), b.stride(0), M, N, K,
                                ctypes.byref(ep), _ptr(ws), ws_bytes, int(splits), _stream())
+        if prof is not None:
+            e1.record()
+            prof.append((e0, e1, 2.0 * M * N * K))
     _lib.check(rc, "sfc_gemm_bf16")
+    _count(2 if splits > 1 else 1)
     return (out, pre) if want_pre else out
 
 
@@ -128,6 +147,7 @@ def layernorm_fwd(x, gamma, beta, eps=1e-5, want_stats=True):
     with torch.cuda.device(x.device):
         _lib.check(lib.sfc_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean), _ptr(rstd), rows, D,
                                          float(eps), _stream()), "sfc_layernorm_fwd")
+    _count(1)
     return y, mean, rstd
 
 
@@ -147,6 +167,7 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, param_dtype=torch.bfloat16):
         _lib.check(lib.sfc_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dx), _ptr(dgamma),
                                          _ptr(dbeta), 1 if param_dtype == torch.float32 else 0, 0, _ptr(scratch), nbytes,
                                          rows, D, _stream()), "sfc_layernorm_bwd")
+    _count(3)
     return dx, dgamma, dbeta
 
 
@@ -162,6 +183,7 @@ def colsum(x, out_dtype=torch.bfloat16):
     with torch.cuda.device(x.device):
         _lib.check(lib.sfc_colsum(_ptr(x), x.stride(0), rows, N, _ptr(out), 1 if out_dtype == torch.float32 else 0, 0,
                                   _ptr(scratch), nbytes, _stream()), "sfc_colsum")
+    _count(2)
     return out
 
 
@@ -193,6 +215,7 @@ def patch_embed_fwd(img, perm, wk, bias, p, g, *, pos=None, out=None, col_off=0,
                                      perm.numel(), _ptr(wk), _ptr(bias), _ptr(pos), pos.stride(0) if pos is not None else 0, out_ptr,
                                      out.stride(1), D, rows_per_img, tok_off, _stream())
     _lib.check(rc, "sfc_patch_embed_fwd")
+    _count(1)
     return out
 
 
@@ -207,6 +230,7 @@ def patch_gather(img, perm, p, g):
     with torch.cuda.device(img.device):
         _lib.check(lib.sfc_patch_gather(_ptr(img), 1 if img.dtype == torch.bfloat16 else 0, B, C, H, W, p, g, _ptr(perm),
                                         perm.numel(), _ptr(A), _stream()), "sfc_patch_gather")
+    _count(1)
     return A
 
 
@@ -225,6 +249,7 @@ def attn_fwd(qkv, B, H, N, *, scale=None, drop_p=0.0, drop_seed=0):
     with torch.cuda.device(qkv.device):
         _lib.check(lib.sfc_attn_fwd(_ptr(qkv), _ptr(out), _ptr(lse), B, H, N, D, float(scale), float(drop_p),
                                     int(drop_seed) & 0xFFFFFFFFFFFFFFFF, _stream()), "sfc_attn_fwd")
+    _count(1)
     return out, lse
 
 
@@ -242,6 +267,7 @@ def attn_bwd(qkv, out, dout, lse, B, H, N, *, scale=None, drop_p=0.0, drop_seed=
         _lib.check(lib.sfc_attn_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), _ptr(scratch), nbytes, B, H, N,
                                     D, float(scale), float(drop_p), int(drop_seed) & 0xFFFFFFFFFFFFFFFF, _stream()),
                    "sfc_attn_bwd")
+    _count(2)
     return dqkv
 
 
@@ -253,6 +279,7 @@ def grad_sumsq(g, accum):
     with torch.cuda.device(g.device):
         _lib.check(lib.sfc_grad_sumsq(_ptr(g), 1 if g.dtype == torch.float32 else 0, g.numel(), _ptr(accum), _stream()),
                    "sfc_grad_sumsq")
+    _count(1)
 
 
 def adamw_step(p, g, m, v, *, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, max_norm=0.0, stats=None):
@@ -265,6 +292,7 @@ def adamw_step(p, g, m, v, *, lr, beta1, beta2, eps, weight_decay, step, grad_sc
                                       1 if m.dtype == torch.float32 else 0, float(lr), float(beta1), float(beta2), float(eps),
                                       float(weight_decay), int(step), float(grad_scale), float(max_norm), _ptr(stats),
                                       _stream()), "sfc_adamw_step")
+    _count(1)
 
 
 def act_bwd(dy, aux, mode, alpha=1.0, drop_p=0.0, drop_seed=0):
@@ -277,4 +305,5 @@ def act_bwd(dy, aux, mode, alpha=1.0, drop_p=0.0, drop_seed=0):
     with torch.cuda.device(dy.device):
         _lib.check(lib.sfc_act_bwd(_ptr(dy), _ptr(aux), _ptr(out), dy.numel(), int(mode), float(alpha), float(drop_p),
                                    int(drop_seed) & 0xFFFFFFFFFFFFFFFF, _stream()), "sfc_act_bwd")
+    _count(1)
     return out

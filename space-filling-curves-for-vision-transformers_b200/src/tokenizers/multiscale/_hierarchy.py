@@ -31,6 +31,7 @@ class GroupedCurveLevel(CurveGatherEmbedding):
         self.grid_size = img_size // pre_patch_size
         self.n_pre_patches = self.grid_size * self.grid_size
         self.n_final_patches = self.n_pre_patches // group_patch_size
+        self.n_patches = self.n_final_patches      # superset of the reference: lets a single level feed VisionTransformer
         self.pre_patch_dim = in_channels * pre_patch_size * pre_patch_size
         self.input_dim = self.pre_patch_dim * group_patch_size
         idx = self._build_indices(self.grid_size)
