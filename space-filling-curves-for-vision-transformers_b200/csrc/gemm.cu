@@ -164,19 +164,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const long long m = (long long)m_tile * BM + row_in_tile;
       const bool row_ok = m < p.M;
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(ewarp * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = n_tile * BN + c * 32;
-        if (n0 >= p.N) break;                      // warp-uniform
-        uint32_t r[32];
-        ptx::tmem_ld_x32(taddr + c * 32, r);
-        ptx::tmem_ld_wait();
-        if (!row_ok) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        epi_apply_store(p.epi, v, m, m, n0, split);
-      }
+      epi_tile<BN>(p.epi, taddr, n_tile * BN, m, m, row_ok, split);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
     }

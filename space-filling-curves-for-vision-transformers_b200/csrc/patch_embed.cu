@@ -251,19 +251,7 @@ patch_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchPa
       const long long tok = row_ok ? m % pp.ntok : 0;
       const long long out_row = bimg * pp.rows_per_img + pp.tok_off + tok;
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(ewarp * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = n_tile * BN + c * 32;
-        if (n0 >= pp.epi.N) break;
-        uint32_t r[32];
-        ptx::tmem_ld_x32(taddr + c * 32, r);
-        ptx::tmem_ld_wait();
-        if (!row_ok) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        epi_apply_store(pp.epi, v, out_row, tok, n0, 0);
-      }
+      epi_tile<BN>(pp.epi, taddr, n_tile * BN, out_row, tok, row_ok, 0);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
     }
