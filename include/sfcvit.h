@@ -81,9 +81,12 @@ int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B, i
 int sfc_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
                       long long rows, int D, float eps, sfc_stream_t stream);
 size_t sfc_layernorm_bwd_scratch_bytes(long long rows, int D);
+/* optional fused extras: dx_drop = dropout-masked copy of dx (mask of a [rows, D] GEMM output drawn with drop_seed),
+ * dcolsum[D] = column sums of dx_drop (of dx when dx_drop is NULL) = bias gradient of the preceding Linear. */
 int sfc_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma, void* dx,
-                      void* dgamma, void* dbeta, int param_fp32, int accumulate, void* scratch, size_t scratch_bytes,
-                      long long rows, int D, sfc_stream_t stream);
+                      void* dx_drop, float drop_p, unsigned long long drop_seed, void* dgamma, void* dbeta,
+                      void* dcolsum, int param_fp32, int accumulate, void* scratch, size_t scratch_bytes, long long rows,
+                      int D, sfc_stream_t stream);
 /* out = alpha * dy * f'(aux) * keep(seed, i) / (1 - drop_p): aux_mode SFC_AUX_NONE, SFC_AUX_RELU_MASK (aux > 0) or
  * SFC_AUX_GELU_GRAD (aux = pre-activation); the dropout mask is the one the GEMM epilogue drew for a contiguous
  * [M, N] output with the same seed. bf16, n % 8 == 0. */

@@ -38,14 +38,39 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
-// Counter-based dropout keep decision (same hash used by forward and backward): splitmix64 of (seed, index).
-__device__ __forceinline__ bool drop_keep(unsigned long long seed, unsigned long long idx, float p) {
-  unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
+// Counter-based dropout (same decisions in forward and backward, no mask tensor): one splitmix64 hash of
+// (seed, index >> 2) yields four 16-bit uniform lanes; element `index` is kept iff its lane >= thr16 = p * 65536.
+// The keep probability is exactly 1 - thr16 / 65536, and that value (not the nominal p) is used for the rescale.
+__device__ __forceinline__ unsigned long long drop_hash4(unsigned long long seed, unsigned long long group) {
+  unsigned long long z = seed + group * 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  const float u = (float)(unsigned)(z >> 40) * (1.0f / 16777216.0f);
-  return u >= p;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint32_t drop_thr16(float p) { return (uint32_t)(p * 65536.0f); }
+__device__ __forceinline__ float drop_inv_keep(float p) {
+  return p > 0.f ? 65536.0f / (65536.0f - (float)drop_thr16(p)) : 1.0f;
+}
+__device__ __forceinline__ bool drop_keep(unsigned long long seed, unsigned long long idx, uint32_t thr16) {
+  const unsigned long long h = drop_hash4(seed, idx >> 2);
+  return ((uint32_t)(h >> (16 * (uint32_t)(idx & 3))) & 0xffffu) >= thr16;
+}
+// v[i] = keep(base + i) ? v[i] * inv_keep : 0 for NV consecutive elements (NV % 4 == 0)
+template <int NV>
+__device__ __forceinline__ void drop_apply(float* v, unsigned long long seed, unsigned long long base, float p) {
+  const uint32_t thr = drop_thr16(p);
+  const float sc = drop_inv_keep(p);
+  if ((base & 3ull) == 0) {
+#pragma unroll
+    for (int g = 0; g < NV / 4; ++g) {
+      const unsigned long long h = drop_hash4(seed, (base >> 2) + g);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[g * 4 + k] = (((uint32_t)(h >> (16 * k)) & 0xffffu) >= thr) ? v[g * 4 + k] * sc : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = drop_keep(seed, base + i, thr) ? v[i] * sc : 0.f;
+  }
 }
 
 __device__ __forceinline__ void epi_unpack8(const uint4& b, float* f) {
@@ -121,12 +146,8 @@ __device__ __forceinline__ void epi_apply_store(const EpiParams& p, float (&v)[3
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
   }
-  if (p.drop_p > 0.0f) {
-    const float sc = 1.0f / (1.0f - p.drop_p);
-    const unsigned long long base = (unsigned long long)m_out * (unsigned long long)p.N + (unsigned long long)n0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = drop_keep(p.drop_seed, base + j, p.drop_p) ? v[j] * sc : 0.0f;
-  }
+  if (p.drop_p > 0.0f)
+    drop_apply<32>(v, p.drop_seed, (unsigned long long)m_out * (unsigned long long)p.N + (unsigned long long)n0, p.drop_p);
   if (p.aux_mode != SFC_AUX_NONE) {
     float a[32];
     if (r.aux_vec) {

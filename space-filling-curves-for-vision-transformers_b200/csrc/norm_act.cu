@@ -84,45 +84,56 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
   }
 }
 
-// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma,  xhat = (x - mean) * rstd
-// per-CTA partial sums of dgamma = sum dy * xhat and dbeta = sum dy go to part[blockIdx.x][2][D] (fp32).
-template <int NV>
-__global__ void __launch_bounds__(kLnWarps * 32)
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma,  xhat = (x - mean) * rstd.
+// Fused extras (all optional): dx_drop = dropout_mask(dx) / keep — the gradient that flows into the Linear whose
+// output was dropped before the residual add (mask re-derived from (seed, row * D + col) exactly as the forward GEMM
+// epilogue drew it) — and the column sums of that tensor (= bias gradient of that Linear).
+// Per-CTA partial sums go to part[blockIdx.x][3][D] (fp32): dgamma = sum dy * xhat, dbeta = sum dy, colsum.
+// Row data stay PACKED (bf16x8 uint4) in registers and are unpacked in each of the two passes, which keeps the
+// kernel at 3 CTAs / SM for D = 768 (a memory-bound kernel needs the loads of many rows in flight).
+template <int NV, bool DROP, bool CSUM>
+__global__ void __launch_bounds__(kLnWarps * 32, 3)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
-                     const __nv_bfloat16* __restrict__ gamma, __nv_bfloat16* __restrict__ dx, float* __restrict__ part,
-                     long long rows, int D) {
-  extern __shared__ float sred[];            // [kLnWarps][2][D]
+                     const __nv_bfloat16* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
+                     __nv_bfloat16* __restrict__ dx_drop, float drop_p, unsigned long long drop_seed,
+                     float* __restrict__ part, long long rows, int D) {
+  extern __shared__ float sred[];            // [kLnWarps][3][D]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nvec = D >> 3;
-  float dg[NV][8], db[NV][8], gm[NV][8];
+  float dg[NV][8], db[NV][8], cs[CSUM ? NV : 1][8];
+  uint4 gmp[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = lane + i * 32;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; gm[i][j] = 0.f; }
-    if (vi < nvec) unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + vi), gm[i]);
+    for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; if (CSUM) cs[i][j] = 0.f; }
+    gmp[i] = (vi < nvec) ? __ldg(reinterpret_cast<const uint4*>(gamma) + vi) : make_uint4(0, 0, 0, 0);
   }
   for (long long row = (long long)blockIdx.x * kLnWarps + wid; row < rows; row += (long long)gridDim.x * kLnWarps) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + row * D);
     const uint4* dyr = reinterpret_cast<const uint4*>(dy + row * D);
+    uint4 xp[NV], dp[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) { xp[i] = __ldg(xr + vi); dp[i] = __ldg(dyr + vi); }
+    }
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float xh[NV][8], g[NV][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + i * 32;
       if (vi < nvec) {
-        float xv[8], dv[8];
-        unpack8(__ldg(xr + vi), xv);
-        unpack8(__ldg(dyr + vi), dv);
+        float xv[8], dv[8], gm[8];
+        unpack8(xp[i], xv); unpack8(dp[i], dv); unpack8(gmp[i], gm);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (xv[j] - mean) * rstd;
-          g[i][j] = dv[j] * gm[i][j];
-          s1 += g[i][j];
-          s2 += g[i][j] * xh[i][j];
-          dg[i][j] += dv[j] * xh[i][j];
+          const float xh = (xv[j] - mean) * rstd;
+          const float g = dv[j] * gm[j];
+          s1 += g;
+          s2 += g * xh;
+          dg[i][j] += dv[j] * xh;
           db[i][j] += dv[j];
         }
       }
@@ -134,32 +145,46 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + i * 32;
       if (vi < nvec) {
-        float o[8];
+        float xv[8], dv[8], gm[8], o[8];
+        unpack8(xp[i], xv); unpack8(dp[i], dv); unpack8(gmp[i], gm);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - s1 - xh[i][j] * s2);
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mean) * rstd;
+          o[j] = rstd * (dv[j] * gm[j] - s1 - xh * s2);
+        }
         dxr[vi] = pack8(o);
+        if (DROP) {
+          drop_apply<8>(o, drop_seed, (unsigned long long)row * (unsigned long long)D + (unsigned long long)(vi * 8), drop_p);
+          reinterpret_cast<uint4*>(dx_drop + row * D)[vi] = pack8(o);
+        }
+        if (CSUM) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cs[i][j] += o[j];
+        }
       }
     }
   }
   // cross-warp reduction of the column partials
+  constexpr int NP = CSUM ? 3 : 2;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = lane + i * 32;
     if (vi < nvec) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        sred[(wid * 2 + 0) * D + vi * 8 + j] = dg[i][j];
-        sred[(wid * 2 + 1) * D + vi * 8 + j] = db[i][j];
+        sred[(wid * 3 + 0) * D + vi * 8 + j] = dg[i][j];
+        sred[(wid * 3 + 1) * D + vi * 8 + j] = db[i][j];
+        if (CSUM) sred[(wid * 3 + 2) * D + vi * 8 + j] = cs[i][j];
       }
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+  for (int c = threadIdx.x; c < NP * D; c += blockDim.x) {
     const int which = c / D, col = c % D;
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < kLnWarps; ++w) s += sred[(w * 2 + which) * D + col];
-    part[((long long)blockIdx.x * 2 + which) * D + col] = s;
+    for (int w = 0; w < kLnWarps; ++w) s += sred[(w * 3 + which) * D + col];
+    part[((long long)blockIdx.x * 3 + which) * D + col] = s;
   }
 }
 
@@ -204,19 +229,45 @@ colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long lo
   }
 }
 
-// out[c] = (accumulate ? out[c] : 0) + sum_b part[b * stride + c]
-__global__ void partial_finalize_kernel(const float* __restrict__ part, int nparts, long long stride, int N, void* __restrict__ out,
-                                        int out_fp32, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N) return;
+// out_v[c] = (accumulate ? out_v[c] : 0) + sum_b part[b * stride + v * vstride + c]   for v < nvec output vectors.
+// grid (ceil(N / 32), nvec), block (32 columns x 8 part-lanes): the partials of a column are summed by 8 threads with
+// independent loads in flight instead of one long dependent loop.
+struct FinalizeOut { void* ptr[3]; };
+__global__ void __launch_bounds__(256) partial_finalize_kernel(const float* __restrict__ part, int nparts, long long stride,
+                                                               long long vstride, int N, FinalizeOut outs, int out_fp32,
+                                                               int accumulate) {
+  __shared__ float sred[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int v = blockIdx.y;
   float s = 0.f;
-  for (int b = 0; b < nparts; ++b) s += part[(long long)b * stride + c];
-  if (out_fp32) {
-    float* o = reinterpret_cast<float*>(out) + c;
-    *o = accumulate ? *o + s : s;
-  } else {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + c;
-    *o = __float2bfloat16(accumulate ? __bfloat162float(*o) + s : s);
+  if (c < N) {
+    const float* base = part + v * vstride + c;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int b = ty;
+    for (; b + 24 < nparts; b += 32) {
+      s0 += base[(long long)b * stride];
+      s1 += base[(long long)(b + 8) * stride];
+      s2 += base[(long long)(b + 16) * stride];
+      s3 += base[(long long)(b + 24) * stride];
+    }
+    for (; b < nparts; b += 8) s0 += base[(long long)b * stride];
+    s = (s0 + s1) + (s2 + s3);
+  }
+  sred[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sred[w][tx];
+    void* out = outs.ptr[v];
+    if (out_fp32) {
+      float* o = reinterpret_cast<float*>(out) + c;
+      *o = accumulate ? *o + t : t;
+    } else {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + c;
+      *o = __float2bfloat16(accumulate ? __bfloat162float(*o) + t : t);
+    }
   }
 }
 
@@ -225,7 +276,6 @@ __global__ void partial_finalize_kernel(const float* __restrict__ part, int npar
 __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ aux,
                                                       __nv_bfloat16* __restrict__ out, long long nvec, int mode, float alpha,
                                                       float drop_p, unsigned long long seed) {
-  const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     float d[8], a[8], o[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(dy) + i), d);
@@ -239,16 +289,16 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __res
         const float pdf = 0.3989422804014327f * __expf(-0.5f * a[j] * a[j]);
         v *= (cdf + a[j] * pdf);
       }
-      if (drop_p > 0.f) v = drop_keep(seed, (unsigned long long)(i * 8 + j), drop_p) ? v * inv_keep : 0.f;
       o[j] = v;
     }
+    if (drop_p > 0.f) drop_apply<8>(o, seed, (unsigned long long)i * 8ull, drop_p);
     reinterpret_cast<uint4*>(out)[i] = pack8(o);
   }
 }
 
 int ln_bwd_blocks(long long rows) {
   long long b = sfc_ceil_div64(rows, kLnWarps);
-  const long long cap = 2ll * sfc_num_sms();
+  const long long cap = 3ll * sfc_num_sms();
   return (int)(b < cap ? b : cap);
 }
 
@@ -270,34 +320,48 @@ extern "C" int sfc_layernorm_fwd(const void* x, const void* gamma, const void* b
 }
 
 extern "C" size_t sfc_layernorm_bwd_scratch_bytes(long long rows, int D) {
-  return (size_t)ln_bwd_blocks(rows) * 2 * (size_t)D * sizeof(float);
+  return (size_t)ln_bwd_blocks(rows) * 3 * (size_t)D * sizeof(float);
 }
 
+// dx_drop / dcolsum may be NULL. dcolsum = column sums of dx_drop (or of dx when dx_drop is NULL).
 extern "C" int sfc_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const void* gamma,
-                                 void* dx, void* dgamma, void* dbeta, int param_fp32, int accumulate, void* scratch,
+                                 void* dx, void* dx_drop, float drop_p, unsigned long long drop_seed, void* dgamma,
+                                 void* dbeta, void* dcolsum, int param_fp32, int accumulate, void* scratch,
                                  size_t scratch_bytes, long long rows, int D, cudaStream_t stream) {
   SFC_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta, "sfc_layernorm_bwd: null pointer");
   SFC_REQUIRE(D % 8 == 0 && D >= 8 && D <= kMaxVec * 256, "sfc_layernorm_bwd: D=%d unsupported", D);
   SFC_REQUIRE(rows > 0, "sfc_layernorm_bwd: rows must be positive");
+  SFC_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "sfc_layernorm_bwd: dropout p out of range");
+  const bool drop = dx_drop != nullptr && drop_p > 0.f;
+  SFC_REQUIRE(dx_drop == nullptr || drop, "sfc_layernorm_bwd: dx_drop given but drop_p == 0");
+  const bool csum = dcolsum != nullptr;
   const int blocks = ln_bwd_blocks(rows);
-  SFC_REQUIRE(scratch && scratch_bytes >= (size_t)blocks * 2 * D * sizeof(float), "sfc_layernorm_bwd: scratch too small");
-  const size_t smem = (size_t)kLnWarps * 2 * D * sizeof(float);
+  SFC_REQUIRE(scratch && scratch_bytes >= (size_t)blocks * 3 * D * sizeof(float), "sfc_layernorm_bwd: scratch too small");
+  const size_t smem = (size_t)kLnWarps * 3 * D * sizeof(float);
   const int nv = sfc_ceil_div(D / 8, 32);
-#define LN_BWD(NV)                                                                                                  \
+#define LN_BWD2(NV, DR, CS)                                                                                         \
   do {                                                                                                              \
-    auto k = layernorm_bwd_kernel<NV>;                                                                              \
+    auto k = layernorm_bwd_kernel<NV, DR, CS>;                                                                      \
     if (smem > 48 * 1024) SFC_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     k<<<blocks, kLnWarps * 32, smem, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd,       \
-                                               (const __nv_bfloat16*)gamma, (__nv_bfloat16*)dx, (float*)scratch, rows, D); \
+                                               (const __nv_bfloat16*)gamma, (__nv_bfloat16*)dx, (__nv_bfloat16*)dx_drop, \
+                                               drop_p, drop_seed, (float*)scratch, rows, D);                        \
+  } while (0)
+#define LN_BWD(NV)                                                                  \
+  do {                                                                              \
+    if (drop && csum) LN_BWD2(NV, true, true);                                      \
+    else if (drop) LN_BWD2(NV, true, false);                                        \
+    else if (csum) LN_BWD2(NV, false, true);                                        \
+    else LN_BWD2(NV, false, false);                                                 \
   } while (0)
   if (nv <= 1) LN_BWD(1); else if (nv <= 2) LN_BWD(2); else if (nv <= 3) LN_BWD(3); else if (nv <= 4) LN_BWD(4); else LN_BWD(8);
 #undef LN_BWD
+#undef LN_BWD2
   SFC_LAUNCH_OK();
-  const int threads = 256;
-  // part layout: [block][2][D] -> dgamma uses offset 0, dbeta offset D, stride 2*D
-  partial_finalize_kernel<<<sfc_ceil_div(D, threads), threads, 0, stream>>>((const float*)scratch, blocks, 2ll * D, D, dgamma, param_fp32, accumulate);
-  SFC_LAUNCH_OK();
-  partial_finalize_kernel<<<sfc_ceil_div(D, threads), threads, 0, stream>>>((const float*)scratch + D, blocks, 2ll * D, D, dbeta, param_fp32, accumulate);
+  FinalizeOut outs;
+  outs.ptr[0] = dgamma; outs.ptr[1] = dbeta; outs.ptr[2] = dcolsum;
+  dim3 grid(sfc_ceil_div(D, 32), csum ? 3 : 2);
+  partial_finalize_kernel<<<grid, 256, 0, stream>>>((const float*)scratch, blocks, 3ll * D, (long long)D, D, outs, param_fp32, accumulate);
   SFC_LAUNCH_OK();
   return 0;
 }
@@ -319,7 +383,9 @@ extern "C" int sfc_colsum(const void* x, long long ld, long long rows, int N, vo
   dim3 grid(sfc_ceil_div(N, 256), rb);
   colsum_partial_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, ld, rows, N, (float*)scratch, sfc_ceil_div64(rows, rb));
   SFC_LAUNCH_OK();
-  partial_finalize_kernel<<<sfc_ceil_div(N, 256), 256, 0, stream>>>((const float*)scratch, rb, (long long)N, N, out, out_fp32, accumulate);
+  FinalizeOut outs;
+  outs.ptr[0] = out; outs.ptr[1] = nullptr; outs.ptr[2] = nullptr;
+  partial_finalize_kernel<<<dim3(sfc_ceil_div(N, 32), 1), 256, 0, stream>>>((const float*)scratch, rb, (long long)N, 0, N, outs, out_fp32, accumulate);
   SFC_LAUNCH_OK();
   return 0;
 }

@@ -35,7 +35,7 @@ SIGNATURES = {
     "sfc_gemm_suggest_splits": (_i, [_i, _i, _i]),
     "sfc_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _vp]),
     "sfc_layernorm_bwd_scratch_bytes": (_sz, [_ll, _i]),
-    "sfc_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _sz, _ll, _i, _vp]),
+    "sfc_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, ctypes.c_ulonglong, _vp, _vp, _vp, _i, _i, _vp, _sz, _ll, _i, _vp]),
     "sfc_colsum_scratch_bytes": (_sz, [_ll, _i]),
     "sfc_colsum": (_i, [_vp, _ll, _ll, _i, _vp, _i, _i, _vp, _sz, _vp]),
     "sfc_patch_embed_kpad": (_i, [_i, _i, _i]),

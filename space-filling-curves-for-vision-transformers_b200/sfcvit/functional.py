@@ -119,7 +119,7 @@ class LinearFn(Function):
         d_res = dy if ctx.has_res else None
         g = dy2
         if ctx.act == ACT_RELU:
-            g = ops.act_bwd(dy2, aux, ops.AUX_RELU_MASK, alpha=1.0 / (1.0 - ctx.drop_p) if ctx.drop_p > 0 else 1.0)
+            g = ops.act_bwd(dy2, aux, ops.AUX_RELU_MASK, alpha=ops.drop_inv_keep(ctx.drop_p))
         elif ctx.act == ACT_GELU:
             g = ops.act_bwd(dy2, aux, ops.AUX_GELU_GRAD, drop_p=ctx.drop_p, drop_seed=ctx.seed)
         elif ctx.drop_p > 0:
@@ -154,7 +154,7 @@ class LayerNormFn(Function):
         dy2 = _bf16_act(dy).reshape(x2.shape)
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
-        dx, dg, db = ops.layernorm_bwd(dy2, x2, mean, rstd, gb, ctx.p_dtype)
+        dx, dg, db, _, _ = ops.layernorm_bwd(dy2, x2, mean, rstd, gb, ctx.p_dtype)
         return dx.reshape(ctx.xs), dg, db, None
 
 
@@ -269,28 +269,29 @@ class EncoderLayerFn(Function):
         B, N, D, heads, drops, seed, pdt = ctx.cfg
         p_attn, p_d1, p_ff, p_d2 = drops
         s_attn, s_d1, s_ff, s_d2 = seed, seed + 1, seed + 2, seed + 3
-        inv_keep = 1.0 / (1.0 - p_ff) if p_ff > 0 else 1.0
+        inv_keep = ops.drop_inv_keep(p_ff)
         d2 = _bf16_act(dout).reshape(B * N, D)
         if not d2.is_contiguous():
             d2 = d2.contiguous()
         # LN2
-        dy2, dg2, dbe2 = ops.layernorm_bwd(d2, y2, mean2, rstd2, g2b, pdt)
-        dy2d = ops.act_bwd(dy2, None, ops.AUX_NONE, drop_p=p_d2, drop_seed=s_d2) if p_d2 > 0 else dy2
+        # LN2 backward also emits the dropout2-masked gradient and its column sums (= linear2.bias gradient)
+        dy2, dg2, dbe2, dy2d, db2 = ops.layernorm_bwd(d2, y2, mean2, rstd2, g2b, pdt, drop_p=p_d2, drop_seed=s_d2, want_colsum=True)
+        if dy2d is None:
+            dy2d = dy2
         # linear2 (+ReLU/dropout mask fused into the dgrad epilogue)
         dh = ops.gemm(dy2d, wf2, b_mn=True, aux=h, aux_mode=ops.AUX_RELU_MASK, alpha=inv_keep)
         dw2 = ops.gemm(dy2d, h, a_mn=True, b_mn=True, out_dtype=pdt, splits=0)
-        db2 = ops.colsum(dy2d, pdt)
         # linear1 (+ residual gradient of x1 fused)
         dx1 = ops.gemm(dh, wf1, b_mn=True, residual=dy2)
         dw1 = ops.gemm(dh, x1, a_mn=True, b_mn=True, out_dtype=pdt, splits=0)
         db1 = ops.colsum(dh, pdt)
         # LN1
-        dy1, dg1, dbe1 = ops.layernorm_bwd(dx1, y1, mean1, rstd1, g1b, pdt)
-        dy1d = ops.act_bwd(dy1, None, ops.AUX_NONE, drop_p=p_d1, drop_seed=s_d1) if p_d1 > 0 else dy1
+        dy1, dg1, dbe1, dy1d, dbo = ops.layernorm_bwd(dx1, y1, mean1, rstd1, g1b, pdt, drop_p=p_d1, drop_seed=s_d1, want_colsum=True)
+        if dy1d is None:
+            dy1d = dy1
         # out_proj
         dattn = ops.gemm(dy1d, wo, b_mn=True)
         dwo = ops.gemm(dy1d, attn, a_mn=True, b_mn=True, out_dtype=pdt, splits=0)
-        dbo = ops.colsum(dy1d, pdt)
         # attention
         dqkv = ops.attn_bwd(qkv, attn, dattn, lse, B, heads, N, drop_p=p_attn, drop_seed=s_attn)
         # in_proj (+ residual gradient of x fused)

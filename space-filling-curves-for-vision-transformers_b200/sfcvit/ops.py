@@ -151,24 +151,37 @@ def layernorm_fwd(x, gamma, beta, eps=1e-5, want_stats=True):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, param_dtype=torch.bfloat16):
-    """Returns (dx bf16, dgamma, dbeta) with dgamma/dbeta in param_dtype (bf16 or fp32)."""
+def drop_inv_keep(p):
+    """Exact rescale used by the kernels: keep probability is 1 - floor(p * 65536) / 65536 (csrc/gemm_epilogue.cuh)."""
+    if p <= 0:
+        return 1.0
+    import numpy as np
+    thr = int(np.float32(p) * np.float32(65536.0))
+    return 65536.0 / (65536.0 - thr)
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, param_dtype=torch.bfloat16, *, drop_p=0.0, drop_seed=0, want_colsum=False):
+    """Returns (dx, dgamma, dbeta, dx_drop, colsum): dx_drop is the dropout-masked copy of dx (None when drop_p == 0),
+    colsum the column sums of dx_drop (or dx) in param_dtype (None unless want_colsum)."""
     lib = _lib.load()
     _require_cuda(dy, x, mean, rstd, gamma)
     assert dy.dtype == torch.bfloat16 and dy.is_contiguous() and x.is_contiguous()
     D = x.shape[-1]
     rows = x.numel() // D
     dx = torch.empty_like(x)
+    dxd = torch.empty_like(x) if drop_p > 0 else None
     dgamma = torch.empty(D, dtype=param_dtype, device=x.device)
     dbeta = torch.empty(D, dtype=param_dtype, device=x.device)
+    csum = torch.empty(D, dtype=param_dtype, device=x.device) if want_colsum else None
     nbytes = lib.sfc_layernorm_bwd_scratch_bytes(rows, D)
     scratch = _workspace(nbytes, x.device)
     with torch.cuda.device(x.device):
-        _lib.check(lib.sfc_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dx), _ptr(dgamma),
-                                         _ptr(dbeta), 1 if param_dtype == torch.float32 else 0, 0, _ptr(scratch), nbytes,
+        _lib.check(lib.sfc_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dx), _ptr(dxd),
+                                         float(drop_p), int(drop_seed) & 0xFFFFFFFFFFFFFFFF, _ptr(dgamma), _ptr(dbeta),
+                                         _ptr(csum), 1 if param_dtype == torch.float32 else 0, 0, _ptr(scratch), nbytes,
                                          rows, D, _stream()), "sfc_layernorm_bwd")
-    _count(3)
-    return dx, dgamma, dbeta
+    _count(2)
+    return dx, dgamma, dbeta, dxd, csum
 
 
 def colsum(x, out_dtype=torch.bfloat16):

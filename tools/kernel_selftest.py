@@ -107,11 +107,15 @@ def check_ln(rows=1000, D=768, seed=0):
     bf = beta.float().requires_grad_(True)
     ref = torch.nn.functional.layer_norm(xf, (D,), gf, bf, 1e-5)
     ref.backward(dy.float())
-    dx, dg, db = ops.layernorm_bwd(dy, x, mean, rstd, gamma, torch.float32)
+    dx, dg, db, _, _ = ops.layernorm_bwd(dy, x, mean, rstd, gamma, torch.float32)
+    dx2, _, _, dxd, cs2 = ops.layernorm_bwd(dy, x, mean, rstd, gamma, torch.float32, drop_p=0.25, drop_seed=99, want_colsum=True)
+    ref_d = ops.act_bwd(dx2, None, ops.AUX_NONE, drop_p=0.25, drop_seed=99)
     cs = ops.colsum(dy, torch.float32)
     res = dict(check="ln", rows=rows, D=D, y_rel=rel(y, ref), dx_rel=rel(dx, xf.grad), dg_rel=rel(dg, gf.grad), db_rel=rel(db, bf.grad),
-               colsum_rel=rel(cs, dy.float().sum(0)))
-    res["ok"] = bool(res["y_rel"] < 5e-3 and res["dx_rel"] < 6e-3 and res["dg_rel"] < 1e-3 and res["db_rel"] < 1e-3 and res["colsum_rel"] < 1e-4)
+               colsum_rel=rel(cs, dy.float().sum(0)), fused_drop_rel=rel(dxd, ref_d), fused_csum_rel=rel(cs2, dxd.float().sum(0)),
+               drop_frac=float((dxd == 0).float().mean()))
+    res["ok"] = bool(res["y_rel"] < 5e-3 and res["dx_rel"] < 6e-3 and res["dg_rel"] < 1e-3 and res["db_rel"] < 1e-3 and res["colsum_rel"] < 1e-4
+                     and res["fused_drop_rel"] < 6e-3 and res["fused_csum_rel"] < 2e-3 and 0.2 < res["drop_frac"] < 0.3)
     return res
 
 
