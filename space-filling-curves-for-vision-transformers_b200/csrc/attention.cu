@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
   const int qi = q0 + r;
   const uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, false, false);
   const uint32_t idesc_o = umma_idesc_bf16(BQ, DH, false, true);
+  const DropKey dkey = drop_key(p.drop_seed, p.drop_p);
   ptx::mbar_wait(bar_q, 0);
   for (int j = 0; j < nkv; ++j) {
     const int buf = j & 1;
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
         }
         if (p.drop_p > 0.f) {
           const unsigned long long base = (((unsigned long long)(b * p.H + h) * p.N + (unsigned long long)qi) * p.N) + (unsigned long long)(j * BKV + c * 32);
-          drop_apply<32>(pv, p.drop_seed, base, p.drop_p);
+          drop_apply<32>(pv, dkey, base);
         }
       } else {
 #pragma unroll
@@ -297,8 +298,8 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const __grid_constant__ C
   const uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, false, false);     // S, dP : K-major x K-major
   const uint32_t idesc_t = umma_idesc_bf16(BKV, DH, true, true);       // dV, dK: MN-major A (P^T / dS^T), MN-major B
   const uint32_t idesc_q = umma_idesc_bf16(BQ, DH, false, true);       // dQ    : K-major A (dS), MN-major B (K)
-  const float inv_keep = drop_inv_keep(p.drop_p);
-  const uint32_t thr16 = drop_thr16(p.drop_p);
+  const DropKey dkey = drop_key(p.drop_seed, p.drop_p);
+  const float inv_keep = dkey.inv_keep;
 
   ptx::mbar_wait(bar_kv, 0);
   for (int i = 0; i < nq; ++i) {
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const __grid_constant__ C
         float dp = __uint_as_float(rd[e]);
         float pd = pr;
         if (p.drop_p > 0.f) {
-          const bool keep = drop_keep(p.drop_seed, base + e, thr16);
+          const bool keep = drop_keep(dkey, base + e);
           pd = keep ? pr * inv_keep : 0.f;
           dp = keep ? dp * inv_keep : 0.f;
         }

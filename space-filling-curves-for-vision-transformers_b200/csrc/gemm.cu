@@ -11,21 +11,25 @@
 // kStages-deep TMA->smem ring, a single elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a
 // double-buffered TMEM accumulator (2 x BN columns) so that the epilogue warps (TMEM -> registers ->
 // bias / activation / residual / mask -> global) of tile i overlap the main loop of tile i+1.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..11 = epilogue (coalesced through a per-warp
+// smem transpose stage, see gemm_epilogue.cuh).
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
 #include "sfcvit.h"
+#include <stdlib.h>
 
 namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kNumThreads = 256;
-constexpr int kEpiThreads = 128;
+constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kNumThreads = 128 + kEpiThreads;
 
 struct GemmParams {
   int M, N, K;
   int num_m_tiles, num_n_tiles, splits, kblocks_per_split, num_k_blocks;
+  int debug;   // SFC_GEMM_DEBUG (timing experiments only): 1 = skip epilogue body, 2 = skip TMA + MMA
   EpiParams epi;
 };
 
@@ -34,11 +38,13 @@ struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kEpiOffset = kStages * kStageBytes;          // per-epilogue-warp transpose stage
+  static constexpr int kBarOffset = kEpiOffset + kEpiWarps * kEpiStageBytes;
   static constexpr int kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16 + 1024 /*alignment slack*/;
+  static_assert(kTotal <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
 };
 
-template <int BN, int kStages, bool A_MN, bool B_MN>
+template <int BN, int kStages, bool A_MN, bool B_MN, bool FAST_EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
   using L = SmemLayout<BN, kStages, A_MN, B_MN>;
@@ -76,7 +82,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (ptx::elect_one()) {
+    if (p.debug != 2 && ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -129,6 +135,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
+        if (p.debug == 2) { ptx::umma_commit(&tmem_full[acc]); continue; }
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
@@ -147,10 +154,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ===================== epilogue (4 warps, thread <-> accumulator row) =====================
-    const int ewarp = warp - 4;                    // == warp % 4 : TMEM lane quarter
-    const int lane = threadIdx.x & 31;
-    const int row_in_tile = ewarp * 32 + lane;
+    // ===================== epilogue (8 warps: lane quarter = warp % 4, column half = (warp - 4) / 4) =====================
+    const int quarter = warp & 3;
+    const int half = (warp - 4) >> 2;
+    uint8_t* stage = smem + L::kEpiOffset + (warp - 4) * kEpiStageBytes;
     int iter = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
       const int split = t % p.splits;
@@ -161,10 +168,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t acc_phase = (iter >> 1) & 1;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
-      const long long m = (long long)m_tile * BM + row_in_tile;
-      const bool row_ok = m < p.M;
-      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(ewarp * 32) << 16);
-      epi_tile<BN>(p.epi, taddr, n_tile * BN, m, m, row_ok, split);
+      const uint32_t taddr = tmem_base + acc * BN + half * (BN / 2) + ((uint32_t)(quarter * 32) << 16);
+      if (p.debug != 1) {
+        if constexpr (FAST_EPI)
+          epi_tile_fast(p.epi, taddr, n_tile * BN + half * (BN / 2), BN / 2, (long long)m_tile * BM + quarter * 32, (long long)p.M,
+                        EpiRowIdentity{}, split, stage);
+        else
+          epi_tile(p.epi, taddr, n_tile * BN + half * (BN / 2), BN / 2, (long long)m_tile * BM + quarter * 32, (long long)p.M,
+                   EpiRowIdentity{}, split, stage);
+      }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
     }
@@ -196,10 +208,10 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, long long spl
   }
 }
 
-template <int BN, int kStages, bool A_MN, bool B_MN>
+template <int BN, int kStages, bool A_MN, bool B_MN, bool FAST_EPI>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using L = SmemLayout<BN, kStages, A_MN, B_MN>;
-  auto kern = gemm_bf16_kernel<BN, kStages, A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<BN, kStages, A_MN, B_MN, FAST_EPI>;
   static bool configured = false;
   if (!configured) {
     SFC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -243,6 +255,8 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
   const int BN = (N > 128) ? 256 : 128;
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
+  static const int debug_mode = getenv("SFC_GEMM_DEBUG") ? atoi(getenv("SFC_GEMM_DEBUG")) : 0;
+  p.debug = debug_mode;
   p.num_m_tiles = sfc_ceil_div(M, BM);
   p.num_n_tiles = sfc_ceil_div(N, BN);
   p.num_k_blocks = sfc_ceil_div(K, BK);
@@ -284,14 +298,20 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
   else             { if (int e = sfc_make_tmap_2d(&tb, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, BK, true)) return e; }
 
   int rc = 0;
+  const bool fast = epi_fast_ok(pk.epi);
+#define SFC_DISPATCH2(BN_, ST_, F_)                                                             \
+  do {                                                                                          \
+    if (!a_mn_major && !b_mn_major) rc = launch_gemm<BN_, ST_, false, false, F_>(ta, tb, pk, stream); \
+    else if (!a_mn_major && b_mn_major) rc = launch_gemm<BN_, ST_, false, true, F_>(ta, tb, pk, stream); \
+    else if (a_mn_major && b_mn_major) rc = launch_gemm<BN_, ST_, true, true, F_>(ta, tb, pk, stream);  \
+    else rc = launch_gemm<BN_, ST_, true, false, F_>(ta, tb, pk, stream);                        \
+  } while (0)
 #define SFC_DISPATCH(BN_, ST_)                                                              \
   do {                                                                                      \
-    if (!a_mn_major && !b_mn_major) rc = launch_gemm<BN_, ST_, false, false>(ta, tb, pk, stream); \
-    else if (!a_mn_major && b_mn_major) rc = launch_gemm<BN_, ST_, false, true>(ta, tb, pk, stream); \
-    else if (a_mn_major && b_mn_major) rc = launch_gemm<BN_, ST_, true, true>(ta, tb, pk, stream);  \
-    else rc = launch_gemm<BN_, ST_, true, false>(ta, tb, pk, stream);                        \
+    if (fast) SFC_DISPATCH2(BN_, ST_, true); else SFC_DISPATCH2(BN_, ST_, false);           \
   } while (0)
   if (BN == 256) SFC_DISPATCH(256, 4); else SFC_DISPATCH(128, 6);
+#undef SFC_DISPATCH2
 #undef SFC_DISPATCH
   if (rc) return rc;
 

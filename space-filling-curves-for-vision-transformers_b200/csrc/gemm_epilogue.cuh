@@ -1,10 +1,11 @@
-// Shared GEMM epilogue (used by gemm.cu and patch_embed.cu): 32 consecutive accumulator columns of one
-// output row are finished in registers and written to global memory.
+// Shared GEMM epilogue (used by gemm.cu and patch_embed.cu).
 // order: *alpha -> +bias[n] -> (store out_pre) -> act -> dropout -> aux (relu mask / gelu') -> +residual -> store
 //
-// The global operands of a chunk (bias / residual / aux, 64 B each per row) are fetched by epi_prefetch() one chunk
-// AHEAD of their use, so that their latency overlaps the TMEM load + math + stores of the previous chunk (the
-// epilogue has only one warp per SM sub-partition, i.e. no other warp to hide a dependent global load behind).
+// tcgen05.ld hands every lane one accumulator ROW (32 columns of it per chunk); writing global memory in that
+// mapping touches 32 different 128-byte lines per instruction and made the epilogue, not the tensor pipe, the
+// limiter of the K = 768 GEMMs. Each chunk is therefore transposed through a 4 KB per-warp shared-memory stage and
+// finished in a mapping where 4 adjacent lanes cover 64 contiguous bytes of one output row, so residual / aux loads
+// and all stores are sector-coalesced. The operands of chunk c+1 are fetched while chunk c is finished.
 #pragma once
 #include "common.cuh"
 #include "sfcvit.h"
@@ -26,11 +27,6 @@ struct EpiParams {
   unsigned long long drop_seed;
 };
 
-struct EpiRegs {                  // raw bf16x8 vectors of one 32-column chunk
-  uint4 bias[4], res[4], aux[4];
-  bool bias_vec, res_vec, aux_vec;   // operand was prefetched with vector loads (else: scalar path at use time)
-};
-
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
@@ -38,38 +34,57 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
-// Counter-based dropout (same decisions in forward and backward, no mask tensor): one splitmix64 hash of
-// (seed, index >> 2) yields four 16-bit uniform lanes; element `index` is kept iff its lane >= thr16 = p * 65536.
-// The keep probability is exactly 1 - thr16 / 65536, and that value (not the nominal p) is used for the rescale.
-__device__ __forceinline__ unsigned long long drop_hash4(unsigned long long seed, unsigned long long group) {
-  unsigned long long z = seed + group * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
-}
+// Counter-based dropout (same decisions in forward and backward, no mask tensor). The 64-bit seed is mixed once per
+// thread (splitmix64) into two 32-bit keys; one 32-bit multiply-xorshift hash of (keys, index >> 1) then yields two
+// 16-bit uniform lanes, and element `index` is kept iff its lane >= thr16 = floor(p * 65536). The keep probability is
+// exactly 1 - thr16 / 65536, and that value (not the nominal p) is used for the rescale.
+struct DropKey {
+  uint32_t s0, s1, thr16;
+  float inv_keep;
+};
 __device__ __forceinline__ uint32_t drop_thr16(float p) { return (uint32_t)(p * 65536.0f); }
 __device__ __forceinline__ float drop_inv_keep(float p) {
   return p > 0.f ? 65536.0f / (65536.0f - (float)drop_thr16(p)) : 1.0f;
 }
-__device__ __forceinline__ bool drop_keep(unsigned long long seed, unsigned long long idx, uint32_t thr16) {
-  const unsigned long long h = drop_hash4(seed, idx >> 2);
-  return ((uint32_t)(h >> (16 * (uint32_t)(idx & 3))) & 0xffffu) >= thr16;
+__device__ __forceinline__ DropKey drop_key(unsigned long long seed, float p) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  DropKey k;
+  k.s0 = (uint32_t)z;
+  k.s1 = (uint32_t)(z >> 32);
+  k.thr16 = drop_thr16(p);
+  k.inv_keep = drop_inv_keep(p);
+  return k;
 }
-// v[i] = keep(base + i) ? v[i] * inv_keep : 0 for NV consecutive elements (NV % 4 == 0)
+__device__ __forceinline__ uint32_t drop_hash2(const DropKey& k, unsigned long long pair) {
+  uint32_t x = ((uint32_t)pair ^ k.s0) * 0x9E3779B1u;
+  x ^= x >> 15;
+  x = (x + (uint32_t)(pair >> 32) * 0x632BE5ABu + k.s1) * 0x85EBCA77u;
+  x ^= x >> 13;
+  x *= 0xC2B2AE3Du;
+  x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ bool drop_keep(const DropKey& k, unsigned long long idx) {
+  const uint32_t h = drop_hash2(k, idx >> 1);
+  return ((idx & 1ull) ? (h >> 16) : (h & 0xffffu)) >= k.thr16;
+}
+// v[i] = keep(base + i) ? v[i] * inv_keep : 0 for NV consecutive elements (NV even)
 template <int NV>
-__device__ __forceinline__ void drop_apply(float* v, unsigned long long seed, unsigned long long base, float p) {
-  const uint32_t thr = drop_thr16(p);
-  const float sc = drop_inv_keep(p);
-  if ((base & 3ull) == 0) {
+__device__ __forceinline__ void drop_apply(float* v, const DropKey& k, unsigned long long base) {
+  if ((base & 1ull) == 0) {
+    const uint32_t thr_hi = k.thr16 << 16;
 #pragma unroll
-    for (int g = 0; g < NV / 4; ++g) {
-      const unsigned long long h = drop_hash4(seed, (base >> 2) + g);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) v[g * 4 + k] = (((uint32_t)(h >> (16 * k)) & 0xffffu) >= thr) ? v[g * 4 + k] * sc : 0.f;
+    for (int g = 0; g < NV / 2; ++g) {
+      const uint32_t h = drop_hash2(k, (base >> 1) + g);
+      v[2 * g] = ((h << 16) >= thr_hi) ? v[2 * g] * k.inv_keep : 0.f;
+      v[2 * g + 1] = (h >= thr_hi) ? v[2 * g + 1] * k.inv_keep : 0.f;    // low bits of h only break ties inside one lane value
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = drop_keep(seed, base + i, thr) ? v[i] * sc : 0.f;
+    for (int i = 0; i < NV; ++i) v[i] = drop_keep(k, base + i) ? v[i] * k.inv_keep : 0.f;
   }
 }
 
@@ -77,162 +92,315 @@ __device__ __forceinline__ void epi_unpack8(const uint4& b, float* f) {
   f[0] = ptx::bf16_lo(b.x); f[1] = ptx::bf16_hi(b.x); f[2] = ptx::bf16_lo(b.y); f[3] = ptx::bf16_hi(b.y);
   f[4] = ptx::bf16_lo(b.z); f[5] = ptx::bf16_hi(b.z); f[6] = ptx::bf16_lo(b.w); f[7] = ptx::bf16_hi(b.w);
 }
+__device__ __forceinline__ uint4 epi_pack8(const float* v) {
+  uint4 o;
+  o.x = ptx::pack_bf16(v[0], v[1]); o.y = ptx::pack_bf16(v[2], v[3]);
+  o.z = ptx::pack_bf16(v[4], v[5]); o.w = ptx::pack_bf16(v[6], v[7]);
+  return o;
+}
+__device__ __forceinline__ bool epi_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// Issues the global loads of chunk n0 (no use of the results here).
-__device__ __forceinline__ void epi_prefetch(const EpiParams& p, EpiRegs& r, long long m_out, long long m_res, int n0, bool row_ok) {
-  const bool full = row_ok && (n0 + 32 <= p.N);
-  r.bias_vec = full && p.bias && ((reinterpret_cast<uintptr_t>(p.bias + n0) & 15) == 0);
-  r.res_vec = full && p.residual && (p.ld_res % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
-  r.aux_vec = full && p.aux_mode != SFC_AUX_NONE && (p.ld_aux % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
-  if (r.bias_vec) {
-    const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
+// Row mapping of a tile row (global accumulator row m) to the row of out / out_pre / aux (m_out) and of the
+// residual (m_res). GEMM: identity. Patch embed: image-major output rows with a token offset, residual = pos[token].
+struct EpiRowIdentity {
+  __device__ __forceinline__ void map(long long m, long long& m_out, long long& m_res) const { m_out = m; m_res = m; }
+};
+
+// Per-tile, per-lane state of the transposed mapping: lane l owns, for it = 0..3, the 8 consecutive columns
+// (l & 3) * 8 .. +7 of tile row it * 8 + (l >> 2) of every 32-column chunk.
+struct EpiLane {
+  long long m_out[4], m_res[4];
+  bool ok[4];
+  bool bias_vec, res_vec, aux_vec, out_vec, pre_vec;
+  DropKey dkey;
+};
+
+struct EpiOps {                    // prefetched global operands of one 32-column chunk (vector path only)
+  uint4 bias, res[4], aux[4];
+};
+
+__device__ __forceinline__ void epi_prefetch(const EpiParams& p, const EpiLane& L, EpiOps& o, int n, bool full) {
+  if (!full) return;
+  if (L.bias_vec) o.bias = __ldg(reinterpret_cast<const uint4*>(p.bias + n));
 #pragma unroll
-    for (int q = 0; q < 4; ++q) r.bias[q] = __ldg(bp + q);
-  }
-  if (r.res_vec) {
-    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m_res * p.ld_res + n0);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) r.res[q] = __ldg(rp + q);
-  }
-  if (r.aux_vec) {
-    const uint4* ap = reinterpret_cast<const uint4*>(p.aux + m_out * p.ld_aux + n0);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) r.aux[q] = __ldg(ap + q);
+  for (int it = 0; it < 4; ++it) {
+    if (L.res_vec && L.ok[it]) o.res[it] = __ldg(reinterpret_cast<const uint4*>(p.residual + L.m_res[it] * p.ld_res + n));
+    if (L.aux_vec && L.ok[it]) o.aux[it] = __ldg(reinterpret_cast<const uint4*>(p.aux + L.m_out[it] * p.ld_aux + n));
   }
 }
 
-// v[32]: raw accumulators of columns n0..n0+31 of one row. m_out: row in out / out_pre / aux; m_res: row in residual.
-__device__ __forceinline__ void epi_apply_store(const EpiParams& p, float (&v)[32], const EpiRegs& r, long long m_out, long long m_res,
-                                                int n0, int split) {
+// Finishes 8 consecutive columns n .. n+7 (nvalid of them inside N) of output row m_out and stores them.
+__device__ __forceinline__ void epi_apply_store8(const EpiParams& p, const EpiLane& L, const EpiOps& o, int it, float (&v)[8], int n,
+                                                 int nvalid, bool full, int split) {
+  const long long m_out = L.m_out[it], m_res = L.m_res[it];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
-  const bool full = (n0 + 32 <= p.N);
+  for (int j = 0; j < 8; ++j) v[j] *= p.alpha;
   if (p.bias) {
-    if (r.bias_vec) {
+    if (L.bias_vec && full) {
+      float f[8];
+      epi_unpack8(o.bias, f);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float f[8];
-        epi_unpack8(r.bias[q], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[q * 8 + j] += f[j];
-      }
+      for (int j = 0; j < 8; ++j) v[j] += f[j];
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < p.N) v[j] += __bfloat162float(p.bias[n0 + j]);
+      for (int j = 0; j < 8; ++j)
+        if (j < nvalid) v[j] += __bfloat162float(p.bias[n + j]);
     }
   }
-  const bool out_vec = full && (p.ld_out % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
   if (p.out_pre) {
-    __nv_bfloat16* op = p.out_pre + m_out * p.ld_out + n0;
-    if (out_vec && ((reinterpret_cast<uintptr_t>(p.out_pre) & 15) == 0)) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 o;
-        o.x = ptx::pack_bf16(v[q * 8 + 0], v[q * 8 + 1]); o.y = ptx::pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-        o.z = ptx::pack_bf16(v[q * 8 + 4], v[q * 8 + 5]); o.w = ptx::pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-        reinterpret_cast<uint4*>(op)[q] = o;
-      }
+    __nv_bfloat16* op = p.out_pre + m_out * p.ld_out + n;
+    if (L.pre_vec && full) {
+      *reinterpret_cast<uint4*>(op) = epi_pack8(v);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < p.N) op[j] = __float2bfloat16(v[j]);
+      for (int j = 0; j < 8; ++j)
+        if (j < nvalid) op[j] = __float2bfloat16(v[j]);
     }
   }
   if (p.act == SFC_ACT_RELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
   } else if (p.act == SFC_ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
   }
   if (p.drop_p > 0.0f)
-    drop_apply<32>(v, p.drop_seed, (unsigned long long)m_out * (unsigned long long)p.N + (unsigned long long)n0, p.drop_p);
+    drop_apply<8>(v, L.dkey, (unsigned long long)m_out * (unsigned long long)p.N + (unsigned long long)n);
   if (p.aux_mode != SFC_AUX_NONE) {
-    float a[32];
-    if (r.aux_vec) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) epi_unpack8(r.aux[q], a + q * 8);
+    float a[8];
+    if (L.aux_vec && full) {
+      epi_unpack8(o.aux[it], a);
     } else {
-      const __nv_bfloat16* ap = p.aux + m_out * p.ld_aux + n0;
+      const __nv_bfloat16* ap = p.aux + m_out * p.ld_aux + n;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) a[j] = (n0 + j < p.N) ? __bfloat162float(ap[j]) : 0.0f;
+      for (int j = 0; j < 8; ++j) a[j] = (j < nvalid) ? __bfloat162float(ap[j]) : 0.0f;
     }
     if (p.aux_mode == SFC_AUX_RELU_MASK) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = a[j] > 0.0f ? v[j] : 0.0f;
+      for (int j = 0; j < 8; ++j) v[j] = a[j] > 0.0f ? v[j] : 0.0f;
     } else {  // SFC_AUX_GELU_GRAD: aux holds the pre-activation
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(a[j]);
+      for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(a[j]);
     }
   }
   if (p.residual) {
-    if (r.res_vec) {
+    if (L.res_vec && full) {
+      float f[8];
+      epi_unpack8(o.res[it], f);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float f[8];
-        epi_unpack8(r.res[q], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[q * 8 + j] += f[j];
-      }
+      for (int j = 0; j < 8; ++j) v[j] += f[j];
     } else {
-      const __nv_bfloat16* rp = p.residual + m_res * p.ld_res + n0;
+      const __nv_bfloat16* rp = p.residual + m_res * p.ld_res + n;
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < p.N) v[j] += __bfloat162float(rp[j]);
+      for (int j = 0; j < 8; ++j)
+        if (j < nvalid) v[j] += __bfloat162float(rp[j]);
     }
   }
   if (p.out_fp32) {
-    float* op = reinterpret_cast<float*>(p.out) + (long long)split * p.split_stride + m_out * p.ld_out + n0;
-    if (full && (p.ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && (p.split_stride % 4 == 0)) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        reinterpret_cast<float4*>(op)[q] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+    float* op = reinterpret_cast<float*>(p.out) + (long long)split * p.split_stride + m_out * p.ld_out + n;
+    if (L.out_vec && full) {
+      reinterpret_cast<float4*>(op)[0] = make_float4(v[0], v[1], v[2], v[3]);
+      reinterpret_cast<float4*>(op)[1] = make_float4(v[4], v[5], v[6], v[7]);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < p.N) op[j] = v[j];
+      for (int j = 0; j < 8; ++j)
+        if (j < nvalid) op[j] = v[j];
     }
   } else {
-    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + m_out * p.ld_out + n0;
-    if (out_vec) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 o;
-        o.x = ptx::pack_bf16(v[q * 8 + 0], v[q * 8 + 1]); o.y = ptx::pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-        o.z = ptx::pack_bf16(v[q * 8 + 4], v[q * 8 + 5]); o.w = ptx::pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-        reinterpret_cast<uint4*>(op)[q] = o;
-      }
+    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + m_out * p.ld_out + n;
+    if (L.out_vec && full) {
+      *reinterpret_cast<uint4*>(op) = epi_pack8(v);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < p.N) op[j] = __float2bfloat16(v[j]);
+      for (int j = 0; j < 8; ++j)
+        if (j < nvalid) op[j] = __float2bfloat16(v[j]);
     }
   }
 }
 
-// Shared driver of the epilogue of one 128-row x BN-column accumulator tile: walks the column chunks with the
-// operands of chunk c+1 in flight while chunk c is finished. `taddr` = TMEM address of this thread's lane, column 0.
-template <int BN>
-__device__ __forceinline__ void epi_tile(const EpiParams& p, uint32_t taddr, int n_base, long long m_out, long long m_res, bool row_ok,
-                                         int split) {
-  EpiRegs cur, nxt;
-  epi_prefetch(p, cur, m_out, m_res, n_base, row_ok && n_base < p.N);
+constexpr int kEpiStageBytes = 4096;   // per epilogue warp: 32 rows x 32 fp32, 16-byte chunks XOR-swizzled by (row & 7)
+
+// Epilogue of one warp's share of an accumulator tile: TMEM lanes [quarter*32, +32) (the warp's lane quarter; `taddr`
+// already carries the lane offset and the first column), columns [n_begin, n_begin + ncols) of the output, global
+// accumulator rows m_base .. m_base+31. Each 32-column chunk is read from TMEM with one row per lane, transposed
+// through the warp's private smem stage, and finished in a mapping where 4 adjacent lanes cover 64 contiguous bytes of
+// one output row (8 rows per instruction): global loads of residual / aux and the stores are sector-coalesced.
+// The global operands of chunk c+1 are in flight while chunk c is finished.
+template <class RowMap>
+__device__ __forceinline__ void epi_tile(const EpiParams& p, uint32_t taddr, int n_begin, int ncols, long long m_base, long long M,
+                                         const RowMap& rm, int split, uint8_t* stage) {
+  const int lane = (int)(threadIdx.x & 31);
+  const int cg = lane & 3, rsub = lane >> 2;
+  EpiLane L;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const long long m = m_base + it * 8 + rsub;
+    L.ok[it] = m < M;
+    rm.map(L.ok[it] ? m : 0, L.m_out[it], L.m_res[it]);
+  }
+  L.bias_vec = p.bias && epi_al16(p.bias);
+  L.res_vec = p.residual && (p.ld_res % 8 == 0) && epi_al16(p.residual);
+  L.aux_vec = p.aux_mode != SFC_AUX_NONE && (p.ld_aux % 8 == 0) && epi_al16(p.aux);
+  L.out_vec = p.out_fp32 ? ((p.ld_out % 4 == 0) && epi_al16(p.out) && (p.split_stride % 4 == 0))
+                         : ((p.ld_out % 8 == 0) && epi_al16(p.out));
+  L.pre_vec = p.out_pre && (p.ld_out % 8 == 0) && epi_al16(p.out_pre);
+  L.dkey = drop_key(p.drop_seed, p.drop_p);
+  if (n_begin >= p.N) return;
+  EpiOps cur, nxt;
+  epi_prefetch(p, L, cur, n_begin + cg * 8, n_begin + 32 <= p.N);
+  const int nchunks = ncols / 32;
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
-    const int n0 = n_base + c * 32;
+  for (int c = 0; c < nchunks; ++c) {
+    const int n0 = n_begin + c * 32;
     if (n0 >= p.N) break;                      // warp-uniform
     uint32_t raw[32];
     ptx::tmem_ld_x32(taddr + c * 32, raw);
-    const bool more = (c + 1 < BN / 32) && (n0 + 32 < p.N);
-    if (more) epi_prefetch(p, nxt, m_out, m_res, n0 + 32, row_ok);
+    const bool more = (c + 1 < nchunks) && (n0 + 32 < p.N);
+    if (more) epi_prefetch(p, L, nxt, n0 + 32 + cg * 8, n0 + 64 <= p.N);
     ptx::tmem_ld_wait();
-    if (row_ok) {
-      float v[32];
+    {
+      uint8_t* srow = stage + lane * 128;
+      const int sw = lane & 7;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-      epi_apply_store(p, v, cur, m_out, m_res, n0, split);
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<uint4*>(srow + ((q ^ sw) << 4)) = make_uint4(raw[q * 4 + 0], raw[q * 4 + 1], raw[q * 4 + 2], raw[q * 4 + 3]);
     }
+    __syncwarp();
+    const bool full = n0 + 32 <= p.N;
+    const int n = n0 + cg * 8;
+    const int nvalid = p.N - n;                // may be <= 0 or > 8
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + rsub;
+      const uint8_t* srow = stage + r * 128;
+      const uint4 lo = *reinterpret_cast<const uint4*>(srow + (((2 * cg) ^ (r & 7)) << 4));
+      const uint4 hi = *reinterpret_cast<const uint4*>(srow + (((2 * cg + 1) ^ (r & 7)) << 4));
+      if (L.ok[it] && nvalid > 0) {
+        float v[8] = {__uint_as_float(lo.x), __uint_as_float(lo.y), __uint_as_float(lo.z), __uint_as_float(lo.w),
+                      __uint_as_float(hi.x), __uint_as_float(hi.y), __uint_as_float(hi.z), __uint_as_float(hi.w)};
+        epi_apply_store8(p, L, cur, it, v, n, nvalid, full, split);
+      }
+    }
+    __syncwarp();                              // stage is rewritten by the next chunk
     if (more) cur = nxt;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Lean variant for the encoder's hot GEMMs. Preconditions (checked on the host by epi_fast_ok): every 32-column chunk
+// is full (N % 32 == 0), all operands 16-byte aligned with vectorisable leading dimensions, no pre-activation copy,
+// activation in {none, ReLU}, aux in {none, ReLU mask}. Per-lane row pointers and all feature predicates are hoisted
+// out of the chunk loop; bias is folded into one FFMA per element.
+// ------------------------------------------------------------------------------------------------------------------
+inline bool epi_fast_ok(const EpiParams& p) {
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (p.N % 32 != 0 || p.out_pre) return false;
+  if (p.act != SFC_ACT_NONE && p.act != SFC_ACT_RELU) return false;
+  if (p.aux_mode != SFC_AUX_NONE && p.aux_mode != SFC_AUX_RELU_MASK) return false;
+  if (p.bias && !al(p.bias)) return false;
+  if (p.residual && (!al(p.residual) || p.ld_res % 8 != 0)) return false;
+  if (p.aux_mode != SFC_AUX_NONE && (!al(p.aux) || p.ld_aux % 8 != 0)) return false;
+  if (!al(p.out)) return false;
+  if (p.out_fp32) return p.ld_out % 4 == 0 && p.split_stride % 4 == 0;
+  return p.ld_out % 8 == 0;
+}
+
+template <class RowMap>
+__device__ __forceinline__ void epi_tile_fast(const EpiParams& p, uint32_t taddr, int n_begin, int ncols, long long m_base, long long M,
+                                              const RowMap& rm, int split, uint8_t* stage) {
+  const int lane = (int)(threadIdx.x & 31);
+  const int cg = lane & 3, rsub = lane >> 2;
+  const bool has_bias = p.bias != nullptr, has_res = p.residual != nullptr, has_aux = p.aux_mode != SFC_AUX_NONE;
+  const bool has_drop = p.drop_p > 0.0f, f32 = p.out_fp32 != 0;
+  const float relu_lo = p.act == SFC_ACT_RELU ? 0.0f : -INFINITY;
+  const float alpha = p.alpha;
+  const DropKey dkey = drop_key(p.drop_seed, p.drop_p);
+  // per-lane row state: byte pointers at column n_begin + cg * 8 of rows it * 8 + rsub
+  const char* resp[4];
+  const char* auxp[4];
+  char* outp[4];
+  unsigned long long didx[4];
+  bool ok[4];
+  const int ncol0 = n_begin + cg * 8;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const long long m = m_base + it * 8 + rsub;
+    ok[it] = m < M;
+    long long m_out, m_res;
+    rm.map(ok[it] ? m : 0, m_out, m_res);
+    resp[it] = reinterpret_cast<const char*>(p.residual) + (m_res * p.ld_res + ncol0) * 2;
+    auxp[it] = reinterpret_cast<const char*>(p.aux) + (m_out * p.ld_aux + ncol0) * 2;
+    outp[it] = reinterpret_cast<char*>(p.out) + (f32 ? ((long long)split * p.split_stride + m_out * p.ld_out + ncol0) * 4
+                                                      : (m_out * p.ld_out + ncol0) * 2);
+    didx[it] = (unsigned long long)m_out * (unsigned long long)p.N + (unsigned long long)ncol0;
+  }
+  const char* biasp = reinterpret_cast<const char*>(p.bias) + ncol0 * 2;
+  uint4 cb = make_uint4(0, 0, 0, 0), cr[4], ca[4], nb = cb, nr[4], na[4];
+  auto prefetch = [&](int coff, uint4& b, uint4 (&r)[4], uint4 (&a)[4]) {     // coff: column offset from n_begin
+    if (has_bias) b = __ldg(reinterpret_cast<const uint4*>(biasp + coff * 2));
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      if (has_res && ok[it]) r[it] = __ldg(reinterpret_cast<const uint4*>(resp[it] + coff * 2));
+      if (has_aux && ok[it]) a[it] = __ldg(reinterpret_cast<const uint4*>(auxp[it] + coff * 2));
+    }
+  };
+  prefetch(0, cb, cr, ca);
+  const int nchunks = ncols / 32;
+  uint8_t* swrite = stage + lane * 128;
+  const int sw = lane & 7;
+#pragma unroll 1
+  for (int c = 0; c < nchunks; ++c) {
+    const int coff = c * 32;
+    if (n_begin + coff >= p.N) break;          // warp-uniform
+    uint32_t raw[32];
+    ptx::tmem_ld_x32(taddr + coff, raw);
+    const bool more = (c + 1 < nchunks) && (n_begin + coff + 32 < p.N);
+    if (more) prefetch(coff + 32, nb, nr, na);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<uint4*>(swrite + ((q ^ sw) << 4)) = make_uint4(raw[q * 4 + 0], raw[q * 4 + 1], raw[q * 4 + 2], raw[q * 4 + 3]);
+    __syncwarp();
+    float bf[8];
+    epi_unpack8(cb, bf);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + rsub;
+      const uint8_t* srow = stage + r * 128;
+      const uint4 lo = *reinterpret_cast<const uint4*>(srow + (((2 * cg) ^ (r & 7)) << 4));
+      const uint4 hi = *reinterpret_cast<const uint4*>(srow + (((2 * cg + 1) ^ (r & 7)) << 4));
+      if (ok[it]) {
+        float v[8] = {__uint_as_float(lo.x), __uint_as_float(lo.y), __uint_as_float(lo.z), __uint_as_float(lo.w),
+                      __uint_as_float(hi.x), __uint_as_float(hi.y), __uint_as_float(hi.z), __uint_as_float(hi.w)};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], alpha, bf[j]), relu_lo);
+        if (has_drop) drop_apply<8>(v, dkey, didx[it] + (unsigned long long)coff);
+        if (has_aux) {
+          float a[8];
+          epi_unpack8(ca[it], a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = a[j] > 0.0f ? v[j] : 0.0f;
+        }
+        if (has_res) {
+          float f[8];
+          epi_unpack8(cr[it], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += f[j];
+        }
+        if (f32) {
+          float4* op = reinterpret_cast<float4*>(outp[it] + coff * 4);
+          op[0] = make_float4(v[0], v[1], v[2], v[3]);
+          op[1] = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+          *reinterpret_cast<uint4*>(outp[it] + coff * 2) = epi_pack8(v);
+        }
+      }
+    }
+    __syncwarp();                              // stage is rewritten by the next chunk
+    if (more) {
+      cb = nb;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) { cr[it] = nr[it]; ca[it] = na[it]; }
+    }
   }
 }

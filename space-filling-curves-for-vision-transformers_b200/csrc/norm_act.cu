@@ -99,6 +99,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      __nv_bfloat16* __restrict__ dx_drop, float drop_p, unsigned long long drop_seed,
                      float* __restrict__ part, long long rows, int D) {
   extern __shared__ float sred[];            // [kLnWarps][3][D]
+  const DropKey dkey = drop_key(drop_seed, drop_p);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nvec = D >> 3;
   float dg[NV][8], db[NV][8], cs[CSUM ? NV : 1][8];
@@ -154,7 +155,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         }
         dxr[vi] = pack8(o);
         if (DROP) {
-          drop_apply<8>(o, drop_seed, (unsigned long long)row * (unsigned long long)D + (unsigned long long)(vi * 8), drop_p);
+          drop_apply<8>(o, dkey, (unsigned long long)row * (unsigned long long)D + (unsigned long long)(vi * 8));
           reinterpret_cast<uint4*>(dx_drop + row * D)[vi] = pack8(o);
         }
         if (CSUM) {
@@ -276,6 +277,7 @@ __global__ void __launch_bounds__(256) partial_finalize_kernel(const float* __re
 __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ aux,
                                                       __nv_bfloat16* __restrict__ out, long long nvec, int mode, float alpha,
                                                       float drop_p, unsigned long long seed) {
+  const DropKey dkey = drop_key(seed, drop_p);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     float d[8], a[8], o[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(dy) + i), d);
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __res
       }
       o[j] = v;
     }
-    if (drop_p > 0.f) drop_apply<8>(o, seed, (unsigned long long)i * 8ull, drop_p);
+    if (drop_p > 0.f) drop_apply<8>(o, dkey, (unsigned long long)i * 8ull);
     reinterpret_cast<uint4*>(out)[i] = pack8(o);
   }
 }

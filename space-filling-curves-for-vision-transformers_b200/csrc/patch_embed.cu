@@ -41,8 +41,20 @@ struct PeSmem {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kEpiOffset = kStages * kStageBytes;          // 4 epilogue warps x transpose stage
+  static constexpr int kBarOffset = kEpiOffset + 4 * kEpiStageBytes;
   static constexpr int kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16 + 1024;
+  static_assert(kTotal <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
+};
+
+// accumulator row m = image * ntok + token  ->  output row (image-major, token offset) and position-embedding row
+struct PeRowMap {
+  int ntok, rows_per_img, tok_off;
+  __device__ __forceinline__ void map(long long m, long long& m_out, long long& m_res) const {
+    const long long bimg = m / ntok, tok = m % ntok;
+    m_out = bimg * rows_per_img + tok_off + tok;
+    m_res = tok;
+  }
 };
 
 __device__ __forceinline__ uint4 pack8f(const float* f) {
@@ -235,8 +247,8 @@ patch_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchPa
   } else if (warp >= 4 && warp < 8) {
     // ===================== epilogue =====================
     const int ewarp = warp - 4;
-    const int lane = threadIdx.x & 31;
-    const int row_in_tile = ewarp * 32 + lane;
+    uint8_t* stage = smem + L::kEpiOffset + ewarp * kEpiStageBytes;
+    PeRowMap rm{pp.ntok, pp.rows_per_img, pp.tok_off};
     int iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const int n_tile = tile % pp.num_n_tiles;
@@ -245,13 +257,8 @@ patch_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchPa
       const uint32_t acc_phase = (iter >> 1) & 1;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
-      const long long m = (long long)m_tile * BM + row_in_tile;
-      const bool row_ok = m < pp.M;
-      const long long bimg = row_ok ? m / pp.ntok : 0;
-      const long long tok = row_ok ? m % pp.ntok : 0;
-      const long long out_row = bimg * pp.rows_per_img + pp.tok_off + tok;
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(ewarp * 32) << 16);
-      epi_tile<BN>(pp.epi, taddr, n_tile * BN, out_row, tok, row_ok, 0);
+      epi_tile(pp.epi, taddr, n_tile * BN, BN, (long long)m_tile * BM + ewarp * 32, pp.M, rm, 0, stage);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
     }
