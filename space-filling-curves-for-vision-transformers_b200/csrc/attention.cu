@@ -16,7 +16,7 @@
 // core, P / dS in registers -> shared memory, dV += P^T dO, dK += dS^T Q (MN-major A operands, accumulators
 // resident in TMEM across the loop) and dQ_i = dS K (red.global.add into an fp32 accumulator).
 #include "common.cuh"
-#include "gemm_epilogue.cuh"   // drop_keep
+#include "gemm_epilogue.cuh"   // DropKey, drop_apply
 #include "sfcvit.h"
 
 namespace {
@@ -54,181 +54,306 @@ __device__ __forceinline__ void store_p_chunk(uint8_t* buf, int r, int c32, cons
 }
 
 // ================================================= forward =================================================
-struct FwdSmem {
-  static constexpr int kQ = 0;
-  static constexpr int kK = kQ + kTile;          // 2 buffers
-  static constexpr int kV = kK + 2 * kTile;      // 2 buffers
-  static constexpr int kP = kV + 2 * kTile;      // 128 x 128 bf16
-  static constexpr int kBar = kP + 2 * kTile;
-  static constexpr int kTotal = kBar + 8 * 8 + 16;
+// Persistent, warp-specialised. Work item = (image b, head h, query pair qp): 256 query rows = two 128-row tiles A
+// and B, each owned by one softmax warpgroup (thread <-> query row <-> TMEM lane), so the tensor core, the TMA engine
+// and the other warpgroup always have independent work while one warpgroup is inside its exp loop.
+//   warp 0 : TMA producer (Q tiles, K / V tiles of `bkv` keys; runs ahead across items)
+//   warp 1 : MMA issuer   (S_w = Q_w K^T into TMEM region w; O_w = P_w V into the same region once P_w is in smem)
+//   warp 2 : TMEM allocator;  warps 4-7 : softmax warpgroup A;  warps 8-11 : softmax warpgroup B
+// The key tile size is a runtime value (any multiple of 16 up to 208): N <= 208 (the 14 x 14 grid: 196 -> 208) is a
+// single pass without online-softmax rescaling; longer sequences use equal tiles of <= 192 keys, double buffered.
+constexpr int kFwdThreads = 384;
+
+struct FwdLayout {          // runtime shared-memory map (bytes), all tile bases 1024-byte aligned
+  int bkv, nkv, stages, p_atoms;
+  int off_k, off_v, off_p, off_bar, total;
 };
 
-__global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p) {
-  // no alignment slack here: two CTAs per SM need every byte of the 228 KB; the 1024-byte alignment that the
-  // 128-byte swizzle needs comes from the declaration and is verified at run time.
-  extern __shared__ __align__(1024) uint8_t smem_dyn[];
-  uint8_t* smem = smem_dyn;
-  if ((ptx::smem_u32(smem) & 1023u) != 0) {
-    if (threadIdx.x == 0) printf("sfcvit: attn_fwd dynamic smem not 1024-byte aligned\n");
-    __trap();
+inline FwdLayout fwd_layout(int N) {
+  FwdLayout L;
+  if (N <= 208) { L.bkv = (N + 15) / 16 * 16; L.nkv = 1; L.stages = 1; }
+  else {
+    L.nkv = (N + 191) / 192;
+    L.bkv = ((N + L.nkv - 1) / L.nkv + 15) / 16 * 16;
+    L.stages = 2;
   }
-  uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + FwdSmem::kBar);
-  uint64_t* bar_kv = bar_q + 1;   // [2]
-  uint64_t* bar_s = bar_q + 3;
-  uint64_t* bar_o = bar_q + 4;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_q + 5);
+  L.p_atoms = (L.bkv + 63) / 64;
+  const int kv_bytes = (L.bkv * 128 + 1023) / 1024 * 1024;
+  L.off_k = 2 * kTile;
+  L.off_v = L.off_k + L.stages * kv_bytes;
+  L.off_p = L.off_v + L.stages * kv_bytes;
+  L.off_bar = L.off_p + 2 * L.p_atoms * kTile;
+  L.total = L.off_bar + 32 * 8 + 16 + 1024;
+  return L;
+}
+
+struct FwdBars {            // mbarrier indices
+  static constexpr int q_full = 0, q_empty = 2, k_full = 4, k_empty = 6, v_full = 8, v_empty = 10, s_full = 12, p_full = 14,
+                       o_full = 16, o_empty = 18, count = 20;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool kSingle>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, const AttnParams p,
+                const FwdLayout L) {
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + FwdBars::count);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int q0 = qt * BQ;
-  const int nkv = (p.N + BKV - 1) / BKV;
-  const int row0 = b * p.N;
+  const int bkv = L.bkv, nkv = L.nkv, stages = L.stages;
+  const int kv_bytes = (bkv * 128 + 1023) / 1024 * 1024;
+  const int nqp = (p.N + 2 * BQ - 1) / (2 * BQ);
+  const int n_items = p.B * p.H * nqp;
 
   if (tid == 0) {
-    ptx::prefetch_tmap(&tmap_qkv);
-    ptx::mbar_init(bar_q, 1);
-    ptx::mbar_init(&bar_kv[0], 1);
-    ptx::mbar_init(&bar_kv[1], 1);
-    ptx::mbar_init(bar_s, 1);
-    ptx::mbar_init(bar_o, 1);
+    ptx::prefetch_tmap(&tmap_q);
+    ptx::prefetch_tmap(&tmap_kv);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bars[FwdBars::q_full + i], 1);
+      ptx::mbar_init(&bars[FwdBars::q_empty + i], 1);
+      ptx::mbar_init(&bars[FwdBars::k_full + i], 1);
+      ptx::mbar_init(&bars[FwdBars::k_empty + i], 1);
+      ptx::mbar_init(&bars[FwdBars::v_full + i], 1);
+      ptx::mbar_init(&bars[FwdBars::v_empty + i], 1);
+      ptx::mbar_init(&bars[FwdBars::s_full + i], 1);
+      ptx::mbar_init(&bars[FwdBars::p_full + i], 128);
+      ptx::mbar_init(&bars[FwdBars::o_full + i], 1);
+      ptx::mbar_init(&bars[FwdBars::o_empty + i], 128);
+    }
     ptx::fence_barrier_init();
   }
-  if (warp == 0) ptx::tmem_alloc<256>(tmem_ptr);
+  if (warp == 2) ptx::tmem_alloc<512>(tmem_ptr);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
-  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
 
-  if (tid == 0) {
-    ptx::mbar_expect_tx(bar_q, kTile);
-    ptx::tma_load_2d(&tmap_qkv, bar_q, smem + FwdSmem::kQ, h * DH, row0 + q0);
-    ptx::mbar_expect_tx(&bar_kv[0], 2 * kTile);
-    ptx::tma_load_2d(&tmap_qkv, &bar_kv[0], smem + FwdSmem::kK, p.D + h * DH, row0);
-    ptx::tma_load_2d(&tmap_qkv, &bar_kv[0], smem + FwdSmem::kV, 2 * p.D + h * DH, row0);
-  }
-
-  const float sl2 = p.scale * kLog2e;
-  float m_run = -INFINITY, l_run = 0.f;
-  float o_acc[DH];
-#pragma unroll
-  for (int d = 0; d < DH; ++d) o_acc[d] = 0.f;
-  const int r = tid;                       // query row within the tile == TMEM lane
-  const int qi = q0 + r;
-  const uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, false, false);
-  const uint32_t idesc_o = umma_idesc_bf16(BQ, DH, false, true);
-  const DropKey dkey = drop_key(p.drop_seed, p.drop_p);
-  ptx::mbar_wait(bar_q, 0);
-  for (int j = 0; j < nkv; ++j) {
-    const int buf = j & 1;
-    if (tid == 0 && j + 1 < nkv) {
-      ptx::mbar_expect_tx(&bar_kv[buf ^ 1], 2 * kTile);
-      ptx::tma_load_2d(&tmap_qkv, &bar_kv[buf ^ 1], smem + FwdSmem::kK + (buf ^ 1) * kTile, p.D + h * DH, row0 + (j + 1) * BKV);
-      ptx::tma_load_2d(&tmap_qkv, &bar_kv[buf ^ 1], smem + FwdSmem::kV + (buf ^ 1) * kTile, 2 * p.D + h * DH, row0 + (j + 1) * BKV);
-    }
-    ptx::mbar_wait(&bar_kv[buf], (j >> 1) & 1);
-    if (tid == 0) {
-      ptx::tc_fence_after();
-      const uint64_t dq = umma_smem_desc_sw128(ptx::smem_u32(smem + FwdSmem::kQ), 0, 1024);
-      const uint64_t dk = umma_smem_desc_sw128(ptx::smem_u32(smem + FwdSmem::kK + buf * kTile), 0, 1024);
-#pragma unroll
-      for (int k = 0; k < DH / 16; ++k) ptx::umma_f16(tmem_s, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
-      ptx::umma_commit(bar_s);
-    }
-    ptx::mbar_wait(bar_s, j & 1);
-    ptx::tc_fence_after();
-
-    const int kv_valid = min(BKV, p.N - j * BKV);     // number of valid key columns in this tile (>= 1)
-    // pass 1: row maximum
-    float mx = -INFINITY;
-#pragma unroll 1
-    for (int c = 0; c < BKV / 32; ++c) {
-      if (c * 32 >= kv_valid) break;
-      uint32_t rr[32];
-      ptx::tmem_ld_x32(tmem_s + lane_off + c * 32, rr);
-      ptx::tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(rr[i]));
-    }
-    const float m_new = fmaxf(m_run, mx);
-    const float alpha = exp2f((m_run - m_new) * sl2);   // m_run = -inf on the first tile -> 0
-    const float mb = m_new * sl2;
-    // pass 2: probabilities, row sum, bf16 P -> smem
-    float psum = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < BKV / 32; ++c) {
-      float pv[32];
-      if (c * 32 < kv_valid) {
-        uint32_t rr[32];
-        ptx::tmem_ld_x32(tmem_s + lane_off + c * 32, rr);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = (c * 32 + i < kv_valid) ? exp2f(__uint_as_float(rr[i]) * sl2 - mb) : 0.f;
-          psum += e;
-          pv[i] = e;
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (ptx::elect_one()) {
+      int ii = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ii) {
+        const int qp = item % nqp, h = (item / nqp) % p.H, b = item / (nqp * p.H);
+        const int row0 = b * p.N;
+        for (int w = 0; w < 2; ++w) {
+          ptx::mbar_wait(&bars[FwdBars::q_empty + w], (ii & 1) ^ 1);
+          ptx::mbar_expect_tx(&bars[FwdBars::q_full + w], kTile);
+          ptx::tma_load_2d(&tmap_q, &bars[FwdBars::q_full + w], smem + w * kTile, h * DH, row0 + qp * 2 * BQ + w * BQ);
         }
-        if (p.drop_p > 0.f) {
-          const unsigned long long base = (((unsigned long long)(b * p.H + h) * p.N + (unsigned long long)qi) * p.N) + (unsigned long long)(j * BKV + c * 32);
-          drop_apply<32>(pv, dkey, base);
+        for (int j = 0; j < nkv; ++j) {
+          const int g = ii * nkv + j;
+          const int st = g % stages;
+          const uint32_t ph = (uint32_t)((g / stages) & 1);
+          ptx::mbar_wait(&bars[FwdBars::k_empty + st], ph ^ 1);
+          ptx::mbar_expect_tx(&bars[FwdBars::k_full + st], (uint32_t)(bkv * 128));
+          ptx::tma_load_2d(&tmap_kv, &bars[FwdBars::k_full + st], smem + L.off_k + st * kv_bytes, p.D + h * DH, row0 + j * bkv);
+          ptx::mbar_wait(&bars[FwdBars::v_empty + st], ph ^ 1);
+          ptx::mbar_expect_tx(&bars[FwdBars::v_full + st], (uint32_t)(bkv * 128));
+          ptx::tma_load_2d(&tmap_kv, &bars[FwdBars::v_full + st], smem + L.off_v + st * kv_bytes, 2 * p.D + h * DH, row0 + j * bkv);
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) pv[i] = 0.f;
       }
-      store_p_chunk(smem + FwdSmem::kP, r, c, pv);
     }
-    l_run = l_run * alpha + psum;
-    m_run = m_new;
-    ptx::tc_fence_before();
-    ptx::fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      ptx::tc_fence_after();
-      const uint32_t sp = ptx::smem_u32(smem + FwdSmem::kP);
-      const uint32_t sv = ptx::smem_u32(smem + FwdSmem::kV + buf * kTile);
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (ptx::elect_one()) {
+      const uint32_t idesc_s = umma_idesc_bf16(BQ, bkv, false, false);
+      const uint32_t idesc_o = umma_idesc_bf16(BQ, DH, false, true);
+      const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int total = my_items * nkv;
+      auto issue_s = [&](int w, int g) {
+        const int j = g % nkv, ii = g / nkv, st = g % stages;
+        if (j == 0) ptx::mbar_wait(&bars[FwdBars::q_full + w], ii & 1);
+        ptx::mbar_wait(&bars[FwdBars::k_full + st], (g / stages) & 1);
+        ptx::mbar_wait(&bars[FwdBars::o_empty + w], (g & 1) ^ 1);          // TMEM region w free (O of step g-1 read out)
+        ptx::tc_fence_after();
+        const uint64_t dq = umma_smem_desc_sw128(ptx::smem_u32(smem + w * kTile), 0, 1024);
+        const uint64_t dk = umma_smem_desc_sw128(ptx::smem_u32(smem + L.off_k + st * kv_bytes), 0, 1024);
 #pragma unroll
-      for (int k = 0; k < BKV / 16; ++k) {
-        const uint64_t da = umma_smem_desc_sw128(sp + (k >> 2) * kTile + (k & 3) * 32, 0, 1024);
-        const uint64_t db = umma_smem_desc_sw128(sv + k * 2048, kTile, 1024);
-        ptx::umma_f16(tmem_o, da, db, idesc_o, k > 0 ? 1u : 0u);
+        for (int k = 0; k < DH / 16; ++k)
+          ptx::umma_f16(tmem_base + w * 256, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
+        ptx::umma_commit(&bars[FwdBars::s_full + w]);
+        if (w == 1) ptx::umma_commit(&bars[FwdBars::k_empty + st]);
+        if (j == nkv - 1) ptx::umma_commit(&bars[FwdBars::q_empty + w]);
+      };
+      auto issue_pv = [&](int w, int g) {
+        const int st = g % stages;
+        ptx::mbar_wait(&bars[FwdBars::p_full + w], g & 1);
+        ptx::mbar_wait(&bars[FwdBars::v_full + st], (g / stages) & 1);
+        ptx::tc_fence_after();
+        const uint32_t sp = ptx::smem_u32(smem + L.off_p + w * L.p_atoms * kTile);
+        const uint32_t sv = ptx::smem_u32(smem + L.off_v + st * kv_bytes);
+        for (int k = 0; k < bkv / 16; ++k) {
+          const uint64_t da = umma_smem_desc_sw128(sp + (k >> 2) * kTile + (k & 3) * 32, 0, 1024);
+          const uint64_t db = umma_smem_desc_sw128(sv + k * 2048, kTile, 1024);
+          ptx::umma_f16(tmem_base + w * 256, da, db, idesc_o, k > 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&bars[FwdBars::o_full + w]);
+        if (w == 1) ptx::umma_commit(&bars[FwdBars::v_empty + st]);
+      };
+      if (total > 0) {
+        issue_s(0, 0);
+        issue_s(1, 0);
+        for (int g = 0; g < total; ++g) {
+          issue_pv(0, g);
+          if (g + 1 < total) issue_s(0, g + 1);
+          issue_pv(1, g);
+          if (g + 1 < total) issue_s(1, g + 1);
+        }
       }
-      ptx::umma_commit(bar_o);
     }
-    ptx::mbar_wait(bar_o, j & 1);
-    ptx::tc_fence_after();
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== softmax warpgroups =====================
+    const int w = (warp - 4) >> 2;                 // 0 = tile A, 1 = tile B
+    const int quarter = warp & 3;
+    const int lane = tid & 31;
+    const int r = quarter * 32 + lane;             // row in tile == TMEM lane
+    const uint32_t t_s = tmem_base + w * 256 + ((uint32_t)(quarter * 32) << 16);
+    uint8_t* p_smem = smem + L.off_p + w * L.p_atoms * kTile;
+    const float sl2 = p.scale * kLog2e;
+    const DropKey dkey = drop_key(p.drop_seed, p.drop_p);
+    const bool has_drop = p.drop_p > 0.f;
+    int g = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int qp = item % nqp, h = (item / nqp) % p.H, b = item / (nqp * p.H);
+      const int q_tile0 = qp * 2 * BQ + w * BQ;
+      const int qi = q_tile0 + r;
+      const bool warp_active = q_tile0 + quarter * 32 < p.N;     // warp-uniform: at least one valid query row
+      float m_run = -INFINITY, l_run = 0.f;
+      float o_acc[kSingle ? 1 : DH];
+      if constexpr (!kSingle) {
 #pragma unroll
-    for (int c = 0; c < DH / 32; ++c) {
-      uint32_t rr[32];
-      ptx::tmem_ld_x32(tmem_o + lane_off + c * 32, rr);
-      ptx::tmem_ld_wait();
+        for (int d = 0; d < DH; ++d) o_acc[d] = 0.f;
+      }
+      for (int j = 0; j < nkv; ++j, ++g) {
+        ptx::mbar_wait(&bars[FwdBars::s_full + w], g & 1);
+        ptx::tc_fence_after();
+        float alpha = 1.f;
+        if (warp_active) {
+          const int kv_valid = min(bkv, p.N - j * bkv);
+          const int nch = (kv_valid + 31) / 32;
+          float mx = -INFINITY;
+#pragma unroll 1
+          for (int c = 0; c < nch; ++c) {
+            uint32_t rr[32];
+            ptx::tmem_ld_x32(t_s + c * 32, rr);
+            ptx::tmem_ld_wait();
+            if (c * 32 + 32 <= kv_valid) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = o_acc[c * 32 + i] * alpha + __uint_as_float(rr[i]);
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rr[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(rr[i]));
+            }
+          }
+          const float m_new = fmaxf(m_run, mx);
+          alpha = ex2_approx((m_run - m_new) * sl2);   // m_run = -inf on the first tile -> 0
+          const float mb = m_new * sl2;
+          float psum = 0.f;
+          const unsigned long long drop_row = (((unsigned long long)(b * p.H + h) * p.N + (unsigned long long)qi) * p.N) + (unsigned long long)(j * bkv);
+          const int nch_all = (bkv + 31) / 32;         // P columns read by the PV MMA: [0, bkv)
+#pragma unroll 1
+          for (int c = 0; c < nch_all; ++c) {
+            float pv[32];
+            if (c < nch) {
+              uint32_t rr[32];
+              ptx::tmem_ld_x32(t_s + c * 32, rr);
+              ptx::tmem_ld_wait();
+              if (c * 32 + 32 <= kv_valid) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { pv[i] = ex2_approx(fmaf(__uint_as_float(rr[i]), sl2, -mb)); psum += pv[i]; }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  pv[i] = (c * 32 + i < kv_valid) ? ex2_approx(fmaf(__uint_as_float(rr[i]), sl2, -mb)) : 0.f;
+                  psum += pv[i];
+                }
+              }
+              if (has_drop) drop_apply<32>(pv, dkey, drop_row + (unsigned long long)(c * 32));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) pv[i] = 0.f;
+            }
+            store_p_chunk(p_smem, r, c, pv);
+          }
+          l_run = l_run * alpha + psum;
+          m_run = m_new;
+        }
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&bars[FwdBars::p_full + w]);
+        ptx::mbar_wait(&bars[FwdBars::o_full + w], g & 1);
+        ptx::tc_fence_after();
+        if (warp_active) {
+          if constexpr (kSingle) {
+            // single key tile: O is final, normalise and store straight from TMEM
+            const float inv_l = 1.0f / l_run;
+#pragma unroll
+            for (int c = 0; c < DH / 32; ++c) {
+              uint32_t rr[32];
+              ptx::tmem_ld_x32(t_s + c * 32, rr);
+              ptx::tmem_ld_wait();
+              if (qi < p.N) {
+                __nv_bfloat16* op = p.out + (long long)(b * p.N + qi) * p.D + h * DH + c * 32;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  uint4 o;
+                  o.x = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 0]) * inv_l, __uint_as_float(rr[q * 8 + 1]) * inv_l);
+                  o.y = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 2]) * inv_l, __uint_as_float(rr[q * 8 + 3]) * inv_l);
+                  o.z = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 4]) * inv_l, __uint_as_float(rr[q * 8 + 5]) * inv_l);
+                  o.w = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 6]) * inv_l, __uint_as_float(rr[q * 8 + 7]) * inv_l);
+                  reinterpret_cast<uint4*>(op)[q] = o;
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < DH / 32; ++c) {
+              uint32_t rr[32];
+              ptx::tmem_ld_x32(t_s + c * 32, rr);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha, __uint_as_float(rr[i]));
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bars[FwdBars::o_empty + w]);
+      }
+      if (qi < p.N) {
+        if constexpr (!kSingle) {
+          const float inv_l = 1.0f / l_run;
+          __nv_bfloat16* op = p.out + (long long)(b * p.N + qi) * p.D + h * DH;
+#pragma unroll
+          for (int q = 0; q < DH / 8; ++q) {
+            uint4 o;
+            o.x = ptx::pack_bf16(o_acc[q * 8 + 0] * inv_l, o_acc[q * 8 + 1] * inv_l);
+            o.y = ptx::pack_bf16(o_acc[q * 8 + 2] * inv_l, o_acc[q * 8 + 3] * inv_l);
+            o.z = ptx::pack_bf16(o_acc[q * 8 + 4] * inv_l, o_acc[q * 8 + 5] * inv_l);
+            o.w = ptx::pack_bf16(o_acc[q * 8 + 6] * inv_l, o_acc[q * 8 + 7] * inv_l);
+            reinterpret_cast<uint4*>(op)[q] = o;
+          }
+        }
+        if (p.lse) p.lse[((long long)b * p.H + h) * p.N + qi] = m_run * p.scale + logf(l_run);
+      }
     }
-    ptx::tc_fence_before();
   }
 
-  if (qi < p.N) {
-    const float inv_l = 1.0f / l_run;
-    __nv_bfloat16* op = p.out + (long long)(row0 + qi) * p.D + h * DH;
-#pragma unroll
-    for (int q = 0; q < DH / 8; ++q) {
-      uint4 o;
-      o.x = ptx::pack_bf16(o_acc[q * 8 + 0] * inv_l, o_acc[q * 8 + 1] * inv_l);
-      o.y = ptx::pack_bf16(o_acc[q * 8 + 2] * inv_l, o_acc[q * 8 + 3] * inv_l);
-      o.z = ptx::pack_bf16(o_acc[q * 8 + 4] * inv_l, o_acc[q * 8 + 5] * inv_l);
-      o.w = ptx::pack_bf16(o_acc[q * 8 + 6] * inv_l, o_acc[q * 8 + 7] * inv_l);
-      reinterpret_cast<uint4*>(op)[q] = o;
-    }
-    if (p.lse) p.lse[((long long)b * p.H + h) * p.N + qi] = m_run * p.scale + logf(l_run);
-  }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<256>(tmem_base);
+    ptx::tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -476,18 +601,24 @@ extern "C" int sfc_attn_fwd(const void* qkv, void* out, float* lse, int B, int H
   if (int e = check_shape(B, H, N, D)) return e;
   SFC_REQUIRE(qkv && out, "sfc_attn_fwd: null pointer");
   SFC_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "sfc_attn_fwd: dropout p out of range");
-  CUtensorMap tq;
+  const FwdLayout L = fwd_layout(N);
+  SFC_REQUIRE(L.total <= 232448, "sfc_attn_fwd: shared-memory plan of %d bytes exceeds 227 KB (N=%d)", L.total, N);
+  CUtensorMap tq, tkv;
   if (int e = sfc_make_tmap_2d(&tq, qkv, 2, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D * 2, DH, BQ, true)) return e;
+  if (int e = sfc_make_tmap_2d(&tkv, qkv, 2, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D * 2, DH, (uint32_t)L.bkv, true)) return e;
   AttnParams p{};
   p.B = B; p.H = H; p.N = N; p.D = D; p.scale = scale; p.drop_p = drop_p; p.drop_seed = drop_seed;
   p.out = (__nv_bfloat16*)out; p.lse = lse;
   static bool configured = false;
   if (!configured) {
-    SFC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kTotal));
+    SFC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    SFC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     configured = true;
   }
-  dim3 grid((N + BQ - 1) / BQ, H, B);
-  attn_fwd_kernel<<<grid, 128, FwdSmem::kTotal, stream>>>(tq, p);
+  const long long items = (long long)B * H * ((N + 2 * BQ - 1) / (2 * BQ));
+  const int grid = (int)(items < sfc_num_sms() ? items : sfc_num_sms());
+  if (L.nkv == 1) attn_fwd_kernel<true><<<grid, kFwdThreads, L.total, stream>>>(tq, tkv, p, L);
+  else attn_fwd_kernel<false><<<grid, kFwdThreads, L.total, stream>>>(tq, tkv, p, L);
   SFC_LAUNCH_OK();
   return 0;
 }
