@@ -39,6 +39,7 @@ struct AttnParams {
   const __nv_bfloat16* dout;  // [B*N, D]
   __nv_bfloat16* dqkv;     // [B*N, 3D]
   float* dq_acc;           // [B*N, D] fp32, zero-initialised
+  float* delta;            // [B, H, N] fp32 rowsum(dO * O)
 };
 
 // write 32 consecutive P values (columns c32*32 .. +31 of row r) as bf16 into the K-major SW128 operand buffer
@@ -46,6 +47,18 @@ __device__ __forceinline__ void store_p_chunk(uint8_t* buf, int r, int c32, cons
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int j8 = c32 * 4 + q;
+    uint4 o;
+    o.x = ptx::pack_bf16(v[q * 8 + 0], v[q * 8 + 1]); o.y = ptx::pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+    o.z = ptx::pack_bf16(v[q * 8 + 4], v[q * 8 + 5]); o.w = ptx::pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+    *reinterpret_cast<uint4*>(buf + (j8 >> 3) * kTile + r * 128 + (((j8 & 7) ^ (r & 7)) << 4)) = o;
+  }
+}
+
+// 16 consecutive values (columns c16*16 .. +15 of row r) into the same layout
+__device__ __forceinline__ void store_p_half(uint8_t* buf, int r, int c16, const float* v) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int j8 = c16 * 2 + q;
     uint4 o;
     o.x = ptx::pack_bf16(v[q * 8 + 0], v[q * 8 + 1]); o.y = ptx::pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
     o.z = ptx::pack_bf16(v[q * 8 + 4], v[q * 8 + 5]); o.w = ptx::pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
@@ -358,216 +371,371 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 }
 
 // ================================================= backward =================================================
+// Persistent, warp-specialised. Work item = (image b, head h, key tile jt of `bkv` <= 128 keys); inside an item the
+// CTA walks the 128-row query tiles ("steps"). dV / dK of the item stay in TMEM across its steps, dQ of each step is
+// reduced into an fp32 scratch with red.global.add (key tiles of one head run on different CTAs).
+//   warp 0 : TMA producer (K, V per item, double buffered; Q, dO per step, 3 stages; runs ahead across items)
+//   warp 1 : MMA issuer
+//   warp 2 : TMEM allocator;  warps 4-11 : two element-wise warpgroups (thread <-> query row; warpgroup c owns the
+//            32-column chunks {2c, 2c+1} of the S / dP tile)
+// TMEM (512 columns): S0 | S1 | dP | dV dK. Per step s the issuer runs
+//   S(s+1) -> S[(s+1)&1]        early, so the exp pass of step s+1 overlaps the gradient MMAs of step s
+//   dV += P^T dO, dK += dS^T Q, dQ(s) = dS K -> S[s&1] (dead by then)      after P / dS of step s are in smem
+//   dP(s+1) = dO V^T -> dP
+// and the warpgroups run  P = exp2(S - lse) (kept in registers)  ->  read dQ(s-1) out  ->  dS = P (dP - delta) scale.
+constexpr int kBwdThreads = 384;
+constexpr int kQdoStages = 3;
+
 struct BwdSmem {
-  static constexpr int kK = 0;
-  static constexpr int kV = kK + kTile;
-  static constexpr int kQ = kV + kTile;           // 2 buffers
-  static constexpr int kDO = kQ + 2 * kTile;      // 2 buffers
-  static constexpr int kP = kDO + 2 * kTile;      // 128 x 128 bf16 (rows = query, cols = key)
+  static constexpr int kK = 0;                          // 2 stages x 16 KB
+  static constexpr int kV = kK + 2 * kTile;             // 2 stages
+  static constexpr int kQ = kV + 2 * kTile;             // 3 stages
+  static constexpr int kDO = kQ + kQdoStages * kTile;   // 3 stages
+  static constexpr int kP = kDO + kQdoStages * kTile;   // 128 x 128 bf16 (rows = query, cols = key)
   static constexpr int kDS = kP + 2 * kTile;
   static constexpr int kBar = kDS + 2 * kTile;
-  static constexpr int kTotal = kBar + 8 * 8 + 16 + 1024;
+  static constexpr int kTotal = kBar + 24 * 8 + 16 + 1024;
+  static_assert(kTotal <= 232448, "exceeds 227 KB");
+};
+
+struct BwdBars {
+  static constexpr int kv_full = 0, kv_empty = 2, qdo_full = 4, qdo_empty = 7, s_full = 10, dp_full = 12, pds_full = 13,
+                       dq_full = 14, dq_empty = 15, count = 16;
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(128) attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
-                                                       const __grid_constant__ CUtensorMap tmap_do, const AttnParams p) {
+// delta[b, h, n] = sum_d dO[b, n, h, d] * O[b, n, h, d]   (8 lanes per (row, head), fully coalesced)
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                                                            float* __restrict__ delta, long long rows, int N, int H) {
+  const long long total = rows * H * 8;
+  const int lane = threadIdx.x & 31;
+  // warp-uniform loop (the shuffles below need all 32 lanes)
+  for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < total; base += (long long)gridDim.x * blockDim.x) {
+    const long long t = base + lane;
+    const bool ok = t < total;
+    const long long rh = (ok ? t : total - 1) >> 3;
+    const long long row = rh / H;
+    const int h = (int)(rh % H);
+    const long long off = (row * H + h) * DH + (t & 7) * 8;
+    float s = 0.f;
+    if (ok) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(o + off)), d = __ldg(reinterpret_cast<const uint4*>(dout + off));
+      s = ptx::bf16_lo(a.x) * ptx::bf16_lo(d.x) + ptx::bf16_hi(a.x) * ptx::bf16_hi(d.x) + ptx::bf16_lo(a.y) * ptx::bf16_lo(d.y) +
+          ptx::bf16_hi(a.y) * ptx::bf16_hi(d.y) + ptx::bf16_lo(a.z) * ptx::bf16_lo(d.z) + ptx::bf16_hi(a.z) * ptx::bf16_hi(d.z) +
+          ptx::bf16_lo(a.w) * ptx::bf16_lo(d.w) + ptx::bf16_hi(a.w) * ptx::bf16_hi(d.w);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (ok && (t & 7) == 0) {
+      const long long b = row / N, n = row % N;
+      delta[(b * H + h) * N + n] = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                const __grid_constant__ CUtensorMap tmap_do, const AttnParams p, const int bkv) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + BwdSmem::kBar);
-  uint64_t* bar_qdo = bar_kv + 1;   // [2]
-  uint64_t* bar_m1 = bar_kv + 3;
-  uint64_t* bar_m2 = bar_kv + 4;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_kv + 5);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::kBar);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + BwdBars::count);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int kv0 = jt * BKV;
-  const int nq = (p.N + BQ - 1) / BQ;
-  const int row0 = b * p.N;
+  const int nq = (p.N + BQ - 1) / BQ;                       // steps per item
+  const int n_kvt = (p.N + bkv - 1) / bkv;
+  const int n_items = p.B * p.H * n_kvt;
+  const int my_items = (int)blockIdx.x < n_items ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int T = my_items * nq;                              // steps of this CTA
 
   if (tid == 0) {
-    ptx::prefetch_tmap(&tmap_qkv);
+    ptx::prefetch_tmap(&tmap_q);
+    ptx::prefetch_tmap(&tmap_kv);
     ptx::prefetch_tmap(&tmap_do);
-    ptx::mbar_init(bar_kv, 1);
-    ptx::mbar_init(&bar_qdo[0], 1);
-    ptx::mbar_init(&bar_qdo[1], 1);
-    ptx::mbar_init(bar_m1, 1);
-    ptx::mbar_init(bar_m2, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bars[BwdBars::kv_full + i], 1);
+      ptx::mbar_init(&bars[BwdBars::kv_empty + i], 1);
+      ptx::mbar_init(&bars[BwdBars::s_full + i], 1);
+    }
+    for (int i = 0; i < kQdoStages; ++i) {
+      ptx::mbar_init(&bars[BwdBars::qdo_full + i], 1);
+      ptx::mbar_init(&bars[BwdBars::qdo_empty + i], 1);
+    }
+    ptx::mbar_init(&bars[BwdBars::dp_full], 1);
+    ptx::mbar_init(&bars[BwdBars::pds_full], 256);
+    ptx::mbar_init(&bars[BwdBars::dq_full], 1);
+    ptx::mbar_init(&bars[BwdBars::dq_empty], 256);
     ptx::fence_barrier_init();
   }
-  if (warp == 0) ptx::tmem_alloc<512>(tmem_ptr);
+  if (warp == 2) ptx::tmem_alloc<512>(tmem_ptr);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 320,
-                 tmem_dq = tmem_base + 384;
-  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t tmem_dp = tmem_base + 256, tmem_dv = tmem_base + 384, tmem_dk = tmem_base + 448;
 
-  if (tid == 0) {
-    ptx::mbar_expect_tx(bar_kv, 2 * kTile);
-    ptx::tma_load_2d(&tmap_qkv, bar_kv, smem + BwdSmem::kK, p.D + h * DH, row0 + kv0);
-    ptx::tma_load_2d(&tmap_qkv, bar_kv, smem + BwdSmem::kV, 2 * p.D + h * DH, row0 + kv0);
-    ptx::mbar_expect_tx(&bar_qdo[0], 2 * kTile);
-    ptx::tma_load_2d(&tmap_qkv, &bar_qdo[0], smem + BwdSmem::kQ, h * DH, row0);
-    ptx::tma_load_2d(&tmap_do, &bar_qdo[0], smem + BwdSmem::kDO, h * DH, row0);
-  }
-
-  const float sl2 = p.scale * kLog2e;
-  const int r = tid;
-  const int kv_valid = min(BKV, p.N - kv0);
-  const uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, false, false);     // S, dP : K-major x K-major
-  const uint32_t idesc_t = umma_idesc_bf16(BKV, DH, true, true);       // dV, dK: MN-major A (P^T / dS^T), MN-major B
-  const uint32_t idesc_q = umma_idesc_bf16(BQ, DH, false, true);       // dQ    : K-major A (dS), MN-major B (K)
-  const DropKey dkey = drop_key(p.drop_seed, p.drop_p);
-  const float inv_keep = dkey.inv_keep;
-
-  ptx::mbar_wait(bar_kv, 0);
-  for (int i = 0; i < nq; ++i) {
-    const int buf = i & 1;
-    const int q0 = i * BQ;
-    if (tid == 0 && i + 1 < nq) {
-      ptx::mbar_expect_tx(&bar_qdo[buf ^ 1], 2 * kTile);
-      ptx::tma_load_2d(&tmap_qkv, &bar_qdo[buf ^ 1], smem + BwdSmem::kQ + (buf ^ 1) * kTile, h * DH, row0 + q0 + BQ);
-      ptx::tma_load_2d(&tmap_do, &bar_qdo[buf ^ 1], smem + BwdSmem::kDO + (buf ^ 1) * kTile, h * DH, row0 + q0 + BQ);
-    }
-    ptx::mbar_wait(&bar_qdo[buf], (i >> 1) & 1);
-    if (tid == 0) {
-      ptx::tc_fence_after();
-      const uint64_t dq = umma_smem_desc_sw128(ptx::smem_u32(smem + BwdSmem::kQ + buf * kTile), 0, 1024);
-      const uint64_t dk = umma_smem_desc_sw128(ptx::smem_u32(smem + BwdSmem::kK), 0, 1024);
-      const uint64_t ddo = umma_smem_desc_sw128(ptx::smem_u32(smem + BwdSmem::kDO + buf * kTile), 0, 1024);
-      const uint64_t dv = umma_smem_desc_sw128(ptx::smem_u32(smem + BwdSmem::kV), 0, 1024);
-#pragma unroll
-      for (int k = 0; k < DH / 16; ++k) ptx::umma_f16(tmem_s, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
-#pragma unroll
-      for (int k = 0; k < DH / 16; ++k) ptx::umma_f16(tmem_dp, ddo + (uint64_t)(k * 2), dv + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
-      ptx::umma_commit(bar_m1);
-    }
-    // per-row statistics (overlaps the MMAs): lse and delta = rowsum(dO * O)
-    const int qi = q0 + r;
-    const bool q_ok = qi < p.N;
-    float lse2 = 0.f, delta = 0.f;
-    if (q_ok) {
-      lse2 = p.lse[((long long)b * p.H + h) * p.N + qi] * kLog2e;
-      const uint4* orow = reinterpret_cast<const uint4*>(p.o + (long long)(row0 + qi) * p.D + h * DH);
-      const uint4* drow = reinterpret_cast<const uint4*>(p.dout + (long long)(row0 + qi) * p.D + h * DH);
-#pragma unroll
-      for (int q = 0; q < DH / 8; ++q) {
-        const uint4 a = __ldg(orow + q), d = __ldg(drow + q);
-        delta += ptx::bf16_lo(a.x) * ptx::bf16_lo(d.x) + ptx::bf16_hi(a.x) * ptx::bf16_hi(d.x);
-        delta += ptx::bf16_lo(a.y) * ptx::bf16_lo(d.y) + ptx::bf16_hi(a.y) * ptx::bf16_hi(d.y);
-        delta += ptx::bf16_lo(a.z) * ptx::bf16_lo(d.z) + ptx::bf16_hi(a.z) * ptx::bf16_hi(d.z);
-        delta += ptx::bf16_lo(a.w) * ptx::bf16_lo(d.w) + ptx::bf16_hi(a.w) * ptx::bf16_hi(d.w);
-      }
-    }
-    ptx::mbar_wait(bar_m1, i & 1);
-    ptx::tc_fence_after();
-#pragma unroll 1
-    for (int c = 0; c < BKV / 32; ++c) {
-      uint32_t rs[32], rd[32];
-      ptx::tmem_ld_x32(tmem_s + lane_off + c * 32, rs);
-      ptx::tmem_ld_x32(tmem_dp + lane_off + c * 32, rd);
-      ptx::tmem_ld_wait();
-      float pv[32], dsv[32];
-      const unsigned long long base = (((unsigned long long)(b * p.H + h) * p.N + (unsigned long long)qi) * p.N) + (unsigned long long)(kv0 + c * 32);
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const bool ok = q_ok && (c * 32 + e < kv_valid);
-        const float pr = ok ? exp2f(__uint_as_float(rs[e]) * sl2 - lse2) : 0.f;
-        float dp = __uint_as_float(rd[e]);
-        float pd = pr;
-        if (p.drop_p > 0.f) {
-          const bool keep = drop_keep(dkey, base + e);
-          pd = keep ? pr * inv_keep : 0.f;
-          dp = keep ? dp * inv_keep : 0.f;
-        }
-        pv[e] = pd;
-        dsv[e] = ok ? pr * (dp - delta) * p.scale : 0.f;
-      }
-      store_p_chunk(smem + BwdSmem::kP, r, c, pv);
-      store_p_chunk(smem + BwdSmem::kDS, r, c, dsv);
-    }
-    ptx::tc_fence_before();
-    ptx::fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      ptx::tc_fence_after();
-      const uint32_t sp = ptx::smem_u32(smem + BwdSmem::kP);
-      const uint32_t sds = ptx::smem_u32(smem + BwdSmem::kDS);
-      const uint32_t sq = ptx::smem_u32(smem + BwdSmem::kQ + buf * kTile);
-      const uint32_t sdo = ptx::smem_u32(smem + BwdSmem::kDO + buf * kTile);
-      const uint32_t sk = ptx::smem_u32(smem + BwdSmem::kK);
-      // dV[kv, d] += sum_q P[q, kv] dO[q, d]   ;   dK[kv, d] += sum_q dS[q, kv] Q[q, d]     (reduction over q rows)
-#pragma unroll
-      for (int k = 0; k < BQ / 16; ++k) {
-        const uint64_t a_p = umma_smem_desc_sw128(sp + k * 2048, kTile, 1024);
-        const uint64_t b_do = umma_smem_desc_sw128(sdo + k * 2048, kTile, 1024);
-        ptx::umma_f16(tmem_dv, a_p, b_do, idesc_t, (i > 0 || k > 0) ? 1u : 0u);
-      }
-#pragma unroll
-      for (int k = 0; k < BQ / 16; ++k) {
-        const uint64_t a_ds = umma_smem_desc_sw128(sds + k * 2048, kTile, 1024);
-        const uint64_t b_q = umma_smem_desc_sw128(sq + k * 2048, kTile, 1024);
-        ptx::umma_f16(tmem_dk, a_ds, b_q, idesc_t, (i > 0 || k > 0) ? 1u : 0u);
-      }
-      // dQ[q, d] = sum_kv dS[q, kv] K[kv, d]
-#pragma unroll
-      for (int k = 0; k < BKV / 16; ++k) {
-        const uint64_t a_ds = umma_smem_desc_sw128(sds + (k >> 2) * kTile + (k & 3) * 32, 0, 1024);
-        const uint64_t b_k = umma_smem_desc_sw128(sk + k * 2048, kTile, 1024);
-        ptx::umma_f16(tmem_dq, a_ds, b_k, idesc_q, k > 0 ? 1u : 0u);
-      }
-      ptx::umma_commit(bar_m2);
-    }
-    ptx::mbar_wait(bar_m2, i & 1);
-    ptx::tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < DH / 32; ++c) {
-      uint32_t rr[32];
-      ptx::tmem_ld_x32(tmem_dq + lane_off + c * 32, rr);
-      ptx::tmem_ld_wait();
-      if (q_ok) {
-        float* dst = p.dq_acc + (long long)(row0 + qi) * p.D + h * DH + c * 32;
-#pragma unroll
-        for (int e = 0; e < 32; e += 4)
-          red_add_v4(dst + e, __uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3]));
-      }
-    }
-    ptx::tc_fence_before();
-  }
-
-  // dV / dK: TMEM lane == key row of this tile
-  const int kvi = kv0 + r;
-#pragma unroll
-  for (int which = 0; which < 2; ++which) {
-    const uint32_t t = which == 0 ? tmem_dk : tmem_dv;
-    __nv_bfloat16* dst = p.dqkv + (long long)(row0 + kvi) * (3 * p.D) + (which == 0 ? p.D : 2 * p.D) + h * DH;
-#pragma unroll
-    for (int c = 0; c < DH / 32; ++c) {
-      uint32_t rr[32];
-      ptx::tmem_ld_x32(t + lane_off + c * 32, rr);
-      ptx::tmem_ld_wait();
-      if (kvi < p.N) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 o;
-          o.x = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 0]), __uint_as_float(rr[q * 8 + 1]));
-          o.y = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 2]), __uint_as_float(rr[q * 8 + 3]));
-          o.z = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 4]), __uint_as_float(rr[q * 8 + 5]));
-          o.w = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 6]), __uint_as_float(rr[q * 8 + 7]));
-          reinterpret_cast<uint4*>(dst + c * 32)[q] = o;
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (ptx::elect_one()) {
+      int ii = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ii) {
+        const int jt = item % n_kvt, h = (item / n_kvt) % p.H, b = item / (n_kvt * p.H);
+        const int row0 = b * p.N;
+        const int kvst = ii & 1;
+        ptx::mbar_wait(&bars[BwdBars::kv_empty + kvst], ((ii >> 1) & 1) ^ 1);
+        ptx::mbar_expect_tx(&bars[BwdBars::kv_full + kvst], (uint32_t)(2 * bkv * 128));
+        ptx::tma_load_2d(&tmap_kv, &bars[BwdBars::kv_full + kvst], smem + BwdSmem::kK + kvst * kTile, p.D + h * DH, row0 + jt * bkv);
+        ptx::tma_load_2d(&tmap_kv, &bars[BwdBars::kv_full + kvst], smem + BwdSmem::kV + kvst * kTile, 2 * p.D + h * DH, row0 + jt * bkv);
+        for (int qt = 0; qt < nq; ++qt) {
+          const int s = ii * nq + qt;
+          const int st = s % kQdoStages;
+          ptx::mbar_wait(&bars[BwdBars::qdo_empty + st], ((s / kQdoStages) & 1) ^ 1);
+          ptx::mbar_expect_tx(&bars[BwdBars::qdo_full + st], 2 * kTile);
+          ptx::tma_load_2d(&tmap_q, &bars[BwdBars::qdo_full + st], smem + BwdSmem::kQ + st * kTile, h * DH, row0 + qt * BQ);
+          ptx::tma_load_2d(&tmap_do, &bars[BwdBars::qdo_full + st], smem + BwdSmem::kDO + st * kTile, h * DH, row0 + qt * BQ);
         }
       }
     }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (ptx::elect_one()) {
+      const uint32_t idesc_s = umma_idesc_bf16(BQ, bkv, false, false);     // S, dP : K-major x K-major, N = bkv
+      const uint32_t idesc_t = umma_idesc_bf16(128, DH, true, true);       // dV, dK: MN-major A (P^T / dS^T), MN-major B
+      const uint32_t idesc_q = umma_idesc_bf16(BQ, DH, false, true);       // dQ    : K-major A (dS), MN-major B (K)
+      auto s_issue = [&](int s) {
+        const int ii = s / nq, qt = s % nq, st = s % kQdoStages, kvst = ii & 1;
+        ptx::mbar_wait(&bars[BwdBars::qdo_full + st], (s / kQdoStages) & 1);
+        if (qt == 0) ptx::mbar_wait(&bars[BwdBars::kv_full + kvst], (ii >> 1) & 1);
+        if (s >= 2) ptx::mbar_wait(&bars[BwdBars::dq_empty], s & 1);       // dQ(s-2) read out of S[s&1]
+        ptx::tc_fence_after();
+        const uint64_t dq = umma_smem_desc_sw128(ptx::smem_u32(smem + BwdSmem::kQ + st * kTile), 0, 1024);
+        const uint64_t dk = umma_smem_desc_sw128(ptx::smem_u32(smem + BwdSmem::kK + kvst * kTile), 0, 1024);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          ptx::umma_f16(tmem_base + (s & 1) * 128, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
+        ptx::umma_commit(&bars[BwdBars::s_full + (s & 1)]);
+      };
+      auto dp_issue = [&](int s) {
+        const int ii = s / nq, st = s % kQdoStages, kvst = ii & 1;
+        const uint64_t ddo = umma_smem_desc_sw128(ptx::smem_u32(smem + BwdSmem::kDO + st * kTile), 0, 1024);
+        const uint64_t dv = umma_smem_desc_sw128(ptx::smem_u32(smem + BwdSmem::kV + kvst * kTile), 0, 1024);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          ptx::umma_f16(tmem_dp, ddo + (uint64_t)(k * 2), dv + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
+        ptx::umma_commit(&bars[BwdBars::dp_full]);
+      };
+      auto grad_issue = [&](int s) {
+        const int ii = s / nq, qt = s % nq, st = s % kQdoStages, kvst = ii & 1;
+        const int item = (int)blockIdx.x + ii * (int)gridDim.x;
+        const int jt = item % n_kvt;
+        const int kv_valid = min(bkv, p.N - jt * bkv);
+        const int q_valid = min(BQ, p.N - qt * BQ);
+        const int nk_q = (q_valid + 15) / 16, nk_kv = (kv_valid + 15) / 16;
+        ptx::mbar_wait(&bars[BwdBars::pds_full], s & 1);
+        ptx::tc_fence_after();
+        const uint32_t sp = ptx::smem_u32(smem + BwdSmem::kP);
+        const uint32_t sds = ptx::smem_u32(smem + BwdSmem::kDS);
+        const uint32_t sq = ptx::smem_u32(smem + BwdSmem::kQ + st * kTile);
+        const uint32_t sdo = ptx::smem_u32(smem + BwdSmem::kDO + st * kTile);
+        const uint32_t sk = ptx::smem_u32(smem + BwdSmem::kK + kvst * kTile);
+        // dV[kv, d] += sum_q P[q, kv] dO[q, d]   ;   dK[kv, d] += sum_q dS[q, kv] Q[q, d]     (reduction over q rows)
+        for (int k = 0; k < nk_q; ++k) {
+          const uint64_t a_p = umma_smem_desc_sw128(sp + k * 2048, kTile, 1024);
+          const uint64_t b_do = umma_smem_desc_sw128(sdo + k * 2048, kTile, 1024);
+          ptx::umma_f16(tmem_dv, a_p, b_do, idesc_t, (qt > 0 || k > 0) ? 1u : 0u);
+        }
+        for (int k = 0; k < nk_q; ++k) {
+          const uint64_t a_ds = umma_smem_desc_sw128(sds + k * 2048, kTile, 1024);
+          const uint64_t b_q = umma_smem_desc_sw128(sq + k * 2048, kTile, 1024);
+          ptx::umma_f16(tmem_dk, a_ds, b_q, idesc_t, (qt > 0 || k > 0) ? 1u : 0u);
+        }
+        // dQ[q, d] = sum_kv dS[q, kv] K[kv, d]  -> S[s & 1] columns 0..63
+        for (int k = 0; k < nk_kv; ++k) {
+          const uint64_t a_ds = umma_smem_desc_sw128(sds + (k >> 2) * kTile + (k & 3) * 32, 0, 1024);
+          const uint64_t b_k = umma_smem_desc_sw128(sk + k * 2048, kTile, 1024);
+          ptx::umma_f16(tmem_base + (s & 1) * 128, a_ds, b_k, idesc_q, k > 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&bars[BwdBars::dq_full]);
+        ptx::umma_commit(&bars[BwdBars::qdo_empty + st]);
+        if (qt == nq - 1) ptx::umma_commit(&bars[BwdBars::kv_empty + kvst]);
+      };
+      if (T > 0) {
+        s_issue(0);
+        dp_issue(0);
+        for (int s = 0; s < T; ++s) {
+          if (s + 1 < T) s_issue(s + 1);
+          grad_issue(s);
+          if (s + 1 < T) dp_issue(s + 1);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== element-wise warpgroups =====================
+    const int ch = (warp - 4) >> 2;                // column half: chunks {2ch, 2ch+1}
+    const int quarter = warp & 3;
+    const int lane = tid & 31;
+    const int r = quarter * 32 + lane;             // query row in tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const float sl2 = p.scale * kLog2e;
+    const DropKey dkey = drop_key(p.drop_seed, p.drop_p);
+    const bool has_drop = p.drop_p > 0.f;
+    const uint32_t thr_hi = dkey.thr16 << 16;
+    const int nch = (bkv + 31) / 32;
+
+    // readout of step sp (its dQ; and dV / dK when it was the last step of its item)
+    auto readout = [&](int sp) {
+      const int ii = sp / nq, qt = sp % nq;
+      const int item = (int)blockIdx.x + ii * (int)gridDim.x;
+      const int jt = item % n_kvt, h = (item / n_kvt) % p.H, b = item / (n_kvt * p.H);
+      const int row0 = b * p.N;
+      ptx::mbar_wait(&bars[BwdBars::dq_full], sp & 1);
+      ptx::tc_fence_after();
+      {
+        uint32_t rr[32];
+        ptx::tmem_ld_x32(tmem_base + (sp & 1) * 128 + lane_off + ch * 32, rr);
+        ptx::tmem_ld_wait();
+        const int qi = qt * BQ + r;
+        if (qi < p.N) {
+          float* dst = p.dq_acc + (long long)(row0 + qi) * p.D + h * DH + ch * 32;
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            red_add_v4(dst + e, __uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3]));
+        }
+      }
+      if (qt == nq - 1) {
+        // dV (warpgroup 0) / dK (warpgroup 1): TMEM lane == key row of this tile
+        const int kvi = jt * bkv + r;
+        const bool ok = r < bkv && kvi < p.N;
+        const uint32_t t = (ch == 0 ? tmem_dv : tmem_dk) + lane_off;
+        __nv_bfloat16* dst = p.dqkv + (long long)(row0 + kvi) * (3 * p.D) + (ch == 0 ? 2 * p.D : p.D) + h * DH;
+#pragma unroll
+        for (int c = 0; c < DH / 32; ++c) {
+          uint32_t rr[32];
+          ptx::tmem_ld_x32(t + c * 32, rr);
+          ptx::tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              o.x = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 0]), __uint_as_float(rr[q * 8 + 1]));
+              o.y = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 2]), __uint_as_float(rr[q * 8 + 3]));
+              o.z = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 4]), __uint_as_float(rr[q * 8 + 5]));
+              o.w = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 6]), __uint_as_float(rr[q * 8 + 7]));
+              reinterpret_cast<uint4*>(dst + c * 32)[q] = o;
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bars[BwdBars::dq_empty]);
+    };
+
+    int s = 0;
+    for (int ii = 0; ii < my_items; ++ii) {
+      const int item = (int)blockIdx.x + ii * (int)gridDim.x;
+      const int jt = item % n_kvt, h = (item / n_kvt) % p.H, b = item / (n_kvt * p.H);
+      const int kv0 = jt * bkv;
+      const int kv_valid = min(bkv, p.N - kv0);
+      for (int qt = 0; qt < nq; ++qt, ++s) {
+        const int qi = qt * BQ + r;
+        const bool q_ok = qi < p.N;
+        const int q_valid = min(BQ, p.N - qt * BQ);
+        const bool warp_active = quarter * 32 < ((q_valid + 15) / 16) * 16;   // rows read by the dV / dK MMAs
+        float lse2 = 0.f, delta = 0.f;
+        if (q_ok) {
+          const long long si = ((long long)b * p.H + h) * p.N + qi;
+          lse2 = __ldg(p.lse + si) * kLog2e;
+          delta = __ldg(p.delta + si);
+        }
+        // ---- phase A: P = exp2(S * scale * log2e - lse * log2e), kept in registers (+ dropout keep bits)
+        float pr[2][32];
+        uint32_t keep[2] = {0xffffffffu, 0xffffffffu};
+        ptx::mbar_wait(&bars[BwdBars::s_full + (s & 1)], (s >> 1) & 1);
+        ptx::tc_fence_after();
+        if (warp_active) {
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = ch * 2 + cc;
+            if (c < nch) {
+              uint32_t rs[32];
+              ptx::tmem_ld_x32(tmem_base + (s & 1) * 128 + lane_off + c * 32, rs);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                const bool ok = q_ok && (c * 32 + e < kv_valid);
+                pr[cc][e] = ok ? ex2_approx(fmaf(__uint_as_float(rs[e]), sl2, -lse2)) : 0.f;
+              }
+              if (has_drop) {
+                const unsigned long long base = (((unsigned long long)(b * p.H + h) * p.N + (unsigned long long)qi) * p.N) + (unsigned long long)(kv0 + c * 32);
+                uint32_t kb = 0;
+                if ((base & 1ull) == 0) {
+#pragma unroll
+                  for (int g2 = 0; g2 < 16; ++g2) {
+                    const uint32_t hsh = drop_hash2(dkey, (base >> 1) + g2);
+                    kb |= ((hsh << 16) >= thr_hi ? 1u : 0u) << (2 * g2);
+                    kb |= (hsh >= thr_hi ? 1u : 0u) << (2 * g2 + 1);
+                  }
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 32; ++e) kb |= (drop_keep(dkey, base + e) ? 1u : 0u) << e;
+                }
+                keep[cc] = kb;
+              }
+            }
+          }
+        }
+        // ---- dQ (and dV / dK) of the previous step leave TMEM; this also guarantees its MMAs no longer read P / dS smem
+        if (s > 0) readout(s - 1);
+        // ---- phase B: dS = P * (dP - delta) * scale; P (dropped) and dS -> shared memory
+        ptx::mbar_wait(&bars[BwdBars::dp_full], s & 1);
+        ptx::tc_fence_after();
+        if (warp_active) {
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = ch * 2 + cc;
+            if (c < nch) {
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                uint32_t rd[16];
+                ptx::tmem_ld_x16(tmem_dp + lane_off + c * 32 + hf * 16, rd);
+                ptx::tmem_ld_wait();
+                float pv[16], dsv[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                  const float pe = pr[cc][hf * 16 + e];
+                  float dp = __uint_as_float(rd[e]);
+                  float pd = pe;
+                  if (has_drop) {
+                    const bool k = (keep[cc] >> (hf * 16 + e)) & 1u;
+                    pd = k ? pe * dkey.inv_keep : 0.f;
+                    dp = k ? dp * dkey.inv_keep : 0.f;
+                  }
+                  pv[e] = pd;
+                  dsv[e] = pe * (dp - delta) * p.scale;      // pe == 0 outside the valid region
+                }
+                store_p_half(smem + BwdSmem::kP, r, c * 2 + hf, pv);
+                store_p_half(smem + BwdSmem::kDS, r, c * 2 + hf, dsv);
+              }
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&bars[BwdBars::pds_full]);
+      }
+    }
+    if (T > 0) readout(T - 1);
   }
+
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem_base);
   }
@@ -623,33 +791,50 @@ extern "C" int sfc_attn_fwd(const void* qkv, void* out, float* lse, int B, int H
   return 0;
 }
 
-extern "C" size_t sfc_attn_bwd_scratch_bytes(int B, int N, int D) { return (size_t)B * N * D * sizeof(float); }
+extern "C" size_t sfc_attn_bwd_scratch_bytes(int B, int N, int D) {
+  return (size_t)B * N * D * sizeof(float) + (size_t)B * (D / DH) * N * sizeof(float);
+}
 
-// dq_acc scratch (fp32 [B*N, D]) is zeroed here (cudaMemsetAsync on the caller's stream).
+// scratch = fp32 dQ accumulator [B*N, D] (zeroed here with cudaMemsetAsync on the caller's stream) + delta [B, H, N].
 extern "C" int sfc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* scratch,
                             size_t scratch_bytes, int B, int H, int N, int D, float scale, float drop_p,
                             unsigned long long drop_seed, cudaStream_t stream) {
   if (int e = check_shape(B, H, N, D)) return e;
   SFC_REQUIRE(qkv && out && dout && lse && dqkv, "sfc_attn_bwd: null pointer");
-  const size_t need = (size_t)B * N * D * sizeof(float);
+  SFC_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "sfc_attn_bwd: dropout p out of range");
+  const size_t dq_bytes = (size_t)B * N * D * sizeof(float);
+  const size_t need = sfc_attn_bwd_scratch_bytes(B, N, D);
   SFC_REQUIRE(scratch && scratch_bytes >= need, "sfc_attn_bwd: scratch too small (%zu < %zu)", scratch_bytes, need);
-  SFC_CUDA_OK(cudaMemsetAsync(scratch, 0, need, stream));
-  CUtensorMap tq, tdo;
+  SFC_CUDA_OK(cudaMemsetAsync(scratch, 0, dq_bytes, stream));
+  const long long rows = (long long)B * N;
+  float* delta = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + dq_bytes);
+  {
+    long long blocks = sfc_ceil_div64(rows * H * 8, 256);
+    const long long cap = 32ll * sfc_num_sms();
+    if (blocks > cap) blocks = cap;
+    attn_bwd_prep_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, rows, N, H);
+    SFC_LAUNCH_OK();
+  }
+  // key tiles: equal sizes, multiple of 16, at most 128 (the M dimension of the dV / dK MMAs)
+  const int n_kvt = (N + 127) / 128;
+  const int bkv = ((N + n_kvt - 1) / n_kvt + 15) / 16 * 16;
+  CUtensorMap tq, tkv, tdo;
   if (int e = sfc_make_tmap_2d(&tq, qkv, 2, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D * 2, DH, BQ, true)) return e;
+  if (int e = sfc_make_tmap_2d(&tkv, qkv, 2, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D * 2, DH, (uint32_t)bkv, true)) return e;
   if (int e = sfc_make_tmap_2d(&tdo, dout, 2, (uint64_t)D, (uint64_t)B * N, (uint64_t)D * 2, DH, BQ, true)) return e;
   AttnParams p{};
   p.B = B; p.H = H; p.N = N; p.D = D; p.scale = scale; p.drop_p = drop_p; p.drop_seed = drop_seed;
   p.lse = const_cast<float*>(lse); p.o = (const __nv_bfloat16*)out; p.dout = (const __nv_bfloat16*)dout;
-  p.dqkv = (__nv_bfloat16*)dqkv; p.dq_acc = (float*)scratch;
+  p.dqkv = (__nv_bfloat16*)dqkv; p.dq_acc = (float*)scratch; p.delta = delta;
   static bool configured = false;
   if (!configured) {
     SFC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal));
     configured = true;
   }
-  dim3 grid((N + BKV - 1) / BKV, H, B);
-  attn_bwd_kernel<<<grid, 128, BwdSmem::kTotal, stream>>>(tq, tdo, p);
+  const long long items = (long long)B * H * ((N + bkv - 1) / bkv);
+  const int grid = (int)(items < sfc_num_sms() ? items : sfc_num_sms());
+  attn_bwd_kernel<<<grid, kBwdThreads, BwdSmem::kTotal, stream>>>(tq, tkv, tdo, p, bkv);
   SFC_LAUNCH_OK();
-  const long long rows = (long long)B * N;
   long long blocks = sfc_ceil_div64(rows * (D / 8), 256);
   const long long cap = 16ll * sfc_num_sms();
   if (blocks > cap) blocks = cap;
