@@ -44,7 +44,7 @@ struct SmemLayout {
   static_assert(kTotal <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
 };
 
-template <int BN, int kStages, bool A_MN, bool B_MN, bool FAST_EPI>
+template <int BN, int kStages, bool A_MN, bool B_MN, bool FAST_EPI, int CL>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
   using L = SmemLayout<BN, kStages, A_MN, B_MN>;
@@ -57,7 +57,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
-  const int total_tiles = p.num_m_tiles * p.num_n_tiles * p.splits;
+  // CL == 2: the two CTAs of a cluster work on m-tiles 2i and 2i+1 of the same n-tile; each loads half of the B tile and
+  // multicasts it to both, halving the L2 -> SM traffic of the (larger) B operand.
+  const int crank = CL > 1 ? (int)ptx::cluster_ctarank() : 0;
+  const int num_m_units = (p.num_m_tiles + CL - 1) / CL;
+  const int total_tiles = num_m_units * p.num_n_tiles * p.splits;      // units of CL m-tiles
+  const int unit0 = (int)blockIdx.x / CL, unit_stride = (int)gridDim.x / CL;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
 
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmap_a);
@@ -66,7 +72,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 1 && ptx::elect_one()) {
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], CL);            // one tcgen05.commit arrival per CTA of the cluster
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
@@ -77,6 +83,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 2) ptx::tmem_alloc<2 * BN>(tmem_ptr);
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) ptx::cluster_sync();       // peer barriers are initialised before any multicast / remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -85,11 +92,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (p.debug != 2 && ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = unit0; t < total_tiles; t += unit_stride) {
         const int split = t % p.splits;
         const int tile = t / p.splits;
         const int n_tile = tile % p.num_n_tiles;
-        const int m_tile = tile / p.num_n_tiles;
+        const int m_tile = (tile / p.num_n_tiles) * CL + crank;      // may be one past the end for the odd CTA: TMA zero-fills
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(kb0 + p.kblocks_per_split, p.num_k_blocks);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -104,12 +111,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int a = 0; a < BM / 64; ++a)
               ptx::tma_load_2d(&tmap_a, &full_bar[stage], sa + a * (BK * 128), m_tile * BM + a * 64, kb * BK);
           }
-          if constexpr (!B_MN) {
-            ptx::tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * BK, n_tile * BN);
-          } else {
+          if constexpr (CL == 1) {
+            if constexpr (!B_MN) {
+              ptx::tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * BK, n_tile * BN);
+            } else {
 #pragma unroll
-            for (int a = 0; a < BN / 64; ++a)
-              ptx::tma_load_2d(&tmap_b, &full_bar[stage], sb + a * (BK * 128), n_tile * BN + a * 64, kb * BK);
+              for (int a = 0; a < BN / 64; ++a)
+                ptx::tma_load_2d(&tmap_b, &full_bar[stage], sb + a * (BK * 128), n_tile * BN + a * 64, kb * BK);
+            }
+          } else {
+            // this CTA's half of the B tile, written to the same offset in both CTAs
+            if constexpr (!B_MN) {
+              ptx::tma_load_2d_mc(&tmap_b, &full_bar[stage], sb + crank * (BN / CL) * 128, kb * BK, n_tile * BN + crank * (BN / CL), kMask);
+            } else {
+#pragma unroll
+              for (int a = 0; a < BN / 64 / CL; ++a) {
+                const int aa = crank * (BN / 64 / CL) + a;
+                ptx::tma_load_2d_mc(&tmap_b, &full_bar[stage], sb + aa * (BK * 128), n_tile * BN + aa * 64, kb * BK, kMask);
+              }
+            }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -126,7 +146,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+      for (int t = unit0; t < total_tiles; t += unit_stride, ++iter) {
         const int split = t % p.splits;
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(kb0 + p.kblocks_per_split, p.num_k_blocks);
@@ -146,7 +166,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             ptx::umma_f16(tmem_d, da + (uint64_t)(k * kAdvA), db + (uint64_t)(k * kAdvB), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          ptx::umma_commit(&empty_bar[stage]);            // frees the smem slot when these MMAs retire
+          if constexpr (CL == 1) ptx::umma_commit(&empty_bar[stage]);            // frees the smem slot when these MMAs retire
+          else ptx::umma_commit_mc(&empty_bar[stage], kMask);                    // ... in both CTAs (the peer refills half of it)
           if (kb == kb1 - 1) ptx::umma_commit(&tmem_full[acc]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -159,11 +180,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int half = (warp - 4) >> 2;
     uint8_t* stage = smem + L::kEpiOffset + (warp - 4) * kEpiStageBytes;
     int iter = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+    for (int t = unit0; t < total_tiles; t += unit_stride, ++iter) {
       const int split = t % p.splits;
       const int tile = t / p.splits;
       const int n_tile = tile % p.num_n_tiles;
-      const int m_tile = tile / p.num_n_tiles;
+      const int m_tile = (tile / p.num_n_tiles) * CL + crank;
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
@@ -184,6 +205,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) ptx::cluster_sync();       // no CTA exits while its peer may still multicast into it
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<2 * BN>(tmem_base);
@@ -208,19 +230,29 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, long long spl
   }
 }
 
-template <int BN, int kStages, bool A_MN, bool B_MN, bool FAST_EPI>
+template <int BN, int kStages, bool A_MN, bool B_MN, bool FAST_EPI, int CL>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using L = SmemLayout<BN, kStages, A_MN, B_MN>;
-  auto kern = gemm_bf16_kernel<BN, kStages, A_MN, B_MN, FAST_EPI>;
+  auto kern = gemm_bf16_kernel<BN, kStages, A_MN, B_MN, FAST_EPI, CL>;
   static bool configured = false;
   if (!configured) {
     SFC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
-  const int total_tiles = p.num_m_tiles * p.num_n_tiles * p.splits;
-  const int grid = total_tiles < sfc_num_sms() ? total_tiles : sfc_num_sms();
-  kern<<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, p);
-  SFC_LAUNCH_OK();
+  const int units = ((p.num_m_tiles + CL - 1) / CL) * p.num_n_tiles * p.splits;
+  const int max_clusters = sfc_num_sms() / CL;
+  const int grid = (units < max_clusters ? units : max_clusters) * CL;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SFC_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
   return 0;
 }
 
@@ -231,18 +263,27 @@ extern "C" size_t sfc_gemm_workspace_bytes(int M, int N, int K, int splits) {
   return (size_t)splits * (size_t)M * (size_t)N * sizeof(float);
 }
 
-// Heuristic split-K factor for reductions over the token dimension (wgrad): enough CTAs for ~2 waves.
+// Split-K factor for reductions over the token dimension (wgrad): the output has few tiles, so K is cut into `s`
+// slices and the work units (tile pairs x slices, one per 2-CTA cluster) should fill whole waves of the 74 clusters.
+// Cost model in units of one k-block of one wave: waves * (k-blocks per slice + fixed per-tile cost) + reduce traffic.
 extern "C" int sfc_gemm_suggest_splits(int M, int N, int K) {
-  const int bn = (N >= 256) ? 256 : 128;
-  const long long tiles = (long long)sfc_ceil_div(M, BM) * sfc_ceil_div(N, bn);
+  const int bn = (N > 128) ? 256 : 128;
+  const int mt = sfc_ceil_div(M, BM), nt = sfc_ceil_div(N, bn);
   const int kblocks = sfc_ceil_div(K, BK);
-  const int sms = sfc_num_sms();
-  if (tiles >= sms || kblocks < 16) return 1;
-  long long s = (2ll * sms + tiles - 1) / tiles;
-  const long long max_s = kblocks / 8 > 0 ? kblocks / 8 : 1;   // at least 8 k-blocks per split
-  if (s > max_s) s = max_s;
-  if (s > 64) s = 64;
-  return s < 1 ? 1 : (int)s;
+  const int cl = mt >= 2 ? 2 : 1;
+  const long long units = (long long)sfc_ceil_div(mt, cl) * nt;
+  const int slots = sfc_num_sms() / cl;
+  if (kblocks < 16) return 1;
+  int max_s = kblocks / 8;
+  if (max_s > 64) max_s = 64;
+  double best = 1e30;
+  int best_s = 1;
+  for (int s = 1; s <= max_s; ++s) {
+    const long long waves = (units * s + slots - 1) / slots;
+    const double cost = (double)waves * (sfc_ceil_div(kblocks, s) + 16.0) + (s > 1 ? s * (0.06 * mt * nt) + 8.0 : 0.0);
+    if (cost < best) { best = cost; best_s = s; }
+  }
+  return best_s;
 }
 
 extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major, long long ldb,
@@ -290,25 +331,29 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
     SFC_REQUIRE(!ep->accumulate, "sfc_gemm_bf16: accumulate requires split-K (splits > 1)");
   }
 
+  const bool fast = epi_fast_ok(pk.epi);
+  static const bool cl_off = getenv("SFC_GEMM_NOCLUSTER") != nullptr;
+  const bool cl2 = fast && !cl_off && p.num_m_tiles >= 2;      // 2-CTA clusters sharing the B tile by TMA multicast
   CUtensorMap ta, tb;
   // K-major operand: global [rows = M or N][cols = K]; MN-major operand: global [rows = K][cols = M or N].
   if (!a_mn_major) { if (int e = sfc_make_tmap_2d(&ta, A, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK, BM, true)) return e; }
   else             { if (int e = sfc_make_tmap_2d(&ta, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, BK, true)) return e; }
-  if (!b_mn_major) { if (int e = sfc_make_tmap_2d(&tb, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, (uint32_t)BN, true)) return e; }
+  if (!b_mn_major) { if (int e = sfc_make_tmap_2d(&tb, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, (uint32_t)(cl2 ? BN / 2 : BN), true)) return e; }
   else             { if (int e = sfc_make_tmap_2d(&tb, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, BK, true)) return e; }
 
   int rc = 0;
-  const bool fast = epi_fast_ok(pk.epi);
-#define SFC_DISPATCH2(BN_, ST_, F_)                                                             \
+#define SFC_DISPATCH2(BN_, ST_, F_, CL_)                                                            \
   do {                                                                                          \
-    if (!a_mn_major && !b_mn_major) rc = launch_gemm<BN_, ST_, false, false, F_>(ta, tb, pk, stream); \
-    else if (!a_mn_major && b_mn_major) rc = launch_gemm<BN_, ST_, false, true, F_>(ta, tb, pk, stream); \
-    else if (a_mn_major && b_mn_major) rc = launch_gemm<BN_, ST_, true, true, F_>(ta, tb, pk, stream);  \
-    else rc = launch_gemm<BN_, ST_, true, false, F_>(ta, tb, pk, stream);                        \
+    if (!a_mn_major && !b_mn_major) rc = launch_gemm<BN_, ST_, false, false, F_, CL_>(ta, tb, pk, stream); \
+    else if (!a_mn_major && b_mn_major) rc = launch_gemm<BN_, ST_, false, true, F_, CL_>(ta, tb, pk, stream); \
+    else if (a_mn_major && b_mn_major) rc = launch_gemm<BN_, ST_, true, true, F_, CL_>(ta, tb, pk, stream);  \
+    else rc = launch_gemm<BN_, ST_, true, false, F_, CL_>(ta, tb, pk, stream);                        \
   } while (0)
 #define SFC_DISPATCH(BN_, ST_)                                                              \
   do {                                                                                      \
-    if (fast) SFC_DISPATCH2(BN_, ST_, true); else SFC_DISPATCH2(BN_, ST_, false);           \
+    if (cl2) SFC_DISPATCH2(BN_, ST_, true, 2);                                              \
+    else if (fast) SFC_DISPATCH2(BN_, ST_, true, 1);                                        \
+    else SFC_DISPATCH2(BN_, ST_, false, 1);                                                 \
   } while (0)
   if (BN == 256) SFC_DISPATCH(256, 4); else SFC_DISPATCH(128, 6);
 #undef SFC_DISPATCH2

@@ -55,6 +55,11 @@ def bench_gemm(M, D=768, F=3072):
         res = rnd(M, N)
         dys = [rnd(M, N) for _ in range(nrot)]
         fl = 2.0 * M * N * K
+        if os.environ.get("OPBENCH_CUBLAS"):
+            report(f"cublas_{name}_plain", timeit(lambda i: torch.matmul(xs[i], w.t()), nrot), fl, M=M, N=N, K=K)
+            report(f"cublas_{name}_bias", timeit(lambda i: torch.nn.functional.linear(xs[i], w, bias), nrot), fl)
+            report(f"cublas_{name}_dgrad", timeit(lambda i: torch.matmul(dys[i], w), nrot), fl)
+            report(f"cublas_{name}_wgrad", timeit(lambda i: torch.matmul(dys[i].t(), xs[i]), nrot), fl)
         report(f"fwd_{name}_plain", timeit(lambda i: ops.gemm(xs[i], w), nrot), fl, M=M, N=N, K=K)
         report(f"fwd_{name}_bias", timeit(lambda i: ops.gemm(xs[i], w, bias=bias), nrot), fl)
         if name == "ff1":
