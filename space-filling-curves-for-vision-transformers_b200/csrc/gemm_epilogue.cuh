@@ -404,3 +404,97 @@ __device__ __forceinline__ void epi_tile_fast(const EpiParams& p, uint32_t taddr
     }
   }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Direct variant (same preconditions as epi_tile_fast): no shared-memory transpose. Every lane finishes the 32 columns
+// of ITS accumulator row and stores them with four 16-byte stores (64 contiguous bytes per row); residual / aux are
+// read the same way. Needs ~50 fewer registers than the transposed variant (used where the CTA is register-tight:
+// patch_embed.cu with 512 threads). `bias_s` = this warp's private fp32 copy of bias[n_begin .. n_begin + ncols) in
+// shared memory (ncols floats; zeros when there is no bias).
+// ------------------------------------------------------------------------------------------------------------------
+template <class RowMap>
+__device__ __forceinline__ void epi_tile_direct(const EpiParams& p, uint32_t taddr, int n_begin, int ncols, long long m_base, long long M,
+                                                const RowMap& rm, int split, float* bias_s) {
+  const int lane = (int)(threadIdx.x & 31);
+  const bool has_res = p.residual != nullptr, has_aux = p.aux_mode != SFC_AUX_NONE;
+  const bool has_drop = p.drop_p > 0.0f, f32 = p.out_fp32 != 0;
+  const float relu_lo = p.act == SFC_ACT_RELU ? 0.0f : -INFINITY;
+  const float alpha = p.alpha;
+  const DropKey dkey = drop_key(p.drop_seed, p.drop_p);
+  __syncwarp();
+  for (int c0 = 0; c0 < ncols; c0 += 128) {       // lane l converts columns 4l .. 4l+3 of each 128-column group
+    const int c = c0 + lane * 4;
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias && c < ncols && n_begin + c < p.N) {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(p.bias + n_begin + c));
+      b4 = make_float4(ptx::bf16_lo(u.x), ptx::bf16_hi(u.x), ptx::bf16_lo(u.y), ptx::bf16_hi(u.y));
+    }
+    if (c < ncols) *reinterpret_cast<float4*>(bias_s + c) = b4;
+  }
+  __syncwarp();
+  const long long m = m_base + lane;
+  const bool ok = m < M;
+  long long m_out, m_res;
+  rm.map(ok ? m : 0, m_out, m_res);
+  const char* resp = reinterpret_cast<const char*>(p.residual) + (m_res * p.ld_res + n_begin) * 2;
+  const char* auxp = reinterpret_cast<const char*>(p.aux) + (m_out * p.ld_aux + n_begin) * 2;
+  char* outp = reinterpret_cast<char*>(p.out) + (f32 ? ((long long)split * p.split_stride + m_out * p.ld_out + n_begin) * 4
+                                                     : (m_out * p.ld_out + n_begin) * 2);
+  const unsigned long long didx = (unsigned long long)m_out * (unsigned long long)p.N + (unsigned long long)n_begin;
+  const int nchunks = ncols / 32;
+#pragma unroll 1
+  for (int c = 0; c < nchunks; ++c) {
+    const int coff = c * 32;
+    if (n_begin + coff >= p.N) break;          // warp-uniform
+    uint32_t raw[32];
+    ptx::tmem_ld_x32(taddr + coff, raw);
+    uint4 cr[4], ca[4];
+    if (ok) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (has_res) cr[q] = __ldg(reinterpret_cast<const uint4*>(resp + coff * 2) + q);
+        if (has_aux) ca[q] = __ldg(reinterpret_cast<const uint4*>(auxp + coff * 2) + q);
+      }
+    }
+    ptx::tmem_ld_wait();
+    if (ok) {
+      float v[32];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + coff + q * 4);     // broadcast read
+        v[q * 4 + 0] = fmaxf(fmaf(__uint_as_float(raw[q * 4 + 0]), alpha, b4.x), relu_lo);
+        v[q * 4 + 1] = fmaxf(fmaf(__uint_as_float(raw[q * 4 + 1]), alpha, b4.y), relu_lo);
+        v[q * 4 + 2] = fmaxf(fmaf(__uint_as_float(raw[q * 4 + 2]), alpha, b4.z), relu_lo);
+        v[q * 4 + 3] = fmaxf(fmaf(__uint_as_float(raw[q * 4 + 3]), alpha, b4.w), relu_lo);
+      }
+      if (has_drop) drop_apply<32>(v, dkey, didx + (unsigned long long)coff);
+      if (has_aux) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float a[8];
+          epi_unpack8(ca[q], a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[q * 8 + j] = a[j] > 0.0f ? v[q * 8 + j] : 0.0f;
+        }
+      }
+      if (has_res) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float f[8];
+          epi_unpack8(cr[q], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[q * 8 + j] += f[j];
+        }
+      }
+      if (f32) {
+        float4* op = reinterpret_cast<float4*>(outp + coff * 4);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) op[q] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+      } else {
+        uint4* op = reinterpret_cast<uint4*>(outp + coff * 2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) op[q] = epi_pack8(&v[q * 8]);
+      }
+    }
+  }
+}

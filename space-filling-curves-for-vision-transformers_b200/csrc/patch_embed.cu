@@ -24,6 +24,7 @@ constexpr int BK = 64;
 constexpr int kThreads = 512;      // warps 0-3 control, 4-7 epilogue, 8-15 gather producers
 constexpr int kEpiThreads = 128;
 constexpr int kProdWarpsPerGroup = 4;
+constexpr int kMaxTblKb = 64;      // k-blocks covered by the precomputed chunk-offset table (K <= 4096)
 
 struct PatchParams {
   const void* img;
@@ -43,7 +44,8 @@ struct PeSmem {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiOffset = kStages * kStageBytes;          // 4 epilogue warps x transpose stage
   static constexpr int kBarOffset = kEpiOffset + 4 * kEpiStageBytes;
-  static constexpr int kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16 + 1024;
+  static constexpr int kTblOffset = kBarOffset + (2 * kStages + 4) * 8 + 16;       // int32 [kMaxTblKb * 8 + kMaxTblKb]
+  static constexpr int kTotal = kTblOffset + kMaxTblKb * 9 * 4 + 1024;
   static_assert(kTotal <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
 };
 
@@ -64,8 +66,74 @@ __device__ __forceinline__ uint4 pack8f(const float* f) {
   return u;
 }
 
-// Gathers the 64 K-elements [kb*64, kb*64+64) of token row m into its 128-byte swizzled smem row.
-template <bool VEC, bool BF16IN>
+// Chunk-offset table (vectorised path, p % 8 == 0): K is ordered (q, c, p1, p2), so the image offset of the 8-element
+// chunk j of k-block kb relative to the origin of pre-patch q is the same for EVERY token:
+//   tbl[kb * 8 + j] = c * H * W + p1 * W + p2   (or -1 past K),   tblq[kb] = q   (p * p % 64 == 0: one (q, c) per k-block)
+// It is built once per CTA, which leaves one add per 16-byte load in the gather loop (no per-chunk divisions).
+__device__ __forceinline__ void build_chunk_table(const PatchParams& pp, int* tbl, int* tblq) {
+  const int p = pp.p;
+  for (int i = threadIdx.x; i < pp.num_k_blocks * 8; i += blockDim.x) {
+    const int k0 = i * 8;
+    int v = -1;
+    if (k0 < pp.K) {
+      const int p2 = k0 % p, t1 = k0 / p, p1 = t1 % p, t2 = t1 / p, c = t2 % pp.C;
+      v = c * pp.H * pp.W + p1 * pp.W + p2;
+    }
+    tbl[i] = v;
+  }
+  for (int kb = threadIdx.x; kb < pp.num_k_blocks; kb += blockDim.x) tblq[kb] = (kb * 64) / (p * p * pp.C);
+}
+
+// element offset of the origin of pre-patch q of token row m (m < M)
+__device__ __forceinline__ long long patch_origin(const PatchParams& pp, long long m, int q) {
+  const int b = (int)(m / pp.ntok);
+  const int t = (int)(m % pp.ntok);
+  const int idx = __ldg(pp.perm + t * pp.g + q);
+  const int r = idx / pp.gw, cc = idx % pp.gw;
+  return (long long)b * pp.C * pp.H * pp.W + (long long)(r * pp.p) * pp.W + cc * pp.p;
+}
+
+// Gathers the 64 K-elements [kb*64, kb*64+64) of one token row into its 128-byte swizzled smem row (vectorised path).
+// `origin` = patch_origin of the k-block's q for this row (ignored when !row_ok).
+template <bool BF16IN>
+__device__ __forceinline__ void gather_row_vec(const PatchParams& pp, bool row_ok, long long origin, int row, int kb, const int* tbl,
+                                               uint8_t* smem_a) {
+  uint8_t* srow = smem_a + row * 128;
+  const int sw = row & 7;
+  uint4 raw[8][BF16IN ? 1 : 2];
+  int off[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    off[j] = tbl[kb * 8 + j];                     // broadcast shared-memory read
+    if (row_ok && off[j] >= 0) {
+      if constexpr (BF16IN) {
+        raw[j][0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(pp.img) + origin + off[j]));
+      } else {
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(pp.img) + origin + off[j]);
+        raw[j][0] = __ldg(src);
+        raw[j][1] = __ldg(src + 1);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (row_ok && off[j] >= 0) {
+      if constexpr (BF16IN) {
+        o = raw[j][0];
+      } else {
+        o.x = ptx::pack_bf16(__uint_as_float(raw[j][0].x), __uint_as_float(raw[j][0].y));
+        o.y = ptx::pack_bf16(__uint_as_float(raw[j][0].z), __uint_as_float(raw[j][0].w));
+        o.z = ptx::pack_bf16(__uint_as_float(raw[j][1].x), __uint_as_float(raw[j][1].y));
+        o.w = ptx::pack_bf16(__uint_as_float(raw[j][1].z), __uint_as_float(raw[j][1].w));
+      }
+    }
+    *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = o;
+  }
+}
+
+// Generic element-wise gather (any p, g): pixel-level tokenizers (p = 1) and small pre-patches.
+template <bool BF16IN>
 __device__ __forceinline__ void gather_row(const PatchParams& pp, long long m, int row, int kb, uint8_t* smem_a) {
   uint8_t* srow = smem_a + row * 128;
   const int sw = row & 7;
@@ -78,50 +146,7 @@ __device__ __forceinline__ void gather_row(const PatchParams& pp, long long m, i
   const int t = (int)(m % pp.ntok);
   const int p = pp.p;
   const long long plane = (long long)pp.H * pp.W;
-  if constexpr (VEC) {
-    // p % 8 == 0: each 8-element chunk is one contiguous run inside a patch row
-    uint4 raw[8][BF16IN ? 1 : 2];
-    bool valid[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k0 = kb * 64 + j * 8;
-      valid[j] = k0 < pp.K;
-      if (valid[j]) {
-        const int p2 = k0 % p;
-        const int t1 = k0 / p;
-        const int p1 = t1 % p;
-        const int t2 = t1 / p;
-        const int c = t2 % pp.C;
-        const int q = t2 / pp.C;
-        const int idx = __ldg(pp.perm + t * pp.g + q);
-        const int r = idx / pp.gw, cc = idx % pp.gw;
-        const long long off = ((long long)b * pp.C + c) * plane + (long long)(r * p + p1) * pp.W + cc * p + p2;
-        if constexpr (BF16IN) {
-          raw[j][0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(pp.img) + off));
-        } else {
-          const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(pp.img) + off);
-          raw[j][0] = __ldg(src);
-          raw[j][1] = __ldg(src + 1);
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      uint4 o = make_uint4(0, 0, 0, 0);
-      if (valid[j]) {
-        if constexpr (BF16IN) {
-          o = raw[j][0];
-        } else {
-          o.x = ptx::pack_bf16(__uint_as_float(raw[j][0].x), __uint_as_float(raw[j][0].y));
-          o.y = ptx::pack_bf16(__uint_as_float(raw[j][0].z), __uint_as_float(raw[j][0].w));
-          o.z = ptx::pack_bf16(__uint_as_float(raw[j][1].x), __uint_as_float(raw[j][1].y));
-          o.w = ptx::pack_bf16(__uint_as_float(raw[j][1].z), __uint_as_float(raw[j][1].w));
-        }
-      }
-      *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = o;
-    }
-  } else {
-    // generic element-wise gather (any p, g): pixel-level tokenizers (p = 1) and small pre-patches
+  {
     const int k_begin = kb * 64;
     int p2 = k_begin % p;
     int t1 = k_begin / p;
@@ -163,7 +188,7 @@ __device__ __forceinline__ void gather_row(const PatchParams& pp, long long m, i
   }
 }
 
-template <int BN, int kStages, bool VEC, bool BF16IN>
+template <int BN, int kStages, bool VEC, bool BF16IN, bool FAST_EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 patch_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchParams pp) {
   static_assert(kStages % 2 == 0, "producer groups alternate stages by parity");
@@ -175,9 +200,12 @@ patch_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchPa
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  int* tbl = reinterpret_cast<int*>(smem + L::kTblOffset);
+  int* tblq = tbl + kMaxTblKb * 8;
 
   const int warp = threadIdx.x >> 5;
   const int total_tiles = pp.num_m_tiles * pp.num_n_tiles;
+  if constexpr (VEC) build_chunk_table(pp, tbl, tblq);
 
   if (warp == 0 && ptx::elect_one()) ptx::prefetch_tmap(&tmap_w);
   if (warp == 1 && ptx::elect_one()) {
@@ -258,7 +286,8 @@ patch_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchPa
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(ewarp * 32) << 16);
-      epi_tile(pp.epi, taddr, n_tile * BN, BN, (long long)m_tile * BM + ewarp * 32, pp.M, rm, 0, stage);
+      if constexpr (FAST_EPI) epi_tile_direct(pp.epi, taddr, n_tile * BN, BN, (long long)m_tile * BM + ewarp * 32, pp.M, rm, 0, reinterpret_cast<float*>(stage));
+      else epi_tile(pp.epi, taddr, n_tile * BN, BN, (long long)m_tile * BM + ewarp * 32, pp.M, rm, 0, stage);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
     }
@@ -271,12 +300,20 @@ patch_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchPa
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / pp.num_n_tiles;
       const long long m = (long long)m_tile * BM + row;
+      const bool row_ok = m < pp.M;
+      int cur_q = -1;
+      long long origin = 0;
       for (int kb = 0; kb < pp.num_k_blocks; ++kb, ++it) {
         if ((it & 1) != group) continue;
         const int stage = it % kStages;
         const uint32_t phase = (it / kStages) & 1;
+        if constexpr (VEC) {
+          const int q = tblq[kb];
+          if (row_ok && q != cur_q && q < pp.g) { origin = patch_origin(pp, m, q); cur_q = q; }
+        }
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-        gather_row<VEC, BF16IN>(pp, m, row, kb, smem + stage * L::kStageBytes);
+        if constexpr (VEC) gather_row_vec<BF16IN>(pp, row_ok, origin, row, kb, tbl, smem + stage * L::kStageBytes);
+        else gather_row<BF16IN>(pp, m, row, kb, smem + stage * L::kStageBytes);
         ptx::fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (ptx::elect_one()) ptx::mbar_arrive(&full_bar[stage]);
@@ -294,30 +331,53 @@ patch_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchPa
 
 // A-only gather: writes the curve-ordered im2col matrix A[M, Kpad] (bf16). Used by the backward pass
 // (weight gradient) only; the forward never materialises it.
-template <bool BF16IN>
+template <bool BF16IN, bool VEC>
 __global__ void __launch_bounds__(256) patch_gather_kernel(const PatchParams pp, __nv_bfloat16* __restrict__ A) {
-  const long long total = pp.M * (long long)(pp.Kpad / 8);
+  const int cpr = pp.Kpad / 8;                                   // 8-element chunks per row
+  const long long total = pp.M * (long long)cpr;
   const int p = pp.p;
   const long long plane = (long long)pp.H * pp.W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long m = i / (pp.Kpad / 8);
-    const int k0 = (int)(i % (pp.Kpad / 8)) * 8;
-    const int b = (int)(m / pp.ntok), t = (int)(m % pp.ntok);
-    float f[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int k = k0 + e;
-      f[e] = 0.f;
-      if (k < pp.K) {
-        const int p2 = k % p, t1 = k / p, p1 = t1 % p, t2 = t1 / p, c = t2 % pp.C, q = t2 / pp.C;
+    const long long m = i / cpr;
+    const int k0 = (int)(i - m * cpr) * 8;
+    const int b = (int)(m / pp.ntok), t = (int)(m - (long long)b * pp.ntok);
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if constexpr (VEC) {
+      // p % 8 == 0: the chunk is one contiguous run inside a patch row
+      if (k0 < pp.K) {
+        const int p2 = k0 % p, t1 = k0 / p, p1 = t1 % p, t2 = t1 / p, c = t2 % pp.C, q = t2 / pp.C;
         const int idx = __ldg(pp.perm + t * pp.g + q);
-        const int r = idx / pp.gw, cc = idx % pp.gw;
+        const int r = idx / pp.gw, cc = idx - r * pp.gw;
         const long long off = ((long long)b * pp.C + c) * plane + (long long)(r * p + p1) * pp.W + cc * p + p2;
-        if constexpr (BF16IN) f[e] = __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(pp.img) + off));
-        else f[e] = __ldg(reinterpret_cast<const float*>(pp.img) + off);
+        if constexpr (BF16IN) {
+          o = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(pp.img) + off));
+        } else {
+          const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(pp.img) + off);
+          const uint4 lo = __ldg(src), hi = __ldg(src + 1);
+          o.x = ptx::pack_bf16(__uint_as_float(lo.x), __uint_as_float(lo.y));
+          o.y = ptx::pack_bf16(__uint_as_float(lo.z), __uint_as_float(lo.w));
+          o.z = ptx::pack_bf16(__uint_as_float(hi.x), __uint_as_float(hi.y));
+          o.w = ptx::pack_bf16(__uint_as_float(hi.z), __uint_as_float(hi.w));
+        }
       }
+    } else {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = k0 + e;
+        f[e] = 0.f;
+        if (k < pp.K) {
+          const int p2 = k % p, t1 = k / p, p1 = t1 % p, t2 = t1 / p, c = t2 % pp.C, q = t2 / pp.C;
+          const int idx = __ldg(pp.perm + t * pp.g + q);
+          const int r = idx / pp.gw, cc = idx % pp.gw;
+          const long long off = ((long long)b * pp.C + c) * plane + (long long)(r * p + p1) * pp.W + cc * p + p2;
+          if constexpr (BF16IN) f[e] = __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(pp.img) + off));
+          else f[e] = __ldg(reinterpret_cast<const float*>(pp.img) + off);
+        }
+      }
+      o = pack8f(f);
     }
-    *reinterpret_cast<uint4*>(A + m * pp.Kpad + k0) = pack8f(f);
+    *reinterpret_cast<uint4*>(A + m * pp.Kpad + k0) = o;
   }
 }
 
@@ -341,10 +401,10 @@ int fill_params(PatchParams& pp, const void* img, int img_bf16, int B, int C, in
   return 0;
 }
 
-template <int BN, int kStages, bool VEC, bool BF16IN>
+template <int BN, int kStages, bool VEC, bool BF16IN, bool FAST_EPI>
 int launch_pe(const CUtensorMap& tw, const PatchParams& pp, cudaStream_t stream) {
   using L = PeSmem<BN, kStages>;
-  auto kern = patch_embed_fwd_kernel<BN, kStages, VEC, BF16IN>;
+  auto kern = patch_embed_fwd_kernel<BN, kStages, VEC, BF16IN, FAST_EPI>;
   static bool configured = false;
   if (!configured) {
     SFC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -377,15 +437,22 @@ extern "C" int sfc_patch_embed_fwd(const void* img, int img_bf16, int B, int C, 
   e.alpha = 1.0f; e.act = SFC_ACT_NONE; e.aux_mode = SFC_AUX_NONE; e.out_fp32 = 0; e.drop_p = 0.f; e.drop_seed = 0;
   CUtensorMap tw;
   if (int err = sfc_make_tmap_2d(&tw, Wk, 2, (uint64_t)pp.Kpad, (uint64_t)D, (uint64_t)pp.Kpad * 2, BK, (uint32_t)BN, true)) return err;
-  const bool vec = (p % 8 == 0) && (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0) && (((long long)H * W) % 8 == 0);
+  const bool vec = (p % 8 == 0) && (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0) && (((long long)H * W) % 8 == 0) &&
+                   pp.num_k_blocks <= kMaxTblKb && ((long long)C * H * W < (1ll << 31));
+  const bool fast = epi_fast_ok(pp.epi);
+#define PE_DISPATCH2(BN_, ST_, F_)                                                              \
+  do {                                                                                          \
+    if (vec && img_bf16) return launch_pe<BN_, ST_, true, true, F_>(tw, pp, stream);            \
+    if (vec && !img_bf16) return launch_pe<BN_, ST_, true, false, F_>(tw, pp, stream);          \
+    if (!vec && img_bf16) return launch_pe<BN_, ST_, false, true, F_>(tw, pp, stream);          \
+    return launch_pe<BN_, ST_, false, false, F_>(tw, pp, stream);                               \
+  } while (0)
 #define PE_DISPATCH(BN_, ST_)                                                                   \
   do {                                                                                          \
-    if (vec && img_bf16) return launch_pe<BN_, ST_, true, true>(tw, pp, stream);                \
-    if (vec && !img_bf16) return launch_pe<BN_, ST_, true, false>(tw, pp, stream);              \
-    if (!vec && img_bf16) return launch_pe<BN_, ST_, false, true>(tw, pp, stream);              \
-    return launch_pe<BN_, ST_, false, false>(tw, pp, stream);                                   \
+    if (fast) PE_DISPATCH2(BN_, ST_, true); else PE_DISPATCH2(BN_, ST_, false);                 \
   } while (0)
   if (BN == 256) PE_DISPATCH(256, 4); else PE_DISPATCH(128, 6);
+#undef PE_DISPATCH2
 #undef PE_DISPATCH
 }
 
@@ -397,10 +464,14 @@ extern "C" int sfc_patch_gather(const void* img, int img_bf16, int B, int C, int
   SFC_REQUIRE(A, "sfc_patch_gather: null output");
   const long long total = pp.M * (long long)(pp.Kpad / 8);
   long long blocks = sfc_ceil_div64(total, 256);
-  const long long cap = 16ll * sfc_num_sms();
+  const long long cap = 32ll * sfc_num_sms();
   if (blocks > cap) blocks = cap;
-  if (img_bf16) patch_gather_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(pp, (__nv_bfloat16*)A);
-  else patch_gather_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(pp, (__nv_bfloat16*)A);
+  const bool vec = (p % 8 == 0) && (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0) && (((long long)H * W) % 8 == 0);
+  const unsigned nb = (unsigned)blocks;
+  if (img_bf16 && vec) patch_gather_kernel<true, true><<<nb, 256, 0, stream>>>(pp, (__nv_bfloat16*)A);
+  else if (img_bf16) patch_gather_kernel<true, false><<<nb, 256, 0, stream>>>(pp, (__nv_bfloat16*)A);
+  else if (vec) patch_gather_kernel<false, true><<<nb, 256, 0, stream>>>(pp, (__nv_bfloat16*)A);
+  else patch_gather_kernel<false, false><<<nb, 256, 0, stream>>>(pp, (__nv_bfloat16*)A);
   SFC_LAUNCH_OK();
   return 0;
 }
