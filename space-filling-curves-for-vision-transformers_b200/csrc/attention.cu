@@ -254,12 +254,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         if (warp_active) {
           const int kv_valid = min(bkv, p.N - j * bkv);
           const int nch = (kv_valid + 31) / 32;
+          // Both passes keep the TMEM load of the next 32-column chunk in flight while the current one is processed
+          // (two register buffers, loop unrolled by two so that they stay in registers).
           float mx = -INFINITY;
-#pragma unroll 1
-          for (int c = 0; c < nch; ++c) {
-            uint32_t rr[32];
-            ptx::tmem_ld_x32(t_s + c * 32, rr);
-            ptx::tmem_ld_wait();
+          uint32_t ra[32], rb[32];
+          auto max_chunk = [&](const uint32_t (&rr)[32], int c) {
             if (c * 32 + 32 <= kv_valid) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rr[i]));
@@ -268,35 +267,75 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               for (int i = 0; i < 32; ++i)
                 if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(rr[i]));
             }
+          };
+          ptx::tmem_ld_x32(t_s, ra);
+          if constexpr (kSingle) {
+#pragma unroll 1
+            for (int c = 0; c < nch; c += 2) {
+              ptx::tmem_ld_wait();
+              if (c + 1 < nch) ptx::tmem_ld_x32(t_s + (c + 1) * 32, rb);
+              max_chunk(ra, c);
+              if (c + 1 < nch) {
+                ptx::tmem_ld_wait();
+                if (c + 2 < nch) ptx::tmem_ld_x32(t_s + (c + 2) * 32, ra);
+                max_chunk(rb, c + 1);
+              }
+            }
+          } else {                                      // o_acc[64] is live here: one buffer only
+#pragma unroll 1
+            for (int c = 0; c < nch; ++c) {
+              ptx::tmem_ld_wait();
+              max_chunk(ra, c);
+              if (c + 1 < nch) ptx::tmem_ld_x32(t_s + (c + 1) * 32, ra);
+            }
           }
+          ptx::tmem_ld_x32(t_s, ra);                    // first chunk of pass 2, in flight during the scalar work below
           const float m_new = fmaxf(m_run, mx);
           alpha = ex2_approx((m_run - m_new) * sl2);   // m_run = -inf on the first tile -> 0
           const float mb = m_new * sl2;
           float psum = 0.f;
-          const unsigned long long drop_row = (((unsigned long long)(b * p.H + h) * p.N + (unsigned long long)qi) * p.N) + (unsigned long long)(j * bkv);
+          // dropout index space: (probability row) x (key index, row pitch padded to 16 so that 16-key groups are aligned)
+          const unsigned long long drop_row = (((unsigned long long)(b * p.H + h) * p.N + (unsigned long long)qi) * (unsigned long long)((p.N + 15) & ~15)) + (unsigned long long)(j * bkv);
           const int nch_all = (bkv + 31) / 32;         // P columns read by the PV MMA: [0, bkv)
-#pragma unroll 1
-          for (int c = 0; c < nch_all; ++c) {
+          auto exp_chunk = [&](const uint32_t (&rr)[32], int c) {
             float pv[32];
-            if (c < nch) {
-              uint32_t rr[32];
-              ptx::tmem_ld_x32(t_s + c * 32, rr);
-              ptx::tmem_ld_wait();
-              if (c * 32 + 32 <= kv_valid) {
+            if (c * 32 + 32 <= kv_valid) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { pv[i] = ex2_approx(fmaf(__uint_as_float(rr[i]), sl2, -mb)); psum += pv[i]; }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  pv[i] = (c * 32 + i < kv_valid) ? ex2_approx(fmaf(__uint_as_float(rr[i]), sl2, -mb)) : 0.f;
-                  psum += pv[i];
-                }
-              }
-              if (has_drop) drop_apply<32>(pv, dkey, drop_row + (unsigned long long)(c * 32));
+              for (int i = 0; i < 32; ++i) { pv[i] = ex2_approx(fmaf(__uint_as_float(rr[i]), sl2, -mb)); psum += pv[i]; }
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) pv[i] = 0.f;
+              for (int i = 0; i < 32; ++i) {
+                pv[i] = (c * 32 + i < kv_valid) ? ex2_approx(fmaf(__uint_as_float(rr[i]), sl2, -mb)) : 0.f;
+                psum += pv[i];
+              }
             }
+            if (has_drop) drop_apply<32, 16>(pv, dkey, drop_row + (unsigned long long)(c * 32));
+            store_p_chunk(p_smem, r, c, pv);
+          };
+          if constexpr (kSingle) {
+#pragma unroll 1
+            for (int c = 0; c < nch; c += 2) {
+              ptx::tmem_ld_wait();
+              if (c + 1 < nch) ptx::tmem_ld_x32(t_s + (c + 1) * 32, rb);
+              exp_chunk(ra, c);
+              if (c + 1 < nch) {
+                ptx::tmem_ld_wait();
+                if (c + 2 < nch) ptx::tmem_ld_x32(t_s + (c + 2) * 32, ra);
+                exp_chunk(rb, c + 1);
+              }
+            }
+          } else {
+#pragma unroll 1
+            for (int c = 0; c < nch; ++c) {
+              ptx::tmem_ld_wait();
+              exp_chunk(ra, c);
+              if (c + 1 < nch) ptx::tmem_ld_x32(t_s + (c + 1) * 32, ra);
+            }
+          }
+          for (int c = nch; c < nch_all; ++c) {        // key columns past the sequence end inside [0, bkv)
+            float pv[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) pv[i] = 0.f;
             store_p_chunk(p_smem, r, c, pv);
           }
           l_run = l_run * alpha + psum;
@@ -655,7 +694,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
         // ---- phase A: P = exp2(S * scale * log2e - lse * log2e), kept in registers (+ dropout keep bits)
         float pr[2][32];
-        uint32_t keep[2] = {0xffffffffu, 0xffffffffu};
         ptx::mbar_wait(&bars[BwdBars::s_full + (s & 1)], (s >> 1) & 1);
         ptx::tc_fence_after();
         if (warp_active) {
@@ -672,20 +710,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 pr[cc][e] = ok ? ex2_approx(fmaf(__uint_as_float(rs[e]), sl2, -lse2)) : 0.f;
               }
               if (has_drop) {
-                const unsigned long long base = (((unsigned long long)(b * p.H + h) * p.N + (unsigned long long)qi) * p.N) + (unsigned long long)(kv0 + c * 32);
-                uint32_t kb = 0;
-                if ((base & 1ull) == 0) {
+                // the keep decision travels to phase B in the sign of P (P >= 0): dropped elements are stored negated
+                const unsigned long long base = (((unsigned long long)(b * p.H + h) * p.N + (unsigned long long)qi) * (unsigned long long)((p.N + 15) & ~15)) + (unsigned long long)(kv0 + c * 32);
+                if ((base & 15ull) == 0) {
 #pragma unroll
-                  for (int g2 = 0; g2 < 16; ++g2) {
-                    const uint32_t hsh = drop_hash2(dkey, (base >> 1) + g2);
-                    kb |= ((hsh << 16) >= thr_hi ? 1u : 0u) << (2 * g2);
-                    kb |= (hsh >= thr_hi ? 1u : 0u) << (2 * g2 + 1);
+                  for (int g2 = 0; g2 < 2; ++g2) {
+                    const uint32_t seed = drop_hash2(dkey, (base >> 4) + g2);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                      const uint32_t x = seed * lcg_mul(e + 1) + lcg_add(e + 1);
+                      pr[cc][g2 * 16 + e] = (x >= thr_hi) ? pr[cc][g2 * 16 + e] : -pr[cc][g2 * 16 + e];
+                    }
                   }
                 } else {
 #pragma unroll
-                  for (int e = 0; e < 32; ++e) kb |= (drop_keep(dkey, base + e) ? 1u : 0u) << e;
+                  for (int e = 0; e < 32; ++e) pr[cc][e] = drop_keep<16>(dkey, base + e) ? pr[cc][e] : -pr[cc][e];
                 }
-                keep[cc] = kb;
               }
             }
           }
@@ -708,11 +748,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 float pv[16], dsv[16];
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                  const float pe = pr[cc][hf * 16 + e];
+                  const float ps = pr[cc][hf * 16 + e];
+                  const float pe = fabsf(ps);
                   float dp = __uint_as_float(rd[e]);
                   float pd = pe;
                   if (has_drop) {
-                    const bool k = (keep[cc] >> (hf * 16 + e)) & 1u;
+                    const bool k = ps > 0.f;
                     pd = k ? pe * dkey.inv_keep : 0.f;
                     dp = k ? dp * dkey.inv_keep : 0.f;
                   }

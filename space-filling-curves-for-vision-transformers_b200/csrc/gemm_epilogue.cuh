@@ -67,24 +67,40 @@ __device__ __forceinline__ uint32_t drop_hash2(const DropKey& k, unsigned long l
   x ^= x >> 16;
   return x;
 }
+// Within an aligned group of G consecutive elements the lanes come from ONE hash (the group seed) expanded by G
+// independent steps of a 32-bit LCG, x_i = seed * A^(i+1) + C_(i+1) (one multiply-add each, no dependency chain);
+// element i of the group is kept iff x_i >= thr16 << 16, i.e. its top 16 bits are the uniform lane. Forward and
+// backward of a dropout site must use the same G (8 for GEMM-output dropout, 16 for attention probabilities).
+constexpr uint32_t kLcgA = 747796405u, kLcgC = 2891336453u;
+__host__ __device__ constexpr uint32_t lcg_mul(int n) { uint32_t a = 1u; for (int i = 0; i < n; ++i) a *= kLcgA; return a; }
+__host__ __device__ constexpr uint32_t lcg_add(int n) { uint32_t c = 0u; for (int i = 0; i < n; ++i) c = c * kLcgA + kLcgC; return c; }
+
+template <int G>
 __device__ __forceinline__ bool drop_keep(const DropKey& k, unsigned long long idx) {
-  const uint32_t h = drop_hash2(k, idx >> 1);
-  return ((idx & 1ull) ? (h >> 16) : (h & 0xffffu)) >= k.thr16;
+  const uint32_t seed = drop_hash2(k, idx / G);
+  uint32_t x = seed;
+  const int pos = (int)(idx % G);
+  for (int i = 0; i <= pos; ++i) x = x * kLcgA + kLcgC;
+  return x >= (k.thr16 << 16);
 }
-// v[i] = keep(base + i) ? v[i] * inv_keep : 0 for NV consecutive elements (NV even)
-template <int NV>
+// v[i] = keep(base + i) ? v[i] * inv_keep : 0 for NV consecutive elements
+template <int NV, int G>
 __device__ __forceinline__ void drop_apply(float* v, const DropKey& k, unsigned long long base) {
-  if ((base & 1ull) == 0) {
-    const uint32_t thr_hi = k.thr16 << 16;
+  static_assert(NV % G == 0, "NV must be a multiple of the group size");
+  const uint32_t thr_hi = k.thr16 << 16;
+  if (base % G == 0) {
 #pragma unroll
-    for (int g = 0; g < NV / 2; ++g) {
-      const uint32_t h = drop_hash2(k, (base >> 1) + g);
-      v[2 * g] = ((h << 16) >= thr_hi) ? v[2 * g] * k.inv_keep : 0.f;
-      v[2 * g + 1] = (h >= thr_hi) ? v[2 * g + 1] * k.inv_keep : 0.f;    // low bits of h only break ties inside one lane value
+    for (int g = 0; g < NV / G; ++g) {
+      const uint32_t seed = drop_hash2(k, base / G + g);
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const uint32_t x = seed * lcg_mul(i + 1) + lcg_add(i + 1);
+        v[g * G + i] = (x >= thr_hi) ? v[g * G + i] * k.inv_keep : 0.f;
+      }
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = drop_keep(k, base + i) ? v[i] * k.inv_keep : 0.f;
+    for (int i = 0; i < NV; ++i) v[i] = drop_keep<G>(k, base + i) ? v[i] * k.inv_keep : 0.f;
   }
 }
 
@@ -165,7 +181,7 @@ __device__ __forceinline__ void epi_apply_store8(const EpiParams& p, const EpiLa
     for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
   }
   if (p.drop_p > 0.0f)
-    drop_apply<8>(v, L.dkey, (unsigned long long)m_out * (unsigned long long)p.N + (unsigned long long)n);
+    drop_apply<8, 8>(v, L.dkey, (unsigned long long)m_out * (unsigned long long)p.N + (unsigned long long)n);
   if (p.aux_mode != SFC_AUX_NONE) {
     float a[8];
     if (L.aux_vec && full) {
@@ -374,7 +390,7 @@ __device__ __forceinline__ void epi_tile_fast(const EpiParams& p, uint32_t taddr
                       __uint_as_float(hi.x), __uint_as_float(hi.y), __uint_as_float(hi.z), __uint_as_float(hi.w)};
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], alpha, bf[j]), relu_lo);
-        if (has_drop) drop_apply<8>(v, dkey, didx[it] + (unsigned long long)coff);
+        if (has_drop) drop_apply<8, 8>(v, dkey, didx[it] + (unsigned long long)coff);
         if (has_aux) {
           float a[8];
           epi_unpack8(ca[it], a);
@@ -467,7 +483,7 @@ __device__ __forceinline__ void epi_tile_direct(const EpiParams& p, uint32_t tad
         v[q * 4 + 2] = fmaxf(fmaf(__uint_as_float(raw[q * 4 + 2]), alpha, b4.z), relu_lo);
         v[q * 4 + 3] = fmaxf(fmaf(__uint_as_float(raw[q * 4 + 3]), alpha, b4.w), relu_lo);
       }
-      if (has_drop) drop_apply<32>(v, dkey, didx + (unsigned long long)coff);
+      if (has_drop) drop_apply<32, 8>(v, dkey, didx + (unsigned long long)coff);
       if (has_aux) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {

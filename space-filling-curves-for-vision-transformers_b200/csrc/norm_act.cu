@@ -155,7 +155,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         }
         dxr[vi] = pack8(o);
         if (DROP) {
-          drop_apply<8>(o, dkey, (unsigned long long)row * (unsigned long long)D + (unsigned long long)(vi * 8));
+          drop_apply<8, 8>(o, dkey, (unsigned long long)row * (unsigned long long)D + (unsigned long long)(vi * 8));
           reinterpret_cast<uint4*>(dx_drop + row * D)[vi] = pack8(o);
         }
         if (CSUM) {
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __res
       }
       o[j] = v;
     }
-    if (drop_p > 0.f) drop_apply<8>(o, dkey, (unsigned long long)i * 8ull);
+    if (drop_p > 0.f) drop_apply<8, 8>(o, dkey, (unsigned long long)i * 8ull);
     reinterpret_cast<uint4*>(out)[i] = pack8(o);
   }
 }
