@@ -32,6 +32,10 @@ typedef struct CUstream_st* sfc_stream_t; /* == cudaStream_t */
 const char* sfc_last_error(void);
 int sfc_abi_version(void);
 int sfc_device_sm_count(void);
+/* Dropout under CUDA graphs: kernels that draw dropout masks (GEMM epilogue, LayerNorm backward, activation backward,
+ * attention) add *epoch_dev (a device-resident 64-bit counter, may be NULL = 0) to their seed at run time, so a captured
+ * step draws fresh masks on every replay when the graph increments the counter. Process-wide; set before capture. */
+void sfc_set_dropout_epoch_ptr(const void* epoch_dev);
 
 /* ---- K1: curve permutation (src/curves/space_filling_curves.py:74-251 generators,
  *      :458-491 grid_size/embed_and_prune_sfc; tokenizer flat index multi_hilbert.py:68-72) ----

@@ -32,6 +32,7 @@ struct AttnParams {
   float scale;
   float drop_p;
   unsigned long long drop_seed;
+  const unsigned long long* drop_epoch;
   __nv_bfloat16* out;      // fwd: O [B*N, D]
   float* lse;              // [B, H, N]
   // backward
@@ -233,7 +234,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t t_s = tmem_base + w * 256 + ((uint32_t)(quarter * 32) << 16);
     uint8_t* p_smem = smem + L.off_p + w * L.p_atoms * kTile;
     const float sl2 = p.scale * kLog2e;
-    const DropKey dkey = drop_key(p.drop_seed, p.drop_p);
+    const DropKey dkey = drop_key(p.drop_seed, p.drop_p, p.drop_epoch);
     const bool has_drop = p.drop_p > 0.f;
     int g = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -622,7 +623,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int r = quarter * 32 + lane;             // query row in tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const float sl2 = p.scale * kLog2e;
-    const DropKey dkey = drop_key(p.drop_seed, p.drop_p);
+    const DropKey dkey = drop_key(p.drop_seed, p.drop_p, p.drop_epoch);
     const bool has_drop = p.drop_p > 0.f;
     const uint32_t thr_hi = dkey.thr16 << 16;
     const int nch = (bkv + 31) / 32;
@@ -816,7 +817,7 @@ extern "C" int sfc_attn_fwd(const void* qkv, void* out, float* lse, int B, int H
   if (int e = sfc_make_tmap_2d(&tq, qkv, 2, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D * 2, DH, BQ, true)) return e;
   if (int e = sfc_make_tmap_2d(&tkv, qkv, 2, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D * 2, DH, (uint32_t)L.bkv, true)) return e;
   AttnParams p{};
-  p.B = B; p.H = H; p.N = N; p.D = D; p.scale = scale; p.drop_p = drop_p; p.drop_seed = drop_seed;
+  p.B = B; p.H = H; p.N = N; p.D = D; p.scale = scale; p.drop_p = drop_p; p.drop_seed = drop_seed; p.drop_epoch = sfc_dropout_epoch_ptr();
   p.out = (__nv_bfloat16*)out; p.lse = lse;
   static bool configured = false;
   if (!configured) {
@@ -864,7 +865,7 @@ extern "C" int sfc_attn_bwd(const void* qkv, const void* out, const void* dout, 
   if (int e = sfc_make_tmap_2d(&tkv, qkv, 2, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D * 2, DH, (uint32_t)bkv, true)) return e;
   if (int e = sfc_make_tmap_2d(&tdo, dout, 2, (uint64_t)D, (uint64_t)B * N, (uint64_t)D * 2, DH, BQ, true)) return e;
   AttnParams p{};
-  p.B = B; p.H = H; p.N = N; p.D = D; p.scale = scale; p.drop_p = drop_p; p.drop_seed = drop_seed;
+  p.B = B; p.H = H; p.N = N; p.D = D; p.scale = scale; p.drop_p = drop_p; p.drop_seed = drop_seed; p.drop_epoch = sfc_dropout_epoch_ptr();
   p.lse = const_cast<float*>(lse); p.o = (const __nv_bfloat16*)out; p.dout = (const __nv_bfloat16*)dout;
   p.dqkv = (__nv_bfloat16*)dqkv; p.dq_acc = (float*)scratch; p.delta = delta;
   static bool configured = false;

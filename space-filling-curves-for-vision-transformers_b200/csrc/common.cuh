@@ -46,6 +46,7 @@ int sfc_make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_
                      uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows, bool swizzle128);
 
 int sfc_num_sms();
+const unsigned long long* sfc_dropout_epoch_ptr();   // device pointer or null (sfc_set_dropout_epoch_ptr)
 
 static inline int sfc_ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t sfc_ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

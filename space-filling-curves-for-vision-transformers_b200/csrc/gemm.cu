@@ -315,7 +315,7 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
   e.ld_out = ep->ld_out; e.ld_res = ep->ld_res; e.ld_aux = ep->ld_aux;
   e.alpha = ep->alpha;
   e.act = ep->act; e.aux_mode = ep->aux_mode; e.out_fp32 = ep->out_fp32;
-  e.drop_p = ep->drop_p; e.drop_seed = ep->drop_seed;
+  e.drop_p = ep->drop_p; e.drop_seed = ep->drop_seed; e.drop_epoch = sfc_dropout_epoch_ptr();
   e.split_stride = 0;
   SFC_REQUIRE(e.aux_mode == SFC_AUX_NONE || e.aux != nullptr, "sfc_gemm_bf16: aux_mode set but aux is null");
   SFC_REQUIRE(e.drop_p >= 0.f && e.drop_p < 1.f, "sfc_gemm_bf16: dropout p out of range");

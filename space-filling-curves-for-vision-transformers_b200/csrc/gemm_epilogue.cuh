@@ -25,6 +25,7 @@ struct EpiParams {
   int out_fp32;
   float drop_p;                   // dropout prob applied after activation (0 = off)
   unsigned long long drop_seed;
+  const unsigned long long* drop_epoch;   // optional device counter mixed into the seed (null = none)
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -46,7 +47,8 @@ __device__ __forceinline__ uint32_t drop_thr16(float p) { return (uint32_t)(p * 
 __device__ __forceinline__ float drop_inv_keep(float p) {
   return p > 0.f ? 65536.0f / (65536.0f - (float)drop_thr16(p)) : 1.0f;
 }
-__device__ __forceinline__ DropKey drop_key(unsigned long long seed, float p) {
+__device__ __forceinline__ DropKey drop_key(unsigned long long seed, float p, const unsigned long long* epoch = nullptr) {
+  if (epoch != nullptr) seed += __ldg(epoch) * 0xD1B54A32D192ED03ull;   // CUDA-graph replays: fresh masks per replay
   unsigned long long z = seed + 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
@@ -260,7 +262,7 @@ __device__ __forceinline__ void epi_tile(const EpiParams& p, uint32_t taddr, int
   L.out_vec = p.out_fp32 ? ((p.ld_out % 4 == 0) && epi_al16(p.out) && (p.split_stride % 4 == 0))
                          : ((p.ld_out % 8 == 0) && epi_al16(p.out));
   L.pre_vec = p.out_pre && (p.ld_out % 8 == 0) && epi_al16(p.out_pre);
-  L.dkey = drop_key(p.drop_seed, p.drop_p);
+  L.dkey = drop_key(p.drop_seed, p.drop_p, p.drop_epoch);
   if (n_begin >= p.N) return;
   EpiOps cur, nxt;
   epi_prefetch(p, L, cur, n_begin + cg * 8, n_begin + 32 <= p.N);
@@ -330,7 +332,7 @@ __device__ __forceinline__ void epi_tile_fast(const EpiParams& p, uint32_t taddr
   const bool has_drop = p.drop_p > 0.0f, f32 = p.out_fp32 != 0;
   const float relu_lo = p.act == SFC_ACT_RELU ? 0.0f : -INFINITY;
   const float alpha = p.alpha;
-  const DropKey dkey = drop_key(p.drop_seed, p.drop_p);
+  const DropKey dkey = drop_key(p.drop_seed, p.drop_p, p.drop_epoch);
   // per-lane row state: byte pointers at column n_begin + cg * 8 of rows it * 8 + rsub
   const char* resp[4];
   const char* auxp[4];
@@ -436,7 +438,7 @@ __device__ __forceinline__ void epi_tile_direct(const EpiParams& p, uint32_t tad
   const bool has_drop = p.drop_p > 0.0f, f32 = p.out_fp32 != 0;
   const float relu_lo = p.act == SFC_ACT_RELU ? 0.0f : -INFINITY;
   const float alpha = p.alpha;
-  const DropKey dkey = drop_key(p.drop_seed, p.drop_p);
+  const DropKey dkey = drop_key(p.drop_seed, p.drop_p, p.drop_epoch);
   __syncwarp();
   for (int c0 = 0; c0 < ncols; c0 += 128) {       // lane l converts columns 4l .. 4l+3 of each 128-column group
     const int c = c0 + lane * 4;

@@ -18,6 +18,11 @@ extern "C" const char* sfc_last_error(void) { return g_err; }
 
 extern "C" int sfc_abi_version(void) { return SFCVIT_ABI_VERSION; }
 
+// Device-side dropout epoch (see sfcvit.h): a process-wide pointer that every launcher forwards to its kernel.
+static const unsigned long long* g_drop_epoch = nullptr;
+extern "C" void sfc_set_dropout_epoch_ptr(const void* dev_ptr) { g_drop_epoch = (const unsigned long long*)dev_ptr; }
+const unsigned long long* sfc_dropout_epoch_ptr() { return g_drop_epoch; }
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -97,9 +97,10 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                      const __nv_bfloat16* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
                      __nv_bfloat16* __restrict__ dx_drop, float drop_p, unsigned long long drop_seed,
+                     const unsigned long long* __restrict__ drop_epoch,
                      float* __restrict__ part, long long rows, int D) {
   extern __shared__ float sred[];            // [kLnWarps][3][D]
-  const DropKey dkey = drop_key(drop_seed, drop_p);
+  const DropKey dkey = drop_key(drop_seed, drop_p, drop_epoch);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nvec = D >> 3;
   float dg[NV][8], db[NV][8], cs[CSUM ? NV : 1][8];
@@ -276,8 +277,9 @@ __global__ void __launch_bounds__(256) partial_finalize_kernel(const float* __re
 // identity; the dropout keep decision is re-derived from (seed, element index) exactly as in the GEMM epilogue.
 __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ aux,
                                                       __nv_bfloat16* __restrict__ out, long long nvec, int mode, float alpha,
-                                                      float drop_p, unsigned long long seed) {
-  const DropKey dkey = drop_key(seed, drop_p);
+                                                      float drop_p, unsigned long long seed,
+                                                      const unsigned long long* __restrict__ drop_epoch) {
+  const DropKey dkey = drop_key(seed, drop_p, drop_epoch);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     float d[8], a[8], o[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(dy) + i), d);
@@ -347,7 +349,7 @@ extern "C" int sfc_layernorm_bwd(const void* dy, const void* x, const float* mea
     if (smem > 48 * 1024) SFC_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     k<<<blocks, kLnWarps * 32, smem, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd,       \
                                                (const __nv_bfloat16*)gamma, (__nv_bfloat16*)dx, (__nv_bfloat16*)dx_drop, \
-                                               drop_p, drop_seed, (float*)scratch, rows, D);                        \
+                                               drop_p, drop_seed, sfc_dropout_epoch_ptr(), (float*)scratch, rows, D);                        \
   } while (0)
 #define LN_BWD(NV)                                                                  \
   do {                                                                              \
@@ -403,7 +405,7 @@ extern "C" int sfc_act_bwd(const void* dy, const void* aux, void* out, long long
   const long long cap = 16ll * sfc_num_sms();
   if (blocks > cap) blocks = cap;
   act_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)aux, (__nv_bfloat16*)out, n / 8,
-                                                       aux_mode, alpha, drop_p, drop_seed);
+                                                       aux_mode, alpha, drop_p, drop_seed, sfc_dropout_epoch_ptr());
   SFC_LAUNCH_OK();
   return 0;
 }

@@ -29,6 +29,7 @@ SIGNATURES = {
     "sfc_last_error": (ctypes.c_char_p, []),
     "sfc_abi_version": (_i, []),
     "sfc_device_sm_count": (_i, []),
+    "sfc_set_dropout_epoch_ptr": (None, [_vp]),
     "sfc_curve_perm_scratch_bytes": (_sz, [_i, _i, _i]),
     "sfc_curve_perm": (_i, [_i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "sfc_gemm_workspace_bytes": (_sz, [_i, _i, _i, _i]),

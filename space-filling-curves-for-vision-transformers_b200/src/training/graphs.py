@@ -1,0 +1,77 @@
+"""CUDA-graph capture of one forward + loss + backward of a libsfcvit-backed model (an addition to the reference API).
+
+The reference wraps its model in ``torch.compile(mode="reduce-overhead")`` (main.py:284), i.e. CUDA-graphed Inductor
+code. The B200 path has no tracing compiler: its kernels are launched through the C ABI, so the equivalent is to capture
+the ~370 launches of a step once and replay them (no Python / ctypes / tensor-map encoding on the critical path).
+
+    step = GraphedStep(model, criterion, example_images, example_targets)
+    loss = step(images, targets)        # copies into the static buffers, replays, returns the static loss tensor
+    optimizer.step()                    # p.grad tensors are static; do NOT zero them to None between replays
+
+Drop every reference to losses / outputs of earlier EAGER passes before constructing it: a live autograd graph keeps
+AccumulateGrad nodes bound to the default stream, which stream capture cannot synchronise with.
+
+Dropout: seeds drawn on the host are frozen into the graph, so the graph increments a device-side epoch counter that
+every mask-drawing kernel mixes into its seed (``sfc_set_dropout_epoch_ptr``): each replay draws fresh masks, and the
+forward / backward of one replay agree.
+"""
+import torch
+
+from sfcvit import _lib, functional as SF
+
+_epoch = {}
+
+
+def dropout_epoch(device):
+    """The process-wide device counter (created on first use and registered with the library)."""
+    device = torch.device(device)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    t = _epoch.get(key)
+    if t is None:
+        if _epoch:
+            raise RuntimeError("the dropout epoch counter is process-wide: one CUDA device per process")
+        t = torch.zeros(1, dtype=torch.int64, device=device)
+        _lib.load().sfc_set_dropout_epoch_ptr(t.data_ptr())
+        _epoch[key] = t
+    return t
+
+
+class GraphedStep:
+    def __init__(self, model, criterion, example_images, example_targets, warmup=3):
+        if not example_images.is_cuda:
+            raise RuntimeError("GraphedStep needs CUDA tensors (no CPU fallback)")
+        self.model, self.criterion = model, criterion
+        self.images = example_images.clone()
+        self.targets = example_targets.clone()
+        self.epoch = dropout_epoch(example_images.device)
+        params = [p for p in model.parameters() if p.requires_grad]
+        # warm-up on a side stream (lazy initialisations, cudaFuncSetAttribute, workspace growth) as torch recommends
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                for p in params:
+                    p.grad = None
+                self.criterion(self.model(self.images), self.targets).backward()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        for p in params:
+            p.grad = None                         # backward inside the capture allocates the static .grad tensors
+        SF._shadow.clear()                        # cached weight conversions must be RE-RUN inside the graph
+        SF._wk_cache.clear()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.epoch.add_(1)
+            self.logits = self.model(self.images)
+            self.loss = self.criterion(self.logits, self.targets)
+            self.loss.backward()
+        SF._shadow.clear()                        # entries created during capture alias graph-private memory
+        SF._wk_cache.clear()
+
+    def __call__(self, images, targets=None):
+        if images is not self.images:
+            self.images.copy_(images, non_blocking=True)
+        if targets is not None and targets is not self.targets:
+            self.targets.copy_(targets, non_blocking=True)
+        self.graph.replay()
+        return self.loss
