@@ -45,6 +45,10 @@ void sfc_set_error(const char* fmt, ...);
 int sfc_make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows,
                      uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows, bool swizzle128);
 
+// same with swizzle_bytes in {0, 32, 64, 128} (box_cols * elem_bytes must not exceed it)
+int sfc_make_tmap_2d_sw(CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows,
+                        uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows, int swizzle_bytes);
+
 int sfc_num_sms();
 const unsigned long long* sfc_dropout_epoch_ptr();   // device pointer or null (sfc_set_dropout_epoch_ptr)
 

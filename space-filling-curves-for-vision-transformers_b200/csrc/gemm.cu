@@ -17,6 +17,7 @@
 #include "gemm_epilogue.cuh"
 #include "sfcvit.h"
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -44,9 +45,11 @@ struct SmemLayout {
   static_assert(kTotal <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
 };
 
-template <int BN, int kStages, bool A_MN, bool B_MN, bool FAST_EPI, int CL>
+// EPI: 0 = general epilogue, 1 = lean transposed (coalesced st.global), 2 = lean + TMA store of bf16 boxes
+template <int BN, int kStages, bool A_MN, bool B_MN, int EPI, int CL>
 __global__ void __launch_bounds__(kNumThreads, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
   using L = SmemLayout<BN, kStages, A_MN, B_MN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -179,6 +182,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int quarter = warp & 3;
     const int half = (warp - 4) >> 2;
     uint8_t* stage = smem + L::kEpiOffset + (warp - 4) * kEpiStageBytes;
+    uint32_t box_counter = 0;
+    if (EPI == 2 && (threadIdx.x & 31) == 0) ptx::prefetch_tmap(&tmap_out);
     int iter = 0;
     for (int t = unit0; t < total_tiles; t += unit_stride, ++iter) {
       const int split = t % p.splits;
@@ -191,16 +196,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + half * (BN / 2) + ((uint32_t)(quarter * 32) << 16);
       if (p.debug != 1) {
-        if constexpr (FAST_EPI)
-          epi_tile_fast(p.epi, taddr, n_tile * BN + half * (BN / 2), BN / 2, (long long)m_tile * BM + quarter * 32, (long long)p.M,
-                        EpiRowIdentity{}, split, stage);
-        else
-          epi_tile(p.epi, taddr, n_tile * BN + half * (BN / 2), BN / 2, (long long)m_tile * BM + quarter * 32, (long long)p.M,
-                   EpiRowIdentity{}, split, stage);
+        const int n0 = n_tile * BN + half * (BN / 2);
+        const long long m0 = (long long)m_tile * BM + quarter * 32;
+        if constexpr (EPI == 2) epi_tile_tma(p.epi, &tmap_out, taddr, n0, BN / 2, m0, (long long)p.M, EpiRowIdentity{}, stage, box_counter);
+        else if constexpr (EPI == 1) epi_tile_fast(p.epi, taddr, n0, BN / 2, m0, (long long)p.M, EpiRowIdentity{}, split, stage);
+        else epi_tile(p.epi, taddr, n0, BN / 2, m0, (long long)p.M, EpiRowIdentity{}, split, stage);
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
     }
+    if constexpr (EPI == 2) ptx::tma_store_wait_all<0>();     // staged boxes must be read out before the CTA retires
   }
 
   ptx::tc_fence_before();
@@ -230,10 +235,10 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, long long spl
   }
 }
 
-template <int BN, int kStages, bool A_MN, bool B_MN, bool FAST_EPI, int CL>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+template <int BN, int kStages, bool A_MN, bool B_MN, int EPI, int CL>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p, cudaStream_t stream) {
   using L = SmemLayout<BN, kStages, A_MN, B_MN>;
-  auto kern = gemm_bf16_kernel<BN, kStages, A_MN, B_MN, FAST_EPI, CL>;
+  auto kern = gemm_bf16_kernel<BN, kStages, A_MN, B_MN, EPI, CL>;
   static bool configured = false;
   if (!configured) {
     SFC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -252,7 +257,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SFC_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  SFC_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, p));
   return 0;
 }
 
@@ -334,7 +339,15 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
   const bool fast = epi_fast_ok(pk.epi);
   static const bool cl_off = getenv("SFC_GEMM_NOCLUSTER") != nullptr;
   const bool cl2 = fast && !cl_off && p.num_m_tiles >= 2;      // 2-CTA clusters sharing the B tile by TMA multicast
-  CUtensorMap ta, tb;
+  static const bool tma_off = getenv("SFC_GEMM_NOTMASTORE") != nullptr;
+  // bf16 output staged in smem boxes and stored by TMA; GEMMs with a residual / aux operand keep the transposed
+  // epilogue, whose operand loads are coalesced (row-per-lane 64-byte reads of [M, N] operands thrash L1)
+  const bool tma_out = fast && !tma_off && !pk.epi.out_fp32 && !pk.epi.residual && pk.epi.aux_mode == SFC_AUX_NONE;
+  CUtensorMap ta, tb, tout;
+  memset(&tout, 0, sizeof(tout));
+  if (tma_out) {
+    if (int e = sfc_make_tmap_2d_sw(&tout, pk.epi.out, 2, (uint64_t)N, (uint64_t)M, (uint64_t)pk.epi.ld_out * 2, 32, 32, 64)) return e;
+  }
   // K-major operand: global [rows = M or N][cols = K]; MN-major operand: global [rows = K][cols = M or N].
   if (!a_mn_major) { if (int e = sfc_make_tmap_2d(&ta, A, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK, BM, true)) return e; }
   else             { if (int e = sfc_make_tmap_2d(&ta, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, BK, true)) return e; }
@@ -344,16 +357,18 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
   int rc = 0;
 #define SFC_DISPATCH2(BN_, ST_, F_, CL_)                                                            \
   do {                                                                                          \
-    if (!a_mn_major && !b_mn_major) rc = launch_gemm<BN_, ST_, false, false, F_, CL_>(ta, tb, pk, stream); \
-    else if (!a_mn_major && b_mn_major) rc = launch_gemm<BN_, ST_, false, true, F_, CL_>(ta, tb, pk, stream); \
-    else if (a_mn_major && b_mn_major) rc = launch_gemm<BN_, ST_, true, true, F_, CL_>(ta, tb, pk, stream);  \
-    else rc = launch_gemm<BN_, ST_, true, false, F_, CL_>(ta, tb, pk, stream);                        \
+    if (!a_mn_major && !b_mn_major) rc = launch_gemm<BN_, ST_, false, false, F_, CL_>(ta, tb, tout, pk, stream); \
+    else if (!a_mn_major && b_mn_major) rc = launch_gemm<BN_, ST_, false, true, F_, CL_>(ta, tb, tout, pk, stream); \
+    else if (a_mn_major && b_mn_major) rc = launch_gemm<BN_, ST_, true, true, F_, CL_>(ta, tb, tout, pk, stream);  \
+    else rc = launch_gemm<BN_, ST_, true, false, F_, CL_>(ta, tb, tout, pk, stream);                        \
   } while (0)
 #define SFC_DISPATCH(BN_, ST_)                                                              \
   do {                                                                                      \
-    if (cl2) SFC_DISPATCH2(BN_, ST_, true, 2);                                              \
-    else if (fast) SFC_DISPATCH2(BN_, ST_, true, 1);                                        \
-    else SFC_DISPATCH2(BN_, ST_, false, 1);                                                 \
+    if (cl2 && tma_out) SFC_DISPATCH2(BN_, ST_, 2, 2);                                      \
+    else if (cl2) SFC_DISPATCH2(BN_, ST_, 1, 2);                                            \
+    else if (tma_out) SFC_DISPATCH2(BN_, ST_, 2, 1);                                        \
+    else if (fast) SFC_DISPATCH2(BN_, ST_, 1, 1);                                           \
+    else SFC_DISPATCH2(BN_, ST_, 0, 1);                                                     \
   } while (0)
   if (BN == 256) SFC_DISPATCH(256, 4); else SFC_DISPATCH(128, 6);
 #undef SFC_DISPATCH2

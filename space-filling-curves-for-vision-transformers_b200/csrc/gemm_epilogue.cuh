@@ -516,3 +516,101 @@ __device__ __forceinline__ void epi_tile_direct(const EpiParams& p, uint32_t tad
     }
   }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// TMA-store variant (bf16 output, same preconditions as epi_tile_fast): each lane finishes the 32 columns of ITS
+// accumulator row (bias by broadcast loads, residual / aux read 64 bytes per row), packs them to bf16 and writes them
+// into a 32-row x 64-byte staging box (SWIZZLE_64B, conflict-free for row-per-lane 16-byte stores); one lane then
+// issues a cp.async.bulk.tensor store of the box. Per 32 x 32 chunk this is 4 shared-memory stores per lane instead
+// of 8 + 8 and no st.global at all: half the shared-memory traffic of the transposed variant (the single-CTA
+// 128 x 256 MMA tile already takes ~75 % of the shared-memory bandwidth) and the store coalescing is done by the TMA
+// unit. Two boxes per warp alternate, so a box is rewritten only after the store issued two chunks earlier has read it.
+// Rows >= M and columns >= N are clipped by the tensor map.
+// `stage` = this warp's 4 KB (two 2 KB boxes, 1024-byte aligned). The caller drains with tma_store_wait_all<0>().
+// ------------------------------------------------------------------------------------------------------------------
+template <class RowMap>
+__device__ __forceinline__ void epi_tile_tma(const EpiParams& p, const CUtensorMap* tmap_out, uint32_t taddr, int n_begin, int ncols,
+                                             long long m_base, long long M, const RowMap& rm, uint8_t* stage, uint32_t& box_counter) {
+  const int lane = (int)(threadIdx.x & 31);
+  const bool has_bias = p.bias != nullptr, has_res = p.residual != nullptr, has_aux = p.aux_mode != SFC_AUX_NONE;
+  const bool has_drop = p.drop_p > 0.0f;
+  const float relu_lo = p.act == SFC_ACT_RELU ? 0.0f : -INFINITY;
+  const float alpha = p.alpha;
+  const DropKey dkey = drop_key(p.drop_seed, p.drop_p, p.drop_epoch);
+  const long long m = m_base + lane;
+  const bool ok = m < M;
+  long long m_out, m_res;
+  rm.map(ok ? m : 0, m_out, m_res);
+  const char* resp = reinterpret_cast<const char*>(p.residual) + (m_res * p.ld_res + n_begin) * 2;
+  const char* auxp = reinterpret_cast<const char*>(p.aux) + (m_out * p.ld_aux + n_begin) * 2;
+  const char* biasp = reinterpret_cast<const char*>(p.bias) + (long long)n_begin * 2;
+  const unsigned long long didx = (unsigned long long)m_out * (unsigned long long)p.N + (unsigned long long)n_begin;
+  const int nchunks = ncols / 32;
+  const int sw = (lane >> 1) & 3;                  // SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
+  uint4 cb[4] = {}, cr[4], ca[4], nr[4], na[4];
+  auto prefetch = [&](int coff, uint4 (&r)[4], uint4 (&a)[4]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (has_res && ok) r[q] = __ldg(reinterpret_cast<const uint4*>(resp + coff * 2) + q);
+      if (has_aux && ok) a[q] = __ldg(reinterpret_cast<const uint4*>(auxp + coff * 2) + q);
+    }
+  };
+  prefetch(0, cr, ca);
+#pragma unroll 1
+  for (int c = 0; c < nchunks; ++c) {
+    const int coff = c * 32;
+    if (n_begin + coff >= p.N) break;              // warp-uniform
+    uint32_t raw[32];
+    ptx::tmem_ld_x32(taddr + coff, raw);
+    if (has_bias) {                                // same address in all lanes (broadcast, L1-resident): hidden by the TMEM load
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cb[q] = __ldg(reinterpret_cast<const uint4*>(biasp + coff * 2) + q);
+    }
+    const bool more = (c + 1 < nchunks) && (n_begin + coff + 32 < p.N);
+    if (more) prefetch(coff + 32, nr, na);
+    ptx::tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float bf[8];
+      epi_unpack8(cb[q], bf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[q * 8 + j] = fmaxf(fmaf(__uint_as_float(raw[q * 8 + j]), alpha, bf[j]), relu_lo);
+    }
+    if (has_drop) drop_apply<32, 8>(v, dkey, didx + (unsigned long long)coff);
+    if (has_aux) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float a[8];
+        epi_unpack8(ca[q], a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[q * 8 + j] = a[j] > 0.0f ? v[q * 8 + j] : 0.0f;
+      }
+    }
+    if (has_res) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float f[8];
+        epi_unpack8(cr[q], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[q * 8 + j] += f[j];
+      }
+    }
+    uint8_t* box = stage + (box_counter & 1u) * 2048;
+    ptx::tma_store_wait_read<1>();                 // the store that read this box two chunks ago has finished reading
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(box + lane * 64 + ((q ^ sw) << 4)) = epi_pack8(&v[q * 8]);
+    ptx::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      ptx::tma_store_2d(tmap_out, box, n_begin + coff, (int)m_base);
+      ptx::tma_store_commit();
+    }
+    ++box_counter;
+    if (more) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { cr[q] = nr[q]; ca[q] = na[q]; }
+    }
+  }
+}

@@ -41,6 +41,11 @@ static PFN_encodeTiled get_encode() {
 
 int sfc_make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows,
                      uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows, bool swizzle128) {
+  return sfc_make_tmap_2d_sw(out, base, elem_bytes, cols, rows, row_stride_bytes, box_cols, box_rows, swizzle128 ? 128 : 0);
+}
+
+int sfc_make_tmap_2d_sw(CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows,
+                        uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows, int swizzle_bytes) {
   PFN_encodeTiled enc = get_encode();
   SFC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
   SFC_REQUIRE(((uintptr_t)base & 15) == 0, "TMA base pointer must be 16-byte aligned (%p)", base);
@@ -54,7 +59,7 @@ int sfc_make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE)), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SFC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) cols=%llu rows=%llu stride=%llu box=%ux%u", (int)r,
               (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)row_stride_bytes, box_cols, box_rows);
