@@ -30,27 +30,33 @@ constexpr int kNumThreads = 128 + kEpiThreads;
 struct GemmParams {
   int M, N, K;
   int num_m_tiles, num_n_tiles, splits, kblocks_per_split, num_k_blocks;
-  int debug;   // SFC_GEMM_DEBUG (timing experiments only): 1 = skip epilogue body, 2 = skip TMA + MMA
   EpiParams epi;
 };
 
-template <int BN, int kStages, bool A_MN, bool B_MN>
+template <int BN, int kStages, int CL>
 struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (BN / CL) * BK * 2;                 // CL == 2: this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiOffset = kStages * kStageBytes;          // per-epilogue-warp transpose stage
+  static constexpr int kEpiOffset = kStages * kStageBytes;          // per-epilogue-warp stage (transpose / TMA boxes)
   static constexpr int kBarOffset = kEpiOffset + kEpiWarps * kEpiStageBytes;
-  static constexpr int kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16 + 1024 /*alignment slack*/;
+  static constexpr int kNumBars = 2 * kStages + 4;                  // full, empty, tmem_full[2], tmem_empty[2]
+  static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16 + 1024 /*alignment slack*/;
   static_assert(kTotal <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
 };
 
-// EPI: 0 = general epilogue, 1 = lean transposed (coalesced st.global), 2 = lean + TMA store of bf16 boxes
+// EPI: 0 = general epilogue, 1 = lean transposed (coalesced st.global), 2 = lean + TMA store of bf16 boxes.
+// CL : 1 = one CTA per 128 x BN tile (tcgen05.mma.cta_group::1);
+//      2 = CTA pairs (2-CTA clusters) on a 256 x BN tile with tcgen05.mma.cta_group::2: CTA r of the pair owns m-tile
+//          2u + r (its A rows, its accumulator rows in its own TMEM) and loads only columns [r*BN/2, (r+1)*BN/2) of the
+//          B tile — the tensor cores of the pair exchange the B halves, so shared-memory operand reads and L2 -> SM
+//          traffic per FLOP drop by a third against CL = 1. The leader (rank 0) issues all MMAs; both CTAs' TMA loads
+//          count their bytes on the leader's full barrier; tcgen05.commit multicasts to both CTAs' barriers.
 template <int BN, int kStages, bool A_MN, bool B_MN, int EPI, int CL>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
-  using L = SmemLayout<BN, kStages, A_MN, B_MN>;
+  using L = SmemLayout<BN, kStages, CL>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
@@ -60,13 +66,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
-  // CL == 2: the two CTAs of a cluster work on m-tiles 2i and 2i+1 of the same n-tile; each loads half of the B tile and
-  // multicasts it to both, halving the L2 -> SM traffic of the (larger) B operand.
   const int crank = CL > 1 ? (int)ptx::cluster_ctarank() : 0;
+  const bool leader = crank == 0;
   const int num_m_units = (p.num_m_tiles + CL - 1) / CL;
   const int total_tiles = num_m_units * p.num_n_tiles * p.splits;      // units of CL m-tiles
   const int unit0 = (int)blockIdx.x / CL, unit_stride = (int)gridDim.x / CL;
   constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
+  constexpr int BNH = BN / CL;                                         // B columns held by this CTA
 
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmap_a);
@@ -75,24 +81,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 1 && ptx::elect_one()) {
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], CL);            // one tcgen05.commit arrival per CTA of the cluster
+      ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
-      ptx::mbar_init(&tmem_empty[s], kEpiThreads);
+      ptx::mbar_init(&tmem_empty[s], CL * kEpiWarps);      // one arrival per epilogue warp (of both CTAs when CL == 2)
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 2) ptx::tmem_alloc<2 * BN>(tmem_ptr);
+  if (warp == 2) {
+    if constexpr (CL == 2) ptx::tmem_alloc_2cta<2 * BN>(tmem_ptr);
+    else ptx::tmem_alloc<2 * BN>(tmem_ptr);
+  }
   ptx::tc_fence_before();
   __syncthreads();
-  if constexpr (CL > 1) ptx::cluster_sync();       // peer barriers are initialised before any multicast / remote arrive
+  if constexpr (CL > 1) ptx::cluster_sync();       // peer barriers are initialised before any remote arrive / multicast commit
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (p.debug != 2 && ptx::elect_one()) {
+    // ===================== TMA producer (every CTA: its A rows and its share of the B tile) =====================
+    if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = unit0; t < total_tiles; t += unit_stride) {
@@ -102,36 +111,44 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int m_tile = (tile / p.num_n_tiles) * CL + crank;      // may be one past the end for the odd CTA: TMA zero-fills
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(kb0 + p.kblocks_per_split, p.num_k_blocks);
+        const int n0 = n_tile * BN + crank * BNH;
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
-          ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
-          if constexpr (!A_MN) {
-            ptx::tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BK, m_tile * BM);
-          } else {
-#pragma unroll
-            for (int a = 0; a < BM / 64; ++a)
-              ptx::tma_load_2d(&tmap_a, &full_bar[stage], sa + a * (BK * 128), m_tile * BM + a * 64, kb * BK);
-          }
           if constexpr (CL == 1) {
-            if constexpr (!B_MN) {
-              ptx::tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * BK, n_tile * BN);
+            ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+            if constexpr (!A_MN) {
+              ptx::tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BK, m_tile * BM);
             } else {
 #pragma unroll
-              for (int a = 0; a < BN / 64; ++a)
-                ptx::tma_load_2d(&tmap_b, &full_bar[stage], sb + a * (BK * 128), n_tile * BN + a * 64, kb * BK);
+              for (int a = 0; a < BM / 64; ++a)
+                ptx::tma_load_2d(&tmap_a, &full_bar[stage], sa + a * (BK * 128), m_tile * BM + a * 64, kb * BK);
+            }
+            if constexpr (!B_MN) {
+              ptx::tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * BK, n0);
+            } else {
+#pragma unroll
+              for (int a = 0; a < BNH / 64; ++a)
+                ptx::tma_load_2d(&tmap_b, &full_bar[stage], sb + a * (BK * 128), n0 + a * 64, kb * BK);
             }
           } else {
-            // this CTA's half of the B tile, written to the same offset in both CTAs
-            if constexpr (!B_MN) {
-              ptx::tma_load_2d_mc(&tmap_b, &full_bar[stage], sb + crank * (BN / CL) * 128, kb * BK, n_tile * BN + crank * (BN / CL), kMask);
+            // both CTAs of the pair count their bytes on the LEADER's full barrier (it issues the MMAs for both)
+            if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+            const uint32_t fb = ptx::mapa_u32(&full_bar[stage], 0);
+            if constexpr (!A_MN) {
+              ptx::tma_load_2d_2cta(&tmap_a, fb, sa, kb * BK, m_tile * BM);
             } else {
 #pragma unroll
-              for (int a = 0; a < BN / 64 / CL; ++a) {
-                const int aa = crank * (BN / 64 / CL) + a;
-                ptx::tma_load_2d_mc(&tmap_b, &full_bar[stage], sb + aa * (BK * 128), n_tile * BN + aa * 64, kb * BK, kMask);
-              }
+              for (int a = 0; a < BM / 64; ++a)
+                ptx::tma_load_2d_2cta(&tmap_a, fb, sa + a * (BK * 128), m_tile * BM + a * 64, kb * BK);
+            }
+            if constexpr (!B_MN) {
+              ptx::tma_load_2d_2cta(&tmap_b, fb, sb, kb * BK, n0);
+            } else {
+#pragma unroll
+              for (int a = 0; a < BNH / 64; ++a)
+                ptx::tma_load_2d_2cta(&tmap_b, fb, sb + a * (BK * 128), n0 + a * 64, kb * BK);
             }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -140,9 +157,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (ptx::elect_one()) {
-      const uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    if (CL == 2 && !leader) {
+      // the peer CTA of a pair issues no MMAs (the leader's cta_group::2 instructions drive both tensor cores)
+    } else if (ptx::elect_one()) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc = umma_idesc_bf16(BM * CL, BN, A_MN, B_MN);
       constexpr uint32_t kLboA = A_MN ? BK * 128 : 0, kLboB = B_MN ? BK * 128 : 0;
       constexpr uint32_t kAdvA = A_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;   // per UMMA_K = 16, in 16-byte units
       constexpr uint32_t kAdvB = B_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;
@@ -155,23 +174,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int kb1 = min(kb0 + p.kblocks_per_split, p.num_k_blocks);
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
-        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        if constexpr (CL == 2) ptx::mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
+        else ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        if (p.debug == 2) { ptx::umma_commit(&tmem_full[acc]); continue; }
         for (int kb = kb0; kb < kb1; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);
+          if constexpr (CL == 2) ptx::mbar_wait_cluster(&full_bar[stage], phase);
+          else ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
           const uint32_t sb = sa + L::kABytes;
           const uint64_t da = umma_smem_desc_sw128(sa, kLboA, 1024);
           const uint64_t db = umma_smem_desc_sw128(sb, kLboB, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            ptx::umma_f16(tmem_d, da + (uint64_t)(k * kAdvA), db + (uint64_t)(k * kAdvB), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          if constexpr (CL == 1) ptx::umma_commit(&empty_bar[stage]);            // frees the smem slot when these MMAs retire
-          else ptx::umma_commit_mc(&empty_bar[stage], kMask);                    // ... in both CTAs (the peer refills half of it)
-          if (kb == kb1 - 1) ptx::umma_commit(&tmem_full[acc]);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint32_t accf = (kb > kb0 || k > 0) ? 1u : 0u;
+            if constexpr (CL == 2) ptx::umma_f16_2cta(tmem_d, da + (uint64_t)(k * kAdvA), db + (uint64_t)(k * kAdvB), idesc, accf);
+            else ptx::umma_f16(tmem_d, da + (uint64_t)(k * kAdvA), db + (uint64_t)(k * kAdvB), idesc, accf);
+          }
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if constexpr (CL == 2) ptx::umma_commit_2cta(&empty_bar[stage], kMask);
+          else ptx::umma_commit(&empty_bar[stage]);
+          if (kb == kb1 - 1) {
+            if constexpr (CL == 2) ptx::umma_commit_2cta(&tmem_full[acc], kMask);
+            else ptx::umma_commit(&tmem_full[acc]);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -195,25 +222,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + half * (BN / 2) + ((uint32_t)(quarter * 32) << 16);
-      if (p.debug != 1) {
-        const int n0 = n_tile * BN + half * (BN / 2);
-        const long long m0 = (long long)m_tile * BM + quarter * 32;
-        if constexpr (EPI == 2) epi_tile_tma(p.epi, &tmap_out, taddr, n0, BN / 2, m0, (long long)p.M, EpiRowIdentity{}, stage, box_counter);
-        else if constexpr (EPI == 1) epi_tile_fast(p.epi, taddr, n0, BN / 2, m0, (long long)p.M, EpiRowIdentity{}, split, stage);
-        else epi_tile(p.epi, taddr, n0, BN / 2, m0, (long long)p.M, EpiRowIdentity{}, split, stage);
-      }
+      const int n0 = n_tile * BN + half * (BN / 2);
+      const long long m0 = (long long)m_tile * BM + quarter * 32;
+      if constexpr (EPI == 2) epi_tile_tma(p.epi, &tmap_out, taddr, n0, BN / 2, m0, (long long)p.M, EpiRowIdentity{}, stage, box_counter);
+      else if constexpr (EPI == 1) epi_tile_fast(p.epi, taddr, n0, BN / 2, m0, (long long)p.M, EpiRowIdentity{}, split, stage);
+      else epi_tile(p.epi, taddr, n0, BN / 2, m0, (long long)p.M, EpiRowIdentity{}, split, stage);
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&tmem_empty[acc]);
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) {               // the accumulator buffer is drained: tell the (leader's) MMA issuer
+        if constexpr (CL == 2) ptx::mbar_arrive_remote(&tmem_empty[acc], 0);
+        else ptx::mbar_arrive(&tmem_empty[acc]);
+      }
     }
     if constexpr (EPI == 2) ptx::tma_store_wait_all<0>();     // staged boxes must be read out before the CTA retires
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if constexpr (CL > 1) ptx::cluster_sync();       // no CTA exits while its peer may still multicast into it
+  if constexpr (CL > 1) ptx::cluster_sync();       // no CTA exits (or frees TMEM) while its peer may still touch it
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<2 * BN>(tmem_base);
+    if constexpr (CL == 2) ptx::tmem_dealloc_2cta<2 * BN>(tmem_base);
+    else ptx::tmem_dealloc<2 * BN>(tmem_base);
   }
 }
 
@@ -237,7 +267,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, long long spl
 
 template <int BN, int kStages, bool A_MN, bool B_MN, int EPI, int CL>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p, cudaStream_t stream) {
-  using L = SmemLayout<BN, kStages, A_MN, B_MN>;
+  using L = SmemLayout<BN, kStages, CL>;
   auto kern = gemm_bf16_kernel<BN, kStages, A_MN, B_MN, EPI, CL>;
   static bool configured = false;
   if (!configured) {
@@ -301,8 +331,6 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
   const int BN = (N > 128) ? 256 : 128;
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
-  static const int debug_mode = getenv("SFC_GEMM_DEBUG") ? atoi(getenv("SFC_GEMM_DEBUG")) : 0;
-  p.debug = debug_mode;
   p.num_m_tiles = sfc_ceil_div(M, BM);
   p.num_n_tiles = sfc_ceil_div(N, BN);
   p.num_k_blocks = sfc_ceil_div(K, BK);
@@ -338,7 +366,7 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
 
   const bool fast = epi_fast_ok(pk.epi);
   static const bool cl_off = getenv("SFC_GEMM_NOCLUSTER") != nullptr;
-  const bool cl2 = fast && !cl_off && p.num_m_tiles >= 2;      // 2-CTA clusters sharing the B tile by TMA multicast
+  const bool cl2 = fast && !cl_off && p.num_m_tiles >= 2;      // CTA pairs, tcgen05.mma.cta_group::2
   static const bool tma_off = getenv("SFC_GEMM_NOTMASTORE") != nullptr;
   // bf16 output staged in smem boxes and stored by TMA; GEMMs with a residual / aux operand keep the transposed
   // epilogue, whose operand loads are coalesced (row-per-lane 64-byte reads of [M, N] operands thrash L1)
@@ -355,22 +383,22 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
   else             { if (int e = sfc_make_tmap_2d(&tb, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, BK, true)) return e; }
 
   int rc = 0;
-#define SFC_DISPATCH2(BN_, ST_, F_, CL_)                                                            \
+#define SFC_DISPATCH2(BN_, F_, CL_)                                                            \
   do {                                                                                          \
-    if (!a_mn_major && !b_mn_major) rc = launch_gemm<BN_, ST_, false, false, F_, CL_>(ta, tb, tout, pk, stream); \
-    else if (!a_mn_major && b_mn_major) rc = launch_gemm<BN_, ST_, false, true, F_, CL_>(ta, tb, tout, pk, stream); \
-    else if (a_mn_major && b_mn_major) rc = launch_gemm<BN_, ST_, true, true, F_, CL_>(ta, tb, tout, pk, stream);  \
-    else rc = launch_gemm<BN_, ST_, true, false, F_, CL_>(ta, tb, tout, pk, stream);                        \
+    if (!a_mn_major && !b_mn_major) rc = launch_gemm<BN_, (CL_ == 2 ? (BN_ == 256 ? 6 : 8) : (BN_ == 256 ? 4 : 6)), false, false, F_, CL_>(ta, tb, tout, pk, stream); \
+    else if (!a_mn_major && b_mn_major) rc = launch_gemm<BN_, (CL_ == 2 ? (BN_ == 256 ? 6 : 8) : (BN_ == 256 ? 4 : 6)), false, true, F_, CL_>(ta, tb, tout, pk, stream); \
+    else if (a_mn_major && b_mn_major) rc = launch_gemm<BN_, (CL_ == 2 ? (BN_ == 256 ? 6 : 8) : (BN_ == 256 ? 4 : 6)), true, true, F_, CL_>(ta, tb, tout, pk, stream);  \
+    else rc = launch_gemm<BN_, (CL_ == 2 ? (BN_ == 256 ? 6 : 8) : (BN_ == 256 ? 4 : 6)), true, false, F_, CL_>(ta, tb, tout, pk, stream);                        \
   } while (0)
-#define SFC_DISPATCH(BN_, ST_)                                                              \
+#define SFC_DISPATCH(BN_)                                                                   \
   do {                                                                                      \
-    if (cl2 && tma_out) SFC_DISPATCH2(BN_, ST_, 2, 2);                                      \
-    else if (cl2) SFC_DISPATCH2(BN_, ST_, 1, 2);                                            \
-    else if (tma_out) SFC_DISPATCH2(BN_, ST_, 2, 1);                                        \
-    else if (fast) SFC_DISPATCH2(BN_, ST_, 1, 1);                                           \
-    else SFC_DISPATCH2(BN_, ST_, 0, 1);                                                     \
+    if (cl2 && tma_out) SFC_DISPATCH2(BN_, 2, 2);                                      \
+    else if (cl2) SFC_DISPATCH2(BN_, 1, 2);                                            \
+    else if (tma_out) SFC_DISPATCH2(BN_, 2, 1);                                        \
+    else if (fast) SFC_DISPATCH2(BN_, 1, 1);                                           \
+    else SFC_DISPATCH2(BN_, 0, 1);                                                     \
   } while (0)
-  if (BN == 256) SFC_DISPATCH(256, 4); else SFC_DISPATCH(128, 6);
+  if (BN == 256) SFC_DISPATCH(256); else SFC_DISPATCH(128);
 #undef SFC_DISPATCH2
 #undef SFC_DISPATCH
   if (rc) return rc;
