@@ -33,19 +33,21 @@ struct GemmParams {
   EpiParams epi;
 };
 
-template <int BN, int kStages, int CL>
+template <int BN, int kStages, int CL, int EPI>
 struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (BN / CL) * BK * 2;                 // CL == 2: this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiOffset = kStages * kStageBytes;          // per-epilogue-warp stage (transpose / TMA boxes)
-  static constexpr int kBarOffset = kEpiOffset + kEpiWarps * kEpiStageBytes;
-  static constexpr int kNumBars = 2 * kStages + 4;                  // full, empty, tmem_full[2], tmem_empty[2]
+  static constexpr int kEpiWarpBytes = EPI >= 3 ? 2 * kEpiStageBytes : kEpiStageBytes;   // + operand boxes
+  static constexpr int kBarOffset = kEpiOffset + kEpiWarps * kEpiWarpBytes;
+  static constexpr int kNumBars = 2 * kStages + 4 + 2 * kEpiWarps;  // full, empty, tmem_full[2], tmem_empty[2], operand[warp][2]
   static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16 + 1024 /*alignment slack*/;
   static_assert(kTotal <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
 };
 
-// EPI: 0 = general epilogue, 1 = lean transposed (coalesced st.global), 2 = lean + TMA store of bf16 boxes.
+// EPI: 0 = general epilogue, 1 = lean transposed (coalesced st.global), 2 = lean + TMA store of bf16 boxes,
+//      3 / 4 = 2 + residual / aux operand fetched by TMA into per-warp boxes.
 // CL : 1 = one CTA per 128 x BN tile (tcgen05.mma.cta_group::1);
 //      2 = CTA pairs (2-CTA clusters) on a 256 x BN tile with tcgen05.mma.cta_group::2: CTA r of the pair owns m-tile
 //          2u + r (its A rows, its accumulator rows in its own TMEM) and loads only columns [r*BN/2, (r+1)*BN/2) of the
@@ -55,15 +57,16 @@ struct SmemLayout {
 template <int BN, int kStages, bool A_MN, bool B_MN, int EPI, int CL>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
-  using L = SmemLayout<BN, kStages, CL>;
+                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_opnd, const GemmParams p) {
+  using L = SmemLayout<BN, kStages, CL, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* opnd_bar = tmem_empty + 2;         // [kEpiWarps][2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(opnd_bar + 2 * kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int crank = CL > 1 ? (int)ptx::cluster_ctarank() : 0;
@@ -87,6 +90,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ptx::mbar_init(&tmem_full[s], 1);
       ptx::mbar_init(&tmem_empty[s], CL * kEpiWarps);      // one arrival per epilogue warp (of both CTAs when CL == 2)
     }
+    for (int s = 0; s < 2 * kEpiWarps; ++s) ptx::mbar_init(&opnd_bar[s], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -208,9 +212,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================== epilogue (8 warps: lane quarter = warp % 4, column half = (warp - 4) / 4) =====================
     const int quarter = warp & 3;
     const int half = (warp - 4) >> 2;
-    uint8_t* stage = smem + L::kEpiOffset + (warp - 4) * kEpiStageBytes;
+    uint8_t* stage = smem + L::kEpiOffset + (warp - 4) * L::kEpiWarpBytes;
     uint32_t box_counter = 0;
-    if (EPI == 2 && (threadIdx.x & 31) == 0) ptx::prefetch_tmap(&tmap_out);
+    if (EPI >= 2 && (threadIdx.x & 31) == 0) {
+      ptx::prefetch_tmap(&tmap_out);
+      if (EPI >= 3) ptx::prefetch_tmap(&tmap_opnd);
+    }
     int iter = 0;
     for (int t = unit0; t < total_tiles; t += unit_stride, ++iter) {
       const int split = t % p.splits;
@@ -224,7 +231,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t taddr = tmem_base + acc * BN + half * (BN / 2) + ((uint32_t)(quarter * 32) << 16);
       const int n0 = n_tile * BN + half * (BN / 2);
       const long long m0 = (long long)m_tile * BM + quarter * 32;
-      if constexpr (EPI == 2) epi_tile_tma(p.epi, &tmap_out, taddr, n0, BN / 2, m0, (long long)p.M, EpiRowIdentity{}, stage, box_counter);
+      if constexpr (EPI >= 2) epi_tile_tma<EPI - 2>(p.epi, &tmap_out, &tmap_opnd, taddr, n0, BN / 2, m0, stage, box_counter, opnd_bar + 2 * (warp - 4));
       else if constexpr (EPI == 1) epi_tile_fast(p.epi, taddr, n0, BN / 2, m0, (long long)p.M, EpiRowIdentity{}, split, stage);
       else epi_tile(p.epi, taddr, n0, BN / 2, m0, (long long)p.M, EpiRowIdentity{}, split, stage);
       ptx::tc_fence_before();
@@ -234,7 +241,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         else ptx::mbar_arrive(&tmem_empty[acc]);
       }
     }
-    if constexpr (EPI == 2) ptx::tma_store_wait_all<0>();     // staged boxes must be read out before the CTA retires
+    if constexpr (EPI >= 2) ptx::tma_store_wait_all<0>();     // staged boxes must be read out before the CTA retires
   }
 
   ptx::tc_fence_before();
@@ -265,9 +272,18 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, long long spl
   }
 }
 
+// smem ring depth: stage = 48 KB (CL 1) / 32 KB (CL 2) at BN 256, half of the B part at BN 128; EPI >= 3 needs 32 KB more
+constexpr int gemm_stages(int bn, int cl, int epi) {
+  const int stage_kb = 16 + (bn / cl) / 8;
+  const int avail_kb = 224 - (epi >= 3 ? 64 : 32);
+  const int s = avail_kb / stage_kb;
+  return s > 8 ? 8 : s;
+}
+
 template <int BN, int kStages, bool A_MN, bool B_MN, int EPI, int CL>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p, cudaStream_t stream) {
-  using L = SmemLayout<BN, kStages, CL>;
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& topnd, const GemmParams& p,
+                cudaStream_t stream) {
+  using L = SmemLayout<BN, kStages, CL, EPI>;
   auto kern = gemm_bf16_kernel<BN, kStages, A_MN, B_MN, EPI, CL>;
   static bool configured = false;
   if (!configured) {
@@ -287,7 +303,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SFC_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, p));
+  SFC_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, topnd, p));
   return 0;
 }
 
@@ -368,15 +384,23 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
   static const bool cl_off = getenv("SFC_GEMM_NOCLUSTER") != nullptr;
   const bool cl2 = fast && !cl_off && p.num_m_tiles >= 2;      // CTA pairs, tcgen05.mma.cta_group::2
   static const bool tma_off = getenv("SFC_GEMM_NOTMASTORE") != nullptr;
-  // bf16 output staged in smem boxes and stored by TMA; GEMMs with a residual / aux operand keep the transposed
-  // epilogue, whose operand loads are coalesced (row-per-lane 64-byte reads of [M, N] operands thrash L1)
-  const bool tma_out = fast && !tma_off && !pk.epi.out_fp32 && !pk.epi.residual && pk.epi.aux_mode == SFC_AUX_NONE;
-  CUtensorMap ta, tb, tout;
+  // bf16 output: staged in swizzled smem boxes and stored by TMA (EPI 2); one [M, N] operand (residual or ReLU-mask
+  // source) is fetched by TMA the same way (EPI 3 / 4). fp32 output (split-K partials) and residual + aux together keep
+  // the transposed epilogue.
+  const bool has_res = pk.epi.residual != nullptr, has_aux = pk.epi.aux_mode != SFC_AUX_NONE;
+  int epi_mode = fast ? 1 : 0;
+  if (fast && !tma_off && !pk.epi.out_fp32 && !(has_res && has_aux)) epi_mode = has_res ? 3 : (has_aux ? 4 : 2);
+  CUtensorMap ta, tb, tout, topnd;
   memset(&tout, 0, sizeof(tout));
-  if (tma_out) {
+  memset(&topnd, 0, sizeof(topnd));
+  if (epi_mode >= 2) {
     if (int e = sfc_make_tmap_2d_sw(&tout, pk.epi.out, 2, (uint64_t)N, (uint64_t)M, (uint64_t)pk.epi.ld_out * 2, 32, 32, 64)) return e;
   }
-  // K-major operand: global [rows = M or N][cols = K]; MN-major operand: global [rows = K][cols = M or N].
+  if (epi_mode == 3) {
+    if (int e = sfc_make_tmap_2d_sw(&topnd, pk.epi.residual, 2, (uint64_t)N, (uint64_t)M, (uint64_t)pk.epi.ld_res * 2, 32, 32, 64)) return e;
+  } else if (epi_mode == 4) {
+    if (int e = sfc_make_tmap_2d_sw(&topnd, pk.epi.aux, 2, (uint64_t)N, (uint64_t)M, (uint64_t)pk.epi.ld_aux * 2, 32, 32, 64)) return e;
+  }
   if (!a_mn_major) { if (int e = sfc_make_tmap_2d(&ta, A, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK, BM, true)) return e; }
   else             { if (int e = sfc_make_tmap_2d(&ta, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, BK, true)) return e; }
   if (!b_mn_major) { if (int e = sfc_make_tmap_2d(&tb, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, (uint32_t)(cl2 ? BN / 2 : BN), true)) return e; }
@@ -385,16 +409,20 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
   int rc = 0;
 #define SFC_DISPATCH2(BN_, F_, CL_)                                                            \
   do {                                                                                          \
-    if (!a_mn_major && !b_mn_major) rc = launch_gemm<BN_, (CL_ == 2 ? (BN_ == 256 ? 6 : 8) : (BN_ == 256 ? 4 : 6)), false, false, F_, CL_>(ta, tb, tout, pk, stream); \
-    else if (!a_mn_major && b_mn_major) rc = launch_gemm<BN_, (CL_ == 2 ? (BN_ == 256 ? 6 : 8) : (BN_ == 256 ? 4 : 6)), false, true, F_, CL_>(ta, tb, tout, pk, stream); \
-    else if (a_mn_major && b_mn_major) rc = launch_gemm<BN_, (CL_ == 2 ? (BN_ == 256 ? 6 : 8) : (BN_ == 256 ? 4 : 6)), true, true, F_, CL_>(ta, tb, tout, pk, stream);  \
-    else rc = launch_gemm<BN_, (CL_ == 2 ? (BN_ == 256 ? 6 : 8) : (BN_ == 256 ? 4 : 6)), true, false, F_, CL_>(ta, tb, tout, pk, stream);                        \
+    if (!a_mn_major && !b_mn_major) rc = launch_gemm<BN_, gemm_stages(BN_, CL_, F_), false, false, F_, CL_>(ta, tb, tout, topnd, pk, stream); \
+    else if (!a_mn_major && b_mn_major) rc = launch_gemm<BN_, gemm_stages(BN_, CL_, F_), false, true, F_, CL_>(ta, tb, tout, topnd, pk, stream); \
+    else if (a_mn_major && b_mn_major) rc = launch_gemm<BN_, gemm_stages(BN_, CL_, F_), true, true, F_, CL_>(ta, tb, tout, topnd, pk, stream);  \
+    else rc = launch_gemm<BN_, gemm_stages(BN_, CL_, F_), true, false, F_, CL_>(ta, tb, tout, topnd, pk, stream);                        \
   } while (0)
 #define SFC_DISPATCH(BN_)                                                                   \
   do {                                                                                      \
-    if (cl2 && tma_out) SFC_DISPATCH2(BN_, 2, 2);                                      \
+    if (cl2 && epi_mode == 4) SFC_DISPATCH2(BN_, 4, 2);                                \
+    else if (cl2 && epi_mode == 3) SFC_DISPATCH2(BN_, 3, 2);                           \
+    else if (cl2 && epi_mode == 2) SFC_DISPATCH2(BN_, 2, 2);                           \
     else if (cl2) SFC_DISPATCH2(BN_, 1, 2);                                            \
-    else if (tma_out) SFC_DISPATCH2(BN_, 2, 1);                                        \
+    else if (epi_mode == 4) SFC_DISPATCH2(BN_, 4, 1);                                  \
+    else if (epi_mode == 3) SFC_DISPATCH2(BN_, 3, 1);                                  \
+    else if (epi_mode == 2) SFC_DISPATCH2(BN_, 2, 1);                                  \
     else if (fast) SFC_DISPATCH2(BN_, 1, 1);                                           \
     else SFC_DISPATCH2(BN_, 0, 1);                                                     \
   } while (0)

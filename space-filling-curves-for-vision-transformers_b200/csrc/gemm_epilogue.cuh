@@ -528,34 +528,32 @@ __device__ __forceinline__ void epi_tile_direct(const EpiParams& p, uint32_t tad
 // Rows >= M and columns >= N are clipped by the tensor map.
 // `stage` = this warp's 4 KB (two 2 KB boxes, 1024-byte aligned). The caller drains with tma_store_wait_all<0>().
 // ------------------------------------------------------------------------------------------------------------------
-template <class RowMap>
-__device__ __forceinline__ void epi_tile_tma(const EpiParams& p, const CUtensorMap* tmap_out, uint32_t taddr, int n_begin, int ncols,
-                                             long long m_base, long long M, const RowMap& rm, uint8_t* stage, uint32_t& box_counter) {
+// OPND: 0 = no [M, N] operand, 1 = residual, 2 = aux (ReLU mask source). The operand is fetched by TMA into per-warp
+// 32 x 32 boxes (same SWIZZLE_64B layout, two boxes alternate, one mbarrier each) one chunk ahead, and every lane reads
+// its own row from shared memory: no uncoalesced global loads, no transposed mapping.
+template <int OPND>
+__device__ __forceinline__ void epi_tile_tma(const EpiParams& p, const CUtensorMap* tmap_out, const CUtensorMap* tmap_opnd, uint32_t taddr,
+                                             int n_begin, int ncols, long long m_base, uint8_t* stage, uint32_t& box_counter,
+                                             uint64_t* obar) {
   const int lane = (int)(threadIdx.x & 31);
-  const bool has_bias = p.bias != nullptr, has_res = p.residual != nullptr, has_aux = p.aux_mode != SFC_AUX_NONE;
+  const bool has_bias = p.bias != nullptr;
   const bool has_drop = p.drop_p > 0.0f;
   const float relu_lo = p.act == SFC_ACT_RELU ? 0.0f : -INFINITY;
   const float alpha = p.alpha;
   const DropKey dkey = drop_key(p.drop_seed, p.drop_p, p.drop_epoch);
   const long long m = m_base + lane;
-  const bool ok = m < M;
-  long long m_out, m_res;
-  rm.map(ok ? m : 0, m_out, m_res);
-  const char* resp = reinterpret_cast<const char*>(p.residual) + (m_res * p.ld_res + n_begin) * 2;
-  const char* auxp = reinterpret_cast<const char*>(p.aux) + (m_out * p.ld_aux + n_begin) * 2;
   const char* biasp = reinterpret_cast<const char*>(p.bias) + (long long)n_begin * 2;
-  const unsigned long long didx = (unsigned long long)m_out * (unsigned long long)p.N + (unsigned long long)n_begin;
+  const unsigned long long didx = (unsigned long long)m * (unsigned long long)p.N + (unsigned long long)n_begin;
   const int nchunks = ncols / 32;
   const int sw = (lane >> 1) & 3;                  // SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
-  uint4 cb[4] = {}, cr[4], ca[4], nr[4], na[4];
-  auto prefetch = [&](int coff, uint4 (&r)[4], uint4 (&a)[4]) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (has_res && ok) r[q] = __ldg(reinterpret_cast<const uint4*>(resp + coff * 2) + q);
-      if (has_aux && ok) a[q] = __ldg(reinterpret_cast<const uint4*>(auxp + coff * 2) + q);
-    }
-  };
-  prefetch(0, cr, ca);
+  uint8_t* obox = stage + 4096;                    // operand boxes follow the two output boxes
+  if (n_begin >= p.N) return;
+  if (OPND != 0 && lane == 0) {                    // operand box of chunk 0
+    const uint32_t b = box_counter & 1u;
+    ptx::mbar_expect_tx(&obar[b], 2048);
+    ptx::tma_load_2d(tmap_opnd, &obar[b], obox + b * 2048, n_begin, (int)m_base);
+  }
+  uint4 cb[4] = {};
 #pragma unroll 1
   for (int c = 0; c < nchunks; ++c) {
     const int coff = c * 32;
@@ -567,7 +565,12 @@ __device__ __forceinline__ void epi_tile_tma(const EpiParams& p, const CUtensorM
       for (int q = 0; q < 4; ++q) cb[q] = __ldg(reinterpret_cast<const uint4*>(biasp + coff * 2) + q);
     }
     const bool more = (c + 1 < nchunks) && (n_begin + coff + 32 < p.N);
-    if (more) prefetch(coff + 32, nr, na);
+    const uint32_t cur = box_counter & 1u;
+    if (OPND != 0 && more && lane == 0) {          // next chunk's operand box; its last readers passed the __syncwarp below
+      const uint32_t nb = cur ^ 1u;
+      ptx::mbar_expect_tx(&obar[nb], 2048);
+      ptx::tma_load_2d(tmap_opnd, &obar[nb], obox + nb * 2048, n_begin + coff + 32, (int)m_base);
+    }
     ptx::tmem_ld_wait();
     float v[32];
 #pragma unroll
@@ -578,25 +581,23 @@ __device__ __forceinline__ void epi_tile_tma(const EpiParams& p, const CUtensorM
       for (int j = 0; j < 8; ++j) v[q * 8 + j] = fmaxf(fmaf(__uint_as_float(raw[q * 8 + j]), alpha, bf[j]), relu_lo);
     }
     if (has_drop) drop_apply<32, 8>(v, dkey, didx + (unsigned long long)coff);
-    if (has_aux) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float a[8];
-        epi_unpack8(ca[q], a);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[q * 8 + j] = a[j] > 0.0f ? v[q * 8 + j] : 0.0f;
-      }
-    }
-    if (has_res) {
+    if constexpr (OPND != 0) {
+      ptx::mbar_wait(&obar[cur], (box_counter >> 1) & 1u);
+      const uint8_t* orow = obox + cur * 2048 + lane * 64;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float f[8];
-        epi_unpack8(cr[q], f);
+        epi_unpack8(*reinterpret_cast<const uint4*>(orow + ((q ^ sw) << 4)), f);
+        if constexpr (OPND == 1) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[q * 8 + j] += f[j];
+          for (int j = 0; j < 8; ++j) v[q * 8 + j] += f[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[q * 8 + j] = f[j] > 0.0f ? v[q * 8 + j] : 0.0f;
+        }
       }
     }
-    uint8_t* box = stage + (box_counter & 1u) * 2048;
+    uint8_t* box = stage + cur * 2048;
     ptx::tma_store_wait_read<1>();                 // the store that read this box two chunks ago has finished reading
     __syncwarp();
 #pragma unroll
@@ -608,9 +609,5 @@ __device__ __forceinline__ void epi_tile_tma(const EpiParams& p, const CUtensorM
       ptx::tma_store_commit();
     }
     ++box_counter;
-    if (more) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { cr[q] = nr[q]; ca[q] = na[q]; }
-    }
   }
 }
