@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "gemm_epilogue.cuh"   // DropKey, drop_apply
 #include "sfcvit.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -41,6 +42,7 @@ struct AttnParams {
   __nv_bfloat16* dqkv;     // [B*N, 3D]
   float* dq_acc;           // [B*N, D] fp32, zero-initialised
   float* delta;            // [B, H, N] fp32 rowsum(dO * O)
+  long long* dbg;          // optional timeline buffer (sfc_debug_set_timeline), CTA 0 only
 };
 
 // write 32 consecutive P values (columns c32*32 .. +31 of row r) as bf16 into the K-major SW128 operand buffer
@@ -158,7 +160,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int qp = item % nqp, h = (item / nqp) % p.H, b = item / (nqp * p.H);
         const int row0 = b * p.N;
         for (int w = 0; w < 2; ++w) {
-          ptx::mbar_wait(&bars[FwdBars::q_empty + w], (ii & 1) ^ 1);
+          ptx::mbar_wait_relaxed(&bars[FwdBars::q_empty + w], (ii & 1) ^ 1);
           ptx::mbar_expect_tx(&bars[FwdBars::q_full + w], kTile);
           ptx::tma_load_2d(&tmap_q, &bars[FwdBars::q_full + w], smem + w * kTile, h * DH, row0 + qp * 2 * BQ + w * BQ);
         }
@@ -166,10 +168,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const int g = ii * nkv + j;
           const int st = g % stages;
           const uint32_t ph = (uint32_t)((g / stages) & 1);
-          ptx::mbar_wait(&bars[FwdBars::k_empty + st], ph ^ 1);
+          ptx::mbar_wait_relaxed(&bars[FwdBars::k_empty + st], ph ^ 1);
           ptx::mbar_expect_tx(&bars[FwdBars::k_full + st], (uint32_t)(bkv * 128));
           ptx::tma_load_2d(&tmap_kv, &bars[FwdBars::k_full + st], smem + L.off_k + st * kv_bytes, p.D + h * DH, row0 + j * bkv);
-          ptx::mbar_wait(&bars[FwdBars::v_empty + st], ph ^ 1);
+          ptx::mbar_wait_relaxed(&bars[FwdBars::v_empty + st], ph ^ 1);
           ptx::mbar_expect_tx(&bars[FwdBars::v_full + st], (uint32_t)(bkv * 128));
           ptx::tma_load_2d(&tmap_kv, &bars[FwdBars::v_full + st], smem + L.off_v + st * kv_bytes, 2 * p.D + h * DH, row0 + j * bkv);
         }
@@ -205,11 +207,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         ptx::tc_fence_after();
         const uint32_t sp = ptx::smem_u32(smem + L.off_p + w * L.p_atoms * kTile);
         const uint32_t sv = ptx::smem_u32(smem + L.off_v + st * kv_bytes);
-        for (int k = 0; k < bkv / 16; ++k) {
-          const uint64_t da = umma_smem_desc_sw128(sp + (k >> 2) * kTile + (k & 3) * 32, 0, 1024);
-          const uint64_t db = umma_smem_desc_sw128(sv + k * 2048, kTile, 1024);
-          ptx::umma_f16(tmem_base + w * 256, da, db, idesc_o, k > 0 ? 1u : 0u);
-        }
+        const uint64_t da0 = umma_smem_desc_sw128(sp, 0, 1024);
+        const uint64_t db0 = umma_smem_desc_sw128(sv, kTile, 1024);
+        const uint32_t a_lo = (uint32_t)da0, a_hi = (uint32_t)(da0 >> 32), b_lo = (uint32_t)db0, b_hi = (uint32_t)(db0 >> 32);
+        const int nk = bkv / 16;
+#pragma unroll
+        for (int k = 0; k < 13; ++k)                 // bkv <= 208; descriptor advances are compile-time constants
+          if (k < nk)
+            ptx::umma_f16_lohi(tmem_base + w * 256, a_lo + (uint32_t)((k >> 2) * (kTile >> 4) + (k & 3) * 2), a_hi,
+                               b_lo + (uint32_t)(k * 128), b_hi, idesc_o, k > 0 ? 1u : 0u);
         ptx::umma_commit(&bars[FwdBars::o_full + w]);
         if (w == 1) ptx::umma_commit(&bars[FwdBars::v_empty + st]);
       };
@@ -416,14 +422,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 // reduced into an fp32 scratch with red.global.add (key tiles of one head run on different CTAs).
 //   warp 0 : TMA producer (K, V per item, double buffered; Q, dO per step, 3 stages; runs ahead across items)
 //   warp 1 : MMA issuer
-//   warp 2 : TMEM allocator;  warps 4-11 : two element-wise warpgroups (thread <-> query row; warpgroup c owns the
-//            32-column chunks {2c, 2c+1} of the S / dP tile)
+//   warp 2 : TMEM allocator;  warps 4-19 : four element-wise warpgroups (thread <-> query row; warpgroup c owns the
+//            32-column chunk c of the S / dP tile) — 4 warps per scheduler hide each other's TMEM / MUFU latencies
 // TMEM (512 columns): S0 | S1 | dP | dV dK. Per step s the issuer runs
 //   S(s+1) -> S[(s+1)&1]        early, so the exp pass of step s+1 overlaps the gradient MMAs of step s
 //   dV += P^T dO, dK += dS^T Q, dQ(s) = dS K -> S[s&1] (dead by then)      after P / dS of step s are in smem
 //   dP(s+1) = dO V^T -> dP
 // and the warpgroups run  P = exp2(S - lse) (kept in registers)  ->  read dQ(s-1) out  ->  dS = P (dP - delta) scale.
-constexpr int kBwdThreads = 384;
+constexpr int kBwdEwWarps = 16;                 // element-wise warps: 4 per TMEM lane quarter, one 32-column chunk each
+constexpr int kBwdThreads = 128 + kBwdEwWarps * 32;
 constexpr int kQdoStages = 3;
 
 struct BwdSmem {
@@ -477,6 +484,30 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16*
   }
 }
 
+// Position in a CTA's step sequence, advanced without divisions: every warp role walks the same sequence, and with
+// five warps per scheduler each scalar instruction of a role costs several cycles of wall time.
+struct BwdCursor {
+  int s, ii, qt, jt, h, b, st3, ph3;     // step, local item, query tile, (key tile, head, image), Q/dO stage and its phase
+  int dj, dh, db, n_kvt, H, nq;
+  __device__ __forceinline__ void init(int n_kvt_, int H_, int nq_) {
+    n_kvt = n_kvt_; H = H_; nq = nq_;
+    const int item = (int)blockIdx.x, g = (int)gridDim.x;
+    jt = item % n_kvt; h = (item / n_kvt) % H; b = item / (n_kvt * H);
+    dj = g % n_kvt; dh = (g / n_kvt) % H; db = g / (n_kvt * H);
+    s = 0; ii = 0; qt = 0; st3 = 0; ph3 = 0;
+  }
+  __device__ __forceinline__ void advance() {
+    ++s;
+    if (++st3 == kQdoStages) { st3 = 0; ph3 ^= 1; }
+    if (++qt == nq) {
+      qt = 0; ++ii;
+      jt += dj; if (jt >= n_kvt) { jt -= n_kvt; ++h; }
+      h += dh; if (h >= H) { h -= H; ++b; }
+      b += db;
+    }
+  }
+};
+
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                 const __grid_constant__ CUtensorMap tmap_do, const AttnParams p, const int bkv) {
@@ -506,9 +537,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       ptx::mbar_init(&bars[BwdBars::qdo_empty + i], 1);
     }
     ptx::mbar_init(&bars[BwdBars::dp_full], 1);
-    ptx::mbar_init(&bars[BwdBars::pds_full], 256);
+    ptx::mbar_init(&bars[BwdBars::pds_full], kBwdEwWarps * 32);
     ptx::mbar_init(&bars[BwdBars::dq_full], 1);
-    ptx::mbar_init(&bars[BwdBars::dq_empty], 256);
+    ptx::mbar_init(&bars[BwdBars::dq_empty], kBwdEwWarps * 32);
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc<512>(tmem_ptr);
@@ -521,23 +552,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (ptx::elect_one()) {
-      int ii = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ii) {
-        const int jt = item % n_kvt, h = (item / n_kvt) % p.H, b = item / (n_kvt * p.H);
-        const int row0 = b * p.N;
-        const int kvst = ii & 1;
-        ptx::mbar_wait(&bars[BwdBars::kv_empty + kvst], ((ii >> 1) & 1) ^ 1);
-        ptx::mbar_expect_tx(&bars[BwdBars::kv_full + kvst], (uint32_t)(2 * bkv * 128));
-        ptx::tma_load_2d(&tmap_kv, &bars[BwdBars::kv_full + kvst], smem + BwdSmem::kK + kvst * kTile, p.D + h * DH, row0 + jt * bkv);
-        ptx::tma_load_2d(&tmap_kv, &bars[BwdBars::kv_full + kvst], smem + BwdSmem::kV + kvst * kTile, 2 * p.D + h * DH, row0 + jt * bkv);
-        for (int qt = 0; qt < nq; ++qt) {
-          const int s = ii * nq + qt;
-          const int st = s % kQdoStages;
-          ptx::mbar_wait(&bars[BwdBars::qdo_empty + st], ((s / kQdoStages) & 1) ^ 1);
-          ptx::mbar_expect_tx(&bars[BwdBars::qdo_full + st], 2 * kTile);
-          ptx::tma_load_2d(&tmap_q, &bars[BwdBars::qdo_full + st], smem + BwdSmem::kQ + st * kTile, h * DH, row0 + qt * BQ);
-          ptx::tma_load_2d(&tmap_do, &bars[BwdBars::qdo_full + st], smem + BwdSmem::kDO + st * kTile, h * DH, row0 + qt * BQ);
+      BwdCursor c;
+      c.init(n_kvt, p.H, nq);
+      for (; c.s < T; c.advance()) {
+        const int row0 = c.b * p.N;
+        if (c.qt == 0) {
+          const int kvst = c.ii & 1;
+          ptx::mbar_wait_relaxed(&bars[BwdBars::kv_empty + kvst], ((c.ii >> 1) & 1) ^ 1);
+          ptx::mbar_expect_tx(&bars[BwdBars::kv_full + kvst], (uint32_t)(2 * bkv * 128));
+          ptx::tma_load_2d(&tmap_kv, &bars[BwdBars::kv_full + kvst], smem + BwdSmem::kK + kvst * kTile, p.D + c.h * DH, row0 + c.jt * bkv);
+          ptx::tma_load_2d(&tmap_kv, &bars[BwdBars::kv_full + kvst], smem + BwdSmem::kV + kvst * kTile, 2 * p.D + c.h * DH, row0 + c.jt * bkv);
         }
+        const int st = c.st3;
+        ptx::mbar_wait_relaxed(&bars[BwdBars::qdo_empty + st], (uint32_t)(c.ph3 ^ 1));
+        ptx::mbar_expect_tx(&bars[BwdBars::qdo_full + st], 2 * kTile);
+        ptx::tma_load_2d(&tmap_q, &bars[BwdBars::qdo_full + st], smem + BwdSmem::kQ + st * kTile, c.h * DH, row0 + c.qt * BQ);
+        ptx::tma_load_2d(&tmap_do, &bars[BwdBars::qdo_full + st], smem + BwdSmem::kDO + st * kTile, c.h * DH, row0 + c.qt * BQ);
       }
     }
     __syncwarp();
@@ -547,10 +577,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const uint32_t idesc_s = umma_idesc_bf16(BQ, bkv, false, false);     // S, dP : K-major x K-major, N = bkv
       const uint32_t idesc_t = umma_idesc_bf16(128, DH, true, true);       // dV, dK: MN-major A (P^T / dS^T), MN-major B
       const uint32_t idesc_q = umma_idesc_bf16(BQ, DH, false, true);       // dQ    : K-major A (dS), MN-major B (K)
-      auto s_issue = [&](int s) {
-        const int ii = s / nq, qt = s % nq, st = s % kQdoStages, kvst = ii & 1;
-        ptx::mbar_wait(&bars[BwdBars::qdo_full + st], (s / kQdoStages) & 1);
-        if (qt == 0) ptx::mbar_wait(&bars[BwdBars::kv_full + kvst], (ii >> 1) & 1);
+      auto s_issue = [&](const BwdCursor& c) {
+        const int s = c.s, st = c.st3, kvst = c.ii & 1;
+        ptx::mbar_wait(&bars[BwdBars::qdo_full + st], (uint32_t)c.ph3);
+        if (c.qt == 0) ptx::mbar_wait(&bars[BwdBars::kv_full + kvst], (c.ii >> 1) & 1);
         if (s >= 2) ptx::mbar_wait(&bars[BwdBars::dq_empty], s & 1);       // dQ(s-2) read out of S[s&1]
         ptx::tc_fence_after();
         const uint64_t dq = umma_smem_desc_sw128(ptx::smem_u32(smem + BwdSmem::kQ + st * kTile), 0, 1024);
@@ -560,8 +590,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           ptx::umma_f16(tmem_base + (s & 1) * 128, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
         ptx::umma_commit(&bars[BwdBars::s_full + (s & 1)]);
       };
-      auto dp_issue = [&](int s) {
-        const int ii = s / nq, st = s % kQdoStages, kvst = ii & 1;
+      auto dp_issue = [&](const BwdCursor& c) {
+        const int st = c.st3, kvst = c.ii & 1;
         const uint64_t ddo = umma_smem_desc_sw128(ptx::smem_u32(smem + BwdSmem::kDO + st * kTile), 0, 1024);
         const uint64_t dv = umma_smem_desc_sw128(ptx::smem_u32(smem + BwdSmem::kV + kvst * kTile), 0, 1024);
 #pragma unroll
@@ -569,106 +599,120 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           ptx::umma_f16(tmem_dp, ddo + (uint64_t)(k * 2), dv + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
         ptx::umma_commit(&bars[BwdBars::dp_full]);
       };
-      auto grad_issue = [&](int s) {
-        const int ii = s / nq, qt = s % nq, st = s % kQdoStages, kvst = ii & 1;
-        const int item = (int)blockIdx.x + ii * (int)gridDim.x;
-        const int jt = item % n_kvt;
-        const int kv_valid = min(bkv, p.N - jt * bkv);
+      auto grad_issue = [&](const BwdCursor& c) {
+        const int s = c.s, qt = c.qt, st = c.st3, kvst = c.ii & 1;
+        const int kv_valid = min(bkv, p.N - c.jt * bkv);
         const int q_valid = min(BQ, p.N - qt * BQ);
         const int nk_q = (q_valid + 15) / 16, nk_kv = (kv_valid + 15) / 16;
-        ptx::mbar_wait(&bars[BwdBars::pds_full], s & 1);
-        ptx::tc_fence_after();
         const uint32_t sp = ptx::smem_u32(smem + BwdSmem::kP);
         const uint32_t sds = ptx::smem_u32(smem + BwdSmem::kDS);
         const uint32_t sq = ptx::smem_u32(smem + BwdSmem::kQ + st * kTile);
         const uint32_t sdo = ptx::smem_u32(smem + BwdSmem::kDO + st * kTile);
         const uint32_t sk = ptx::smem_u32(smem + BwdSmem::kK + kvst * kTile);
         // dV[kv, d] += sum_q P[q, kv] dO[q, d]   ;   dK[kv, d] += sum_q dS[q, kv] Q[q, d]     (reduction over q rows)
-        for (int k = 0; k < nk_q; ++k) {
-          const uint64_t a_p = umma_smem_desc_sw128(sp + k * 2048, kTile, 1024);
-          const uint64_t b_do = umma_smem_desc_sw128(sdo + k * 2048, kTile, 1024);
-          ptx::umma_f16(tmem_dv, a_p, b_do, idesc_t, (qt > 0 || k > 0) ? 1u : 0u);
-        }
-        for (int k = 0; k < nk_q; ++k) {
-          const uint64_t a_ds = umma_smem_desc_sw128(sds + k * 2048, kTile, 1024);
-          const uint64_t b_q = umma_smem_desc_sw128(sq + k * 2048, kTile, 1024);
-          ptx::umma_f16(tmem_dk, a_ds, b_q, idesc_t, (qt > 0 || k > 0) ? 1u : 0u);
-        }
+        // Descriptors as {lo, hi} words with compile-time advances: the single issuing thread shares its scheduler with
+        // two element-wise warps, so every instruction it does not execute shortens the critical path of the step.
+        auto lohi = [](uint64_t d, uint32_t& lo, uint32_t& hi) { lo = (uint32_t)d; hi = (uint32_t)(d >> 32); };
+        uint32_t p_lo, p_hi, do_lo, do_hi, ds_lo, ds_hi, q_lo, q_hi, dsk_lo, dsk_hi, k_lo, k_hi;
+        lohi(umma_smem_desc_sw128(sp, kTile, 1024), p_lo, p_hi);
+        lohi(umma_smem_desc_sw128(sdo, kTile, 1024), do_lo, do_hi);
+        lohi(umma_smem_desc_sw128(sds, kTile, 1024), ds_lo, ds_hi);
+        lohi(umma_smem_desc_sw128(sq, kTile, 1024), q_lo, q_hi);
+        lohi(umma_smem_desc_sw128(sds, 0, 1024), dsk_lo, dsk_hi);
+        lohi(umma_smem_desc_sw128(sk, kTile, 1024), k_lo, k_hi);
+        const uint32_t acc0 = qt > 0 ? 1u : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < nk_q) ptx::umma_f16_lohi(tmem_dv, p_lo + (uint32_t)(k * 128), p_hi, do_lo + (uint32_t)(k * 128), do_hi, idesc_t, k > 0 ? 1u : acc0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < nk_q) ptx::umma_f16_lohi(tmem_dk, ds_lo + (uint32_t)(k * 128), ds_hi, q_lo + (uint32_t)(k * 128), q_hi, idesc_t, k > 0 ? 1u : acc0);
         // dQ[q, d] = sum_kv dS[q, kv] K[kv, d]  -> S[s & 1] columns 0..63
-        for (int k = 0; k < nk_kv; ++k) {
-          const uint64_t a_ds = umma_smem_desc_sw128(sds + (k >> 2) * kTile + (k & 3) * 32, 0, 1024);
-          const uint64_t b_k = umma_smem_desc_sw128(sk + k * 2048, kTile, 1024);
-          ptx::umma_f16(tmem_base + (s & 1) * 128, a_ds, b_k, idesc_q, k > 0 ? 1u : 0u);
-        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < nk_kv)
+            ptx::umma_f16_lohi(tmem_base + (s & 1) * 128, dsk_lo + (uint32_t)((k >> 2) * (kTile >> 4) + (k & 3) * 2), dsk_hi,
+                               k_lo + (uint32_t)(k * 128), k_hi, idesc_q, k > 0 ? 1u : 0u);
         ptx::umma_commit(&bars[BwdBars::dq_full]);
         ptx::umma_commit(&bars[BwdBars::qdo_empty + st]);
         if (qt == nq - 1) ptx::umma_commit(&bars[BwdBars::kv_empty + kvst]);
       };
+      long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
       if (T > 0) {
-        s_issue(0);
-        dp_issue(0);
+        BwdCursor c0, c1;                                        // steps s and s + 1
+        c0.init(n_kvt, p.H, nq);
+        c1 = c0;
+        s_issue(c0);
+        dp_issue(c0);
+        c1.advance();
         for (int s = 0; s < T; ++s) {
-          if (s + 1 < T) s_issue(s + 1);
-          grad_issue(s);
-          if (s + 1 < T) dp_issue(s + 1);
+          if (dbg && s < 64) dbg[s * 16 + 8] = clock64();
+          if (s + 1 < T) s_issue(c1);
+          if (dbg && s < 64) dbg[s * 16 + 9] = clock64();
+          ptx::mbar_wait(&bars[BwdBars::pds_full], s & 1);       // P / dS of step s are in smem, dP(s) has been consumed
+          if (dbg && s < 64) dbg[s * 16 + 12] = clock64();
+          ptx::tc_fence_after();
+          if (s + 1 < T) dp_issue(c1);                           // first: it is the input the warpgroups wait for next
+          if (dbg && s < 64) dbg[s * 16 + 11] = clock64();
+          grad_issue(c0);
+          if (dbg && s < 64) dbg[s * 16 + 10] = clock64();
+          c0 = c1;
+          c1.advance();
         }
       }
     }
     __syncwarp();
   } else if (warp >= 4) {
     // ===================== element-wise warpgroups =====================
-    const int ch = (warp - 4) >> 2;                // column half: chunks {2ch, 2ch+1}
+    const int ch = (warp - 4) >> 2;                // this warp's 32-column chunk of the S / dP tile (0..3)
     const int quarter = warp & 3;
     const int lane = tid & 31;
     const int r = quarter * 32 + lane;             // query row in tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const float sl2 = p.scale * kLog2e;
+    const float scale_ = p.scale;
     const DropKey dkey = drop_key(p.drop_seed, p.drop_p, p.drop_epoch);
     const bool has_drop = p.drop_p > 0.f;
     const uint32_t thr_hi = dkey.thr16 << 16;
     const int nch = (bkv + 31) / 32;
 
     // readout of step sp (its dQ; and dV / dK when it was the last step of its item)
-    auto readout = [&](int sp) {
-      const int ii = sp / nq, qt = sp % nq;
-      const int item = (int)blockIdx.x + ii * (int)gridDim.x;
-      const int jt = item % n_kvt, h = (item / n_kvt) % p.H, b = item / (n_kvt * p.H);
-      const int row0 = b * p.N;
+    auto readout = [&](const BwdCursor& cp) {
+      const int sp = cp.s, qt = cp.qt, jt = cp.jt, h = cp.h;
+      const int row0 = cp.b * p.N;
       ptx::mbar_wait(&bars[BwdBars::dq_full], sp & 1);
       ptx::tc_fence_after();
       {
-        uint32_t rr[32];
-        ptx::tmem_ld_x32(tmem_base + (sp & 1) * 128 + lane_off + ch * 32, rr);
+        uint32_t rr[16];
+        ptx::tmem_ld_x16(tmem_base + (sp & 1) * 128 + lane_off + ch * 16, rr);
         ptx::tmem_ld_wait();
         const int qi = qt * BQ + r;
         if (qi < p.N) {
-          float* dst = p.dq_acc + (long long)(row0 + qi) * p.D + h * DH + ch * 32;
+          float* dst = p.dq_acc + (long long)(row0 + qi) * p.D + h * DH + ch * 16;
 #pragma unroll
-          for (int e = 0; e < 32; e += 4)
+          for (int e = 0; e < 16; e += 4)
             red_add_v4(dst + e, __uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3]));
         }
       }
       if (qt == nq - 1) {
-        // dV (warpgroup 0) / dK (warpgroup 1): TMEM lane == key row of this tile
+        // dV (chunks 0, 1) / dK (chunks 2, 3), 32 columns per warp: TMEM lane == key row of this tile
         const int kvi = jt * bkv + r;
         const bool ok = r < bkv && kvi < p.N;
-        const uint32_t t = (ch == 0 ? tmem_dv : tmem_dk) + lane_off;
-        __nv_bfloat16* dst = p.dqkv + (long long)(row0 + kvi) * (3 * p.D) + (ch == 0 ? 2 * p.D : p.D) + h * DH;
+        const int half = ch & 1;
+        const uint32_t t = (ch < 2 ? tmem_dv : tmem_dk) + lane_off + half * 32;
+        __nv_bfloat16* dst = p.dqkv + (long long)(row0 + kvi) * (3 * p.D) + (ch < 2 ? 2 * p.D : p.D) + h * DH + half * 32;
+        uint32_t rr[32];
+        ptx::tmem_ld_x32(t, rr);
+        ptx::tmem_ld_wait();
+        if (ok) {
 #pragma unroll
-        for (int c = 0; c < DH / 32; ++c) {
-          uint32_t rr[32];
-          ptx::tmem_ld_x32(t + c * 32, rr);
-          ptx::tmem_ld_wait();
-          if (ok) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 o;
-              o.x = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 0]), __uint_as_float(rr[q * 8 + 1]));
-              o.y = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 2]), __uint_as_float(rr[q * 8 + 3]));
-              o.z = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 4]), __uint_as_float(rr[q * 8 + 5]));
-              o.w = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 6]), __uint_as_float(rr[q * 8 + 7]));
-              reinterpret_cast<uint4*>(dst + c * 32)[q] = o;
-            }
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 0]), __uint_as_float(rr[q * 8 + 1]));
+            o.y = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 2]), __uint_as_float(rr[q * 8 + 3]));
+            o.z = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 4]), __uint_as_float(rr[q * 8 + 5]));
+            o.w = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 6]), __uint_as_float(rr[q * 8 + 7]));
+            reinterpret_cast<uint4*>(dst)[q] = o;
           }
         }
       }
@@ -676,103 +720,116 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       ptx::mbar_arrive(&bars[BwdBars::dq_empty]);
     };
 
-    int s = 0;
-    for (int ii = 0; ii < my_items; ++ii) {
-      const int item = (int)blockIdx.x + ii * (int)gridDim.x;
-      const int jt = item % n_kvt, h = (item / n_kvt) % p.H, b = item / (n_kvt * p.H);
-      const int kv0 = jt * bkv;
-      const int kv_valid = min(bkv, p.N - kv0);
-      for (int qt = 0; qt < nq; ++qt, ++s) {
+    // row statistics of a step: lse * log2e (+inf for rows past the sequence end, so that P = exp2(-inf) = 0 without a
+    // branch) and delta. They are loaded one step ahead: the global-load latency hides behind the previous step.
+    auto load_stats = [&](const BwdCursor& cn, float& l2, float& dl) {
+      l2 = INFINITY; dl = 0.f;
+      const int qi2 = cn.qt * BQ + r;
+      if (cn.s < T && qi2 < p.N) {
+        const long long si = ((long long)cn.b * p.H + cn.h) * p.N + qi2;
+        // volatile asm: issued HERE (the compiler may not sink it to its use in the next step); the multiply by
+        // log2e happens at use, so this step does not stall on the load
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(l2) : "l"(p.lse + si));
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(dl) : "l"(p.delta + si));
+      }
+    };
+    BwdCursor cur, nxt, prev;
+    cur.init(n_kvt, p.H, nq);
+    nxt = cur;
+    prev = cur;
+    float lse2_next, delta_next;
+    load_stats(cur, lse2_next, delta_next);
+    nxt.advance();
+    for (; cur.s < T; prev = cur, cur = nxt, nxt.advance()) {
+      {
+        const int s = cur.s, qt = cur.qt, h = cur.h, b = cur.b;
+        const int kv0 = cur.jt * bkv;
+        const int kv_valid = min(bkv, p.N - kv0);
         const int qi = qt * BQ + r;
-        const bool q_ok = qi < p.N;
         const int q_valid = min(BQ, p.N - qt * BQ);
         const bool warp_active = quarter * 32 < ((q_valid + 15) / 16) * 16;   // rows read by the dV / dK MMAs
-        float lse2 = 0.f, delta = 0.f;
-        if (q_ok) {
-          const long long si = ((long long)b * p.H + h) * p.N + qi;
-          lse2 = __ldg(p.lse + si) * kLog2e;
-          delta = __ldg(p.delta + si);
-        }
+        const float lse2 = lse2_next * kLog2e, delta = delta_next;
+        load_stats(nxt, lse2_next, delta_next);
         // ---- phase A: P = exp2(S * scale * log2e - lse * log2e), kept in registers (+ dropout keep bits)
-        float pr[2][32];
+        float pr[32];
+        long long* dbg = (blockIdx.x == 0 && tid == 128 && s < 64) ? p.dbg : nullptr;
+        if (dbg) dbg[s * 16 + 0] = clock64();
         ptx::mbar_wait(&bars[BwdBars::s_full + (s & 1)], (s >> 1) & 1);
+        if (dbg) dbg[s * 16 + 1] = clock64();
         ptx::tc_fence_after();
-        if (warp_active) {
+        const int c = ch;
+        const bool chunk_active = warp_active && c < nch;
+        if (chunk_active) {
+          uint32_t rs[32];
+          ptx::tmem_ld_x32(tmem_base + (s & 1) * 128 + lane_off + c * 32, rs);
+          ptx::tmem_ld_wait();
+          if (c * 32 + 32 <= kv_valid) {
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int c = ch * 2 + cc;
-            if (c < nch) {
-              uint32_t rs[32];
-              ptx::tmem_ld_x32(tmem_base + (s & 1) * 128 + lane_off + c * 32, rs);
-              ptx::tmem_ld_wait();
+            for (int e = 0; e < 32; ++e) pr[e] = ex2_approx(fmaf(__uint_as_float(rs[e]), sl2, -lse2));
+          } else {
 #pragma unroll
-              for (int e = 0; e < 32; ++e) {
-                const bool ok = q_ok && (c * 32 + e < kv_valid);
-                pr[cc][e] = ok ? ex2_approx(fmaf(__uint_as_float(rs[e]), sl2, -lse2)) : 0.f;
-              }
-              if (has_drop) {
-                // the keep decision travels to phase B in the sign of P (P >= 0): dropped elements are stored negated
-                const unsigned long long base = (((unsigned long long)(b * p.H + h) * p.N + (unsigned long long)qi) * (unsigned long long)((p.N + 15) & ~15)) + (unsigned long long)(kv0 + c * 32);
-                if ((base & 15ull) == 0) {
+            for (int e = 0; e < 32; ++e)
+              pr[e] = (c * 32 + e < kv_valid) ? ex2_approx(fmaf(__uint_as_float(rs[e]), sl2, -lse2)) : 0.f;
+          }
+          if (has_drop) {
+            // the keep decision travels to phase B in the sign of P (P >= 0): dropped elements are stored negated
+            const unsigned long long base = (((unsigned long long)(b * p.H + h) * p.N + (unsigned long long)qi) * (unsigned long long)((p.N + 15) & ~15)) + (unsigned long long)(kv0 + c * 32);
+            if ((base & 15ull) == 0) {
 #pragma unroll
-                  for (int g2 = 0; g2 < 2; ++g2) {
-                    const uint32_t seed = drop_hash2(dkey, (base >> 4) + g2);
+              for (int g2 = 0; g2 < 2; ++g2) {
+                const uint32_t seed = drop_hash2(dkey, (base >> 4) + g2);
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                      const uint32_t x = seed * lcg_mul(e + 1) + lcg_add(e + 1);
-                      pr[cc][g2 * 16 + e] = (x >= thr_hi) ? pr[cc][g2 * 16 + e] : -pr[cc][g2 * 16 + e];
-                    }
-                  }
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 32; ++e) pr[cc][e] = drop_keep<16>(dkey, base + e) ? pr[cc][e] : -pr[cc][e];
+                for (int e = 0; e < 16; ++e) {
+                  const uint32_t x = seed * lcg_mul(e + 1) + lcg_add(e + 1);
+                  pr[g2 * 16 + e] = (x >= thr_hi) ? pr[g2 * 16 + e] : -pr[g2 * 16 + e];
                 }
               }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) pr[e] = drop_keep<16>(dkey, base + e) ? pr[e] : -pr[e];
             }
           }
         }
         // ---- dQ (and dV / dK) of the previous step leave TMEM; this also guarantees its MMAs no longer read P / dS smem
-        if (s > 0) readout(s - 1);
+        if (dbg) dbg[s * 16 + 2] = clock64();
+        if (s > 0) readout(prev);
+        if (dbg) dbg[s * 16 + 3] = clock64();
         // ---- phase B: dS = P * (dP - delta) * scale; P (dropped) and dS -> shared memory
         ptx::mbar_wait(&bars[BwdBars::dp_full], s & 1);
+        if (dbg) dbg[s * 16 + 4] = clock64();
         ptx::tc_fence_after();
-        if (warp_active) {
+        if (chunk_active) {
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int c = ch * 2 + cc;
-            if (c < nch) {
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t rd[16];
+            ptx::tmem_ld_x16(tmem_dp + lane_off + c * 32 + hf * 16, rd);
+            ptx::tmem_ld_wait();
+            float pv[16], dsv[16];
 #pragma unroll
-              for (int hf = 0; hf < 2; ++hf) {
-                uint32_t rd[16];
-                ptx::tmem_ld_x16(tmem_dp + lane_off + c * 32 + hf * 16, rd);
-                ptx::tmem_ld_wait();
-                float pv[16], dsv[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                  const float ps = pr[cc][hf * 16 + e];
-                  const float pe = fabsf(ps);
-                  float dp = __uint_as_float(rd[e]);
-                  float pd = pe;
-                  if (has_drop) {
-                    const bool k = ps > 0.f;
-                    pd = k ? pe * dkey.inv_keep : 0.f;
-                    dp = k ? dp * dkey.inv_keep : 0.f;
-                  }
-                  pv[e] = pd;
-                  dsv[e] = pe * (dp - delta) * p.scale;      // pe == 0 outside the valid region
-                }
-                store_p_half(smem + BwdSmem::kP, r, c * 2 + hf, pv);
-                store_p_half(smem + BwdSmem::kDS, r, c * 2 + hf, dsv);
+            for (int e = 0; e < 16; ++e) {
+              const float ps = pr[hf * 16 + e];
+              const float pe = fabsf(ps);
+              const float dp = __uint_as_float(rd[e]);
+              if (has_drop) {
+                const bool k = ps > 0.f;
+                pv[e] = k ? pe * dkey.inv_keep : 0.f;
+                dsv[e] = pe * scale_ * (k ? fmaf(dp, dkey.inv_keep, -delta) : -delta);
+              } else {
+                pv[e] = pe;
+                dsv[e] = pe * scale_ * (dp - delta);       // pe == 0 outside the valid region
               }
             }
+            store_p_half(smem + BwdSmem::kP, r, c * 2 + hf, pv);
+            store_p_half(smem + BwdSmem::kDS, r, c * 2 + hf, dsv);
           }
         }
+        if (dbg) dbg[s * 16 + 5] = clock64();
         ptx::tc_fence_before();
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&bars[BwdBars::pds_full]);
       }
     }
-    if (T > 0) readout(T - 1);
+    if (T > 0) readout(prev);
   }
 
   ptx::tc_fence_before();
@@ -797,6 +854,8 @@ __global__ void dq_finalize_kernel(const float* __restrict__ dq_acc, __nv_bfloat
     *reinterpret_cast<uint4*>(dqkv + m * (3ll * D) + c) = o;
   }
 }
+
+long long* g_attn_dbg = nullptr;
 
 int check_shape(int B, int H, int N, int D) {
   SFC_REQUIRE(B > 0 && H > 0 && N > 0 && D == H * DH, "attention: only head_dim = 64 is supported (D=%d, heads=%d)", D, H);
@@ -867,7 +926,7 @@ extern "C" int sfc_attn_bwd(const void* qkv, const void* out, const void* dout, 
   AttnParams p{};
   p.B = B; p.H = H; p.N = N; p.D = D; p.scale = scale; p.drop_p = drop_p; p.drop_seed = drop_seed; p.drop_epoch = sfc_dropout_epoch_ptr();
   p.lse = const_cast<float*>(lse); p.o = (const __nv_bfloat16*)out; p.dout = (const __nv_bfloat16*)dout;
-  p.dqkv = (__nv_bfloat16*)dqkv; p.dq_acc = (float*)scratch; p.delta = delta;
+  p.dqkv = (__nv_bfloat16*)dqkv; p.dq_acc = (float*)scratch; p.delta = delta; p.dbg = g_attn_dbg;
   static bool configured = false;
   if (!configured) {
     SFC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal));
@@ -884,3 +943,6 @@ extern "C" int sfc_attn_bwd(const void* qkv, const void* out, const void* dout, 
   SFC_LAUNCH_OK();
   return 0;
 }
+
+// Debug: per-step clock64() timeline of CTA 0 of the next sfc_attn_bwd launches (>= 64 * 16 int64; NULL = off).
+extern "C" void sfc_debug_set_timeline(void* dev_ptr) { g_attn_dbg = (long long*)dev_ptr; }
