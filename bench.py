@@ -67,7 +67,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -244,11 +244,13 @@ def main():
 
     # ---------------- roofline pass: the same step launched eagerly with CUDA events around every GEMM launch
     ops.GEMM_PROFILE = []
+    ops.PE_PROFILE = []
     roof_steps = min(3, max(1, args.steps))
     for i in range(roof_steps):
         eager_step(dev_imgs[i % n_bufs])
     sync_all()
     prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+    pe_prof, ops.PE_PROFILE = ops.PE_PROFILE, None
     gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
     gemm_flops = sum(f for _, _, f in prof)
 
@@ -317,6 +319,18 @@ def main():
         "whole_step_frac_of_peak": step_flops / (ms_total / args.steps * 1e-3) / 1e12 / peaks["tf_sustained"],
     }
 
+    # second metric named by BASELINE.json: HBM GB/s of the fused curve-gather patch embed (algorithmic bytes = image read
+    # once + token matrix written once), timed in the same eager replica
+    pe_ms = sum(a.elapsed_time(b_) for a, b_, _, _ in pe_prof) / max(1, len(pe_prof))
+    pe_bytes = pe_prof[0][2] if pe_prof else 0
+    pe_flops = pe_prof[0][3] if pe_prof else 0
+    pe_gbs = pe_bytes / (pe_ms * 1e-3) / 1e9 if pe_ms > 0 else 0.0
+    t_roof_ms = max(pe_bytes / (peaks["hbm_gbs"] * 1e9), pe_flops / (peaks["tf_sustained"] * 1e12)) * 1e3
+    patch_embed = {"kernel": "patch_embed_fwd_kernel (curve-order gather fused into the tcgen05 patch-embedding GEMM)", "ms": pe_ms,
+                   "algorithmic_bytes": pe_bytes, "achieved_gbs": pe_gbs, "hbm_peak_gbs": peaks["hbm_gbs"],
+                   "frac_hbm": pe_gbs / peaks["hbm_gbs"], "bound": "tensor at K = 768 (SURVEY.md §8d)",
+                   "frac_of_max_hbm_tensor_roofline": t_roof_ms / pe_ms if pe_ms > 0 else 0.0, "input_dtype": "fp32"}
+
     # ---------------- timed region 2: end to end (pinned host inputs -> H2D every step, loss read back)
     host_imgs = [torch.randn(B, 3, c["img"], c["img"]).pin_memory() for _ in range(2)]
     stage = [torch.empty(B, 3, c["img"], c["img"], device=device) for _ in range(2)]
@@ -372,7 +386,7 @@ def main():
                        "dropout": not args.no_dropout, "params_dtype": "bf16", "parallelism": f"dp{world}",
                        "launch": "eager" if graphed is None else "forward+backward replayed from one CUDA graph; optimizer eager",
                        "l2_policy": f"{n_bufs} rotating input batches of {B * 3 * c['img'] ** 2 * 4 / 1e6:.0f} MB (> 126 MB L2); activations per step ~GBs"},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "patch_embed": patch_embed, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
             "gpu_launches_per_step": launches / args.steps, "clocks": clocks, "loss": float(loss.item()),
             "allreduce_buckets_per_step": opt.last_num_buckets,
         }

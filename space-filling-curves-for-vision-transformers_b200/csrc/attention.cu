@@ -160,7 +160,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int qp = item % nqp, h = (item / nqp) % p.H, b = item / (nqp * p.H);
         const int row0 = b * p.N;
         for (int w = 0; w < 2; ++w) {
-          ptx::mbar_wait_relaxed(&bars[FwdBars::q_empty + w], (ii & 1) ^ 1);
+          ptx::mbar_wait(&bars[FwdBars::q_empty + w], (ii & 1) ^ 1);
           ptx::mbar_expect_tx(&bars[FwdBars::q_full + w], kTile);
           ptx::tma_load_2d(&tmap_q, &bars[FwdBars::q_full + w], smem + w * kTile, h * DH, row0 + qp * 2 * BQ + w * BQ);
         }
@@ -168,10 +168,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const int g = ii * nkv + j;
           const int st = g % stages;
           const uint32_t ph = (uint32_t)((g / stages) & 1);
-          ptx::mbar_wait_relaxed(&bars[FwdBars::k_empty + st], ph ^ 1);
+          ptx::mbar_wait(&bars[FwdBars::k_empty + st], ph ^ 1);
           ptx::mbar_expect_tx(&bars[FwdBars::k_full + st], (uint32_t)(bkv * 128));
           ptx::tma_load_2d(&tmap_kv, &bars[FwdBars::k_full + st], smem + L.off_k + st * kv_bytes, p.D + h * DH, row0 + j * bkv);
-          ptx::mbar_wait_relaxed(&bars[FwdBars::v_empty + st], ph ^ 1);
+          ptx::mbar_wait(&bars[FwdBars::v_empty + st], ph ^ 1);
           ptx::mbar_expect_tx(&bars[FwdBars::v_full + st], (uint32_t)(bkv * 128));
           ptx::tma_load_2d(&tmap_kv, &bars[FwdBars::v_full + st], smem + L.off_v + st * kv_bytes, 2 * p.D + h * DH, row0 + j * bkv);
         }
@@ -558,13 +558,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int row0 = c.b * p.N;
         if (c.qt == 0) {
           const int kvst = c.ii & 1;
-          ptx::mbar_wait_relaxed(&bars[BwdBars::kv_empty + kvst], ((c.ii >> 1) & 1) ^ 1);
+          ptx::mbar_wait(&bars[BwdBars::kv_empty + kvst], ((c.ii >> 1) & 1) ^ 1);
           ptx::mbar_expect_tx(&bars[BwdBars::kv_full + kvst], (uint32_t)(2 * bkv * 128));
           ptx::tma_load_2d(&tmap_kv, &bars[BwdBars::kv_full + kvst], smem + BwdSmem::kK + kvst * kTile, p.D + c.h * DH, row0 + c.jt * bkv);
           ptx::tma_load_2d(&tmap_kv, &bars[BwdBars::kv_full + kvst], smem + BwdSmem::kV + kvst * kTile, 2 * p.D + c.h * DH, row0 + c.jt * bkv);
         }
         const int st = c.st3;
-        ptx::mbar_wait_relaxed(&bars[BwdBars::qdo_empty + st], (uint32_t)(c.ph3 ^ 1));
+        ptx::mbar_wait(&bars[BwdBars::qdo_empty + st], (uint32_t)(c.ph3 ^ 1));
         ptx::mbar_expect_tx(&bars[BwdBars::qdo_full + st], 2 * kTile);
         ptx::tma_load_2d(&tmap_q, &bars[BwdBars::qdo_full + st], smem + BwdSmem::kQ + st * kTile, c.h * DH, row0 + c.qt * BQ);
         ptx::tma_load_2d(&tmap_do, &bars[BwdBars::qdo_full + st], smem + BwdSmem::kDO + st * kTile, c.h * DH, row0 + c.qt * BQ);

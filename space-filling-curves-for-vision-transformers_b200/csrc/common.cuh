@@ -177,6 +177,21 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
   }
 }
 
+// Wait with sleep back-off for warps whose wait is long and not latency-critical (GEMM epilogue warps wait a whole
+// main loop for the accumulator): polling burns issue slots and power on a power-capped part.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++spins == (1u << 26)) {
+      printf("sfcvit: mbarrier wait timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void mbar_wait_sleep_default(uint64_t* bar, uint32_t parity) { mbar_wait_sleep(bar, parity, 64); }
+
 // ---- proxies / fences ----
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

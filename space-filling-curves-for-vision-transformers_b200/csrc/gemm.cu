@@ -117,7 +117,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int kb1 = min(kb0 + p.kblocks_per_split, p.num_k_blocks);
         const int n0 = n_tile * BN + crank * BNH;
         for (int kb = kb0; kb < kb1; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_wait_sleep(&empty_bar[stage], phase ^ 1, 32);
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
           if constexpr (CL == 1) {
@@ -226,7 +226,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int m_tile = (tile / p.num_n_tiles) * CL + crank;
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
-      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::mbar_wait_sleep(&tmem_full[acc], acc_phase, 64);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + half * (BN / 2) + ((uint32_t)(quarter * 32) << 16);
       const int n0 = n_tile * BN + half * (BN / 2);

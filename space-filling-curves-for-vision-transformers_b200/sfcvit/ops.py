@@ -14,6 +14,7 @@ CURVE_IDS = {"hilbert_curve": 0, "z_curve": 1, "peano_curve": 2, "moore_curve": 
 # ---- instrumentation (bench.py): kernel-launch counter and optional per-GEMM CUDA-event timing -------------
 LAUNCHES = 0            # kernels launched through the C ABI by this process
 GEMM_PROFILE = None     # when a list: (start_event, end_event, flops) appended per sfc_gemm_bf16 call
+PE_PROFILE = None       # when a list: (start_event, end_event, algorithmic_bytes, flops) per sfc_patch_embed_fwd call
 
 
 def _count(n):
@@ -223,10 +224,17 @@ def patch_embed_fwd(img, perm, wk, bias, p, g, *, pos=None, out=None, col_off=0,
     assert out.dtype == torch.bfloat16 and out.stride(-1) == 1 and out.shape[0] == B and out.shape[1] == rows_per_img
     assert out.stride(0) == rows_per_img * out.stride(1)
     out_ptr = ctypes.c_void_p(out.data_ptr() + 2 * col_off)
+    prof = PE_PROFILE
     with torch.cuda.device(img.device):
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         rc = lib.sfc_patch_embed_fwd(_ptr(img), 1 if img.dtype == torch.bfloat16 else 0, B, C, H, W, p, g, _ptr(perm),
                                      perm.numel(), _ptr(wk), _ptr(bias), _ptr(pos), pos.stride(0) if pos is not None else 0, out_ptr,
                                      out.stride(1), D, rows_per_img, tok_off, _stream())
+        if prof is not None:
+            e1.record()
+            prof.append((e0, e1, img.numel() * img.element_size() + B * ntok * D * 2, 2.0 * B * ntok * (g * p * p * C) * D))
     _lib.check(rc, "sfc_patch_embed_fwd")
     _count(1)
     return out
