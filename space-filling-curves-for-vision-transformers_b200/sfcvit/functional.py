@@ -310,3 +310,61 @@ def encoder_layer(x, layer, heads, eps, drops, seed):
                                 layer.linear1.weight, layer.linear1.bias, layer.linear2.weight, layer.linear2.bias,
                                 layer.norm1.weight, layer.norm1.bias, layer.norm2.weight, layer.norm2.bias,
                                 int(heads), float(eps), tuple(float(d) for d in drops), int(seed))
+
+
+class AttentionFn(Function):
+    """softmax(Q K^T * scale) V on the packed projection qkv [B, N, 3 * H * 64] (K4); no probability tensor is kept."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads, scale, drop_p, seed):
+        B, N, D3 = qkv.shape
+        q2 = _bf16_act(qkv).reshape(B * N, D3)
+        if not q2.is_contiguous():
+            q2 = q2.contiguous()
+        out, lse = ops.attn_fwd(q2, B, heads, N, scale=scale, drop_p=drop_p, drop_seed=seed)
+        ctx.save_for_backward(q2, out, lse)
+        ctx.cfg = (B, N, heads, scale, drop_p, seed)
+        return out.reshape(B, N, D3 // 3)
+
+    @staticmethod
+    def backward(ctx, dout):
+        q2, out, lse = ctx.saved_tensors
+        B, N, heads, scale, drop_p, seed = ctx.cfg
+        d2 = _bf16_act(dout).reshape(out.shape)
+        if not d2.is_contiguous():
+            d2 = d2.contiguous()
+        dqkv = ops.attn_bwd(q2, out, d2, lse, B, heads, N, scale=scale, drop_p=drop_p, drop_seed=seed)
+        return dqkv.reshape(B, N, -1), None, None, None, None
+
+
+def attention(qkv, heads, scale=None, drop_p=0.0, seed=0):
+    if scale is None:
+        scale = (qkv.shape[-1] // 3 // heads) ** -0.5
+    return AttentionFn.apply(qkv, int(heads), float(scale), float(drop_p), int(seed))
+
+
+class PatchRowsFn(Function):
+    """Curve-ordered patch vectors [B, n_tokens, g*p*p*C] (bf16, feature order (q, c, p1, p2)) gathered straight from the
+    NCHW image by sfc_patch_gather — for tokenizers that normalise the patch vector BEFORE projecting it
+    (altvit.py:92-99), where the gather cannot be fused into the projection GEMM. No gradient w.r.t. the image."""
+
+    @staticmethod
+    def forward(ctx, img, perm32, p, g):
+        if not img.is_cuda:
+            raise RuntimeError("sfcvit: CUDA tensors only (the B200 path has no CPU fallback)")
+        if img.dtype not in (torch.float32, torch.bfloat16):
+            img = img.float()
+        img = img.contiguous()
+        B, C = img.shape[0], img.shape[1]
+        K = g * p * p * C
+        A = ops.patch_gather(img, perm32, p, g)
+        ntok = perm32.numel() // g
+        return A[:, :K].reshape(B, ntok, K) if A.shape[1] != K else A.reshape(B, ntok, K)
+
+    @staticmethod
+    def backward(ctx, dout):
+        return None, None, None, None
+
+
+def patch_rows(img, perm32, p, g=1):
+    return PatchRowsFn.apply(img, perm32, int(p), int(g))

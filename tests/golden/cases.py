@@ -35,6 +35,13 @@ TOKENIZER_CASES["conv_hilbert_32_p4_d192"] = ("conv", dict(hilbert=True, img_siz
 # 14 x 14 grid: the "generalised Hilbert" of the north star; single-level hierarchical wrapper supplies n_patches
 TOKENIZER_CASES["sfc_hilbert_56_p4_d128"] = ("hier", dict(curve="hilbert", img_size=56, C=3, groups=[1], D=128, pre0=4), (3, 3, 56, 56))
 
+# reference src/models/altvit.py (pre-norm GELU ViT): name -> (class, kwargs, batch)
+ALTVIT_CASES = {
+    "hilbertvit_32_p4": ("HilbertViT", dict(image_size=32, patch_size=4, num_classes=10, dim=128, depth=2, heads=2, mlp_dim=256), 4),
+    "simplevit_28_p4": ("SimpleViT", dict(image_size=28, patch_size=4, num_classes=7, dim=64, depth=1, heads=1, mlp_dim=128), 3),
+    "hilbertvit_64_p8_tiny": ("HilbertViT", dict(image_size=64, patch_size=8, num_classes=10, dim=192, depth=1, heads=3, mlp_dim=384), 2),
+}
+
 INIT_SEED = 42      # main.py:151
 DATA_SEED = 7
 

@@ -22,6 +22,7 @@ import cases  # noqa: E402
 import ref_import  # noqa: E402
 from oracle import curves as oc  # noqa: E402
 from oracle import model as om  # noqa: E402
+from oracle import altvit as oa  # noqa: E402
 
 
 def h16(a):
@@ -107,6 +108,35 @@ def main():
         meta[name] = {"loss": res["ref"][1], "grads": res["ref"][2],
                       "state_abs_sum": {k: float(v.double().abs().sum()) for k, v in sd_r.items() if v.dtype.is_floating_point}}
         print("model", name, "loss", res["ref"][1], "params with grad", len(res["ref"][2]))
+    # ---------------- altvit (pre-norm GELU ViT, src/models/altvit.py)
+    for name, (cls, kw, batch) in cases.ALTVIT_CASES.items():
+        torch.manual_seed(cases.INIT_SEED)
+        rm = getattr(ref["altvit"], cls)(**kw)
+        torch.manual_seed(cases.INIT_SEED)
+        omod = getattr(oa, cls)(**kw)
+        sd_r, sd_o = rm.state_dict(), omod.state_dict()
+        assert list(sd_r) == list(sd_o), (name, set(sd_r) ^ set(sd_o))
+        for k in sd_r:
+            assert torch.equal(sd_r[k], sd_o[k]), (name, k)
+        if cls == "HilbertViT":
+            assert torch.equal(rm.to_patch_embedding.hilbert_indices, omod.to_patch_embedding.hilbert_indices), name
+        x = cases.make_input((batch, 3, kw["image_size"], kw["image_size"]))
+        tgt = cases.make_soft_targets(batch, kw["num_classes"])
+        res = {}
+        for tag, mdl in (("ref", rm), ("oracle", omod)):
+            mdl.train()
+            mdl.zero_grad()
+            logits = mdl(x)
+            loss = om.soft_target_cross_entropy(logits, tgt)
+            loss.backward()
+            res[tag] = (logits.detach(), float(loss), cases.grad_summary(mdl))
+        assert torch.equal(res["ref"][0], res["oracle"][0]), name
+        assert res["ref"][1] == res["oracle"][1], name
+        assert res["ref"][2] == res["oracle"][2], name
+        arrays["altvit/" + name + "/logits"] = res["ref"][0].numpy()
+        meta["altvit/" + name] = {"loss": res["ref"][1], "grads": res["ref"][2],
+                                  "state_abs_sum": {k: float(v.double().abs().sum()) for k, v in sd_r.items() if v.dtype.is_floating_point}}
+        print("altvit", name, "loss", res["ref"][1], "params with grad", len(res["ref"][2]))
     np.savez_compressed(os.path.join(HERE, "models.npz"), **arrays)
     json.dump(meta, open(os.path.join(HERE, "models.json"), "w"), indent=1, sort_keys=True)
     print("done")

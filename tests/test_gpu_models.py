@@ -84,3 +84,40 @@ def test_training_mode_dropout_runs_and_is_seeded(cuda_device):
     a.float().square().mean().backward()
     for n, p in m.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
+
+
+@pytest.mark.parametrize("name", sorted(cases.ALTVIT_CASES))
+def test_altvit_forward_backward_parity(cuda_device, name):
+    """src.models.altvit (pre-norm GELU ViT on the libsfcvit kernels) vs the fp32 CPU oracle, same seed and inputs."""
+    from oracle import altvit as oa
+    from src.models import altvit as sa
+    cls, kw, batch = cases.ALTVIT_CASES[name]
+    torch.manual_seed(cases.INIT_SEED)
+    o = getattr(oa, cls)(**kw)
+    torch.manual_seed(cases.INIT_SEED)
+    s = getattr(sa, cls)(**kw)
+    sd_o, sd_s = o.state_dict(), s.state_dict()
+    assert list(sd_o) == list(sd_s)
+    for k in sd_o:
+        assert torch.equal(sd_o[k], sd_s[k]), k
+    if cls == "HilbertViT":
+        assert torch.equal(o.to_patch_embedding.hilbert_indices, s.to_patch_embedding.hilbert_indices)   # curve kernel: bit-exact
+    s = s.to(cuda_device)
+    o.train(); s.train()
+    x = cases.make_input((batch, 3, kw["image_size"], kw["image_size"]))
+    tgt = cases.make_soft_targets(batch, kw["num_classes"])
+    lo = o(x)
+    om.soft_target_cross_entropy(lo, tgt).backward()
+    ls = s(x.to(cuda_device))
+    assert ls.dtype == torch.float32 and tuple(ls.shape) == tuple(lo.shape)
+    om.soft_target_cross_entropy(ls.float(), tgt.to(cuda_device)).backward()
+    assert cases.rel_l2(ls, lo) < 2e-2
+    po, ps = dict(o.named_parameters()), dict(s.named_parameters())
+    dot = no = ns = 0.0
+    for n, p in po.items():
+        g = ps[n].grad
+        assert g is not None and g.dtype == ps[n].dtype, n
+        assert cases.rel_l2(g, p.grad) < 1e-1, (n, cases.rel_l2(g, p.grad))
+        gd, pd = g.detach().double().cpu().flatten(), p.grad.double().flatten()
+        dot += float(gd @ pd); no += float(pd @ pd); ns += float(gd @ gd)
+    assert dot / (no ** 0.5 * ns ** 0.5) > 0.999

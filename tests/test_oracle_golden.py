@@ -88,3 +88,27 @@ def test_model_fixture(name):
     assert set(gs) == set(meta["grads"])
     for k, (norm, _s, _f) in meta["grads"].items():
         assert abs(gs[k][0] - norm) <= 1e-4 * max(norm, 1e-6), k
+
+
+@pytest.mark.parametrize("name", sorted(cases.ALTVIT_CASES))
+def test_altvit_fixture(name):
+    """oracle/altvit.py vs logits / loss / gradient norms recorded from the live reference's src/models/altvit.py."""
+    from oracle import altvit as oa
+    cls, kw, batch = cases.ALTVIT_CASES[name]
+    meta = json.load(open(os.path.join(GOLD, "models.json")))["altvit/" + name]
+    gold_logits = np.load(os.path.join(GOLD, "models.npz"))["altvit/" + name + "/logits"]
+    torch.manual_seed(cases.INIT_SEED)
+    m = getattr(oa, cls)(**kw)
+    for k, v in m.state_dict().items():
+        if v.dtype.is_floating_point:
+            assert abs(float(v.double().abs().sum()) - meta["state_abs_sum"][k]) <= 1e-9 * max(1.0, meta["state_abs_sum"][k]), k
+    m.train()
+    logits = m(cases.make_input((batch, 3, kw["image_size"], kw["image_size"])))
+    loss = om.soft_target_cross_entropy(logits, cases.make_soft_targets(batch, kw["num_classes"]))
+    loss.backward()
+    assert cases.rel_l2(logits, torch.from_numpy(gold_logits)) < 1e-5
+    assert abs(float(loss.detach()) - meta["loss"]) < 1e-5
+    gs = cases.grad_summary(m)
+    assert set(gs) == set(meta["grads"])
+    for k, (norm, _s, _f) in meta["grads"].items():
+        assert abs(gs[k][0] - norm) <= 1e-4 * max(norm, 1e-6), k
