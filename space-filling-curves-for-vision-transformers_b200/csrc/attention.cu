@@ -40,7 +40,9 @@ struct AttnParams {
   const __nv_bfloat16* o;  // [B*N, D]
   const __nv_bfloat16* dout;  // [B*N, D]
   __nv_bfloat16* dqkv;     // [B*N, 3D]
-  float* dq_acc;           // [B*N, D] fp32, zero-initialised
+  float* dq_acc;           // [B*N, D] fp32, zero-initialised (more than two key tiles: red.global.add)
+  __nv_bfloat16* dq_part;  // one or two key tiles: bf16 [B*N, D] partial of key tile 0 when there are two (no atomics)
+  int dq_mode;             // 0 = atomics into dq_acc, 1 = single key tile -> dqkv directly, 2 = tile 0 -> dq_part, tile 1 -> dqkv
   float* delta;            // [B, H, N] fp32 rowsum(dO * O)
   long long* dbg;          // optional timeline buffer (sfc_debug_set_timeline), CTA 0 only
 };
@@ -688,10 +690,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         ptx::tmem_ld_wait();
         const int qi = qt * BQ + r;
         if (qi < p.N) {
-          float* dst = p.dq_acc + (long long)(row0 + qi) * p.D + h * DH + ch * 16;
+          if (p.dq_mode == 0) {
+            float* dst = p.dq_acc + (long long)(row0 + qi) * p.D + h * DH + ch * 16;
 #pragma unroll
-          for (int e = 0; e < 16; e += 4)
-            red_add_v4(dst + e, __uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3]));
+            for (int e = 0; e < 16; e += 4)
+              red_add_v4(dst + e, __uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3]));
+          } else {
+            // one or two key tiles per head: every dQ element has at most two contributions, each written exactly once as
+            // bf16 (tile 0 of two -> scratch, otherwise -> dqkv); dq_add_kernel sums them. No memset, no atomics.
+            __nv_bfloat16* dst = (p.dq_mode == 2 && jt == 0) ? p.dq_part + (long long)(row0 + qi) * p.D + h * DH + ch * 16
+                                                              : p.dqkv + (long long)(row0 + qi) * (3 * p.D) + h * DH + ch * 16;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              uint4 o;
+              o.x = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 0]), __uint_as_float(rr[q * 8 + 1]));
+              o.y = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 2]), __uint_as_float(rr[q * 8 + 3]));
+              o.z = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 4]), __uint_as_float(rr[q * 8 + 5]));
+              o.w = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 6]), __uint_as_float(rr[q * 8 + 7]));
+              reinterpret_cast<uint4*>(dst)[q] = o;
+            }
+          }
         }
       }
       if (qt == nq - 1) {
@@ -840,6 +858,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
+// dqkv[:, 0:D] += dq_part   (two key tiles per head: the second tile's partial is already in dqkv)
+__global__ void dq_add_kernel(const __nv_bfloat16* __restrict__ part, __nv_bfloat16* __restrict__ dqkv, long long rows, int D) {
+  const long long total = rows * (D / 8);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / (D / 8);
+    const int c = (int)(i % (D / 8)) * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(part + m * D + c);
+    uint4* dst = reinterpret_cast<uint4*>(dqkv + m * (3ll * D) + c);
+    const uint4 b = *dst;
+    uint4 o;
+    o.x = ptx::pack_bf16(ptx::bf16_lo(a.x) + ptx::bf16_lo(b.x), ptx::bf16_hi(a.x) + ptx::bf16_hi(b.x));
+    o.y = ptx::pack_bf16(ptx::bf16_lo(a.y) + ptx::bf16_lo(b.y), ptx::bf16_hi(a.y) + ptx::bf16_hi(b.y));
+    o.z = ptx::pack_bf16(ptx::bf16_lo(a.z) + ptx::bf16_lo(b.z), ptx::bf16_hi(a.z) + ptx::bf16_hi(b.z));
+    o.w = ptx::pack_bf16(ptx::bf16_lo(a.w) + ptx::bf16_lo(b.w), ptx::bf16_hi(a.w) + ptx::bf16_hi(b.w));
+    *dst = o;
+  }
+}
+
 // dqkv[:, 0:D] = bf16(dq_acc)
 __global__ void dq_finalize_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqkv, long long rows, int D) {
   const long long total = rows * (D / 8);
@@ -896,7 +932,8 @@ extern "C" size_t sfc_attn_bwd_scratch_bytes(int B, int N, int D) {
   return (size_t)B * N * D * sizeof(float) + (size_t)B * (D / DH) * N * sizeof(float);
 }
 
-// scratch = fp32 dQ accumulator [B*N, D] (zeroed here with cudaMemsetAsync on the caller's stream) + delta [B, H, N].
+// scratch = dQ workspace [B*N, D] (fp32 accumulator for > 2 key tiles, bf16 partial of tile 0 for 2, unused for 1) +
+// delta [B, H, N].
 extern "C" int sfc_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* scratch,
                             size_t scratch_bytes, int B, int H, int N, int D, float scale, float drop_p,
                             unsigned long long drop_seed, cudaStream_t stream) {
@@ -906,7 +943,11 @@ extern "C" int sfc_attn_bwd(const void* qkv, const void* out, const void* dout, 
   const size_t dq_bytes = (size_t)B * N * D * sizeof(float);
   const size_t need = sfc_attn_bwd_scratch_bytes(B, N, D);
   SFC_REQUIRE(scratch && scratch_bytes >= need, "sfc_attn_bwd: scratch too small (%zu < %zu)", scratch_bytes, need);
-  SFC_CUDA_OK(cudaMemsetAsync(scratch, 0, dq_bytes, stream));
+  // key tiles: equal sizes, multiple of 16, at most 128 (the M dimension of the dV / dK MMAs)
+  const int n_kvt = (N + 127) / 128;
+  const int bkv = ((N + n_kvt - 1) / n_kvt + 15) / 16 * 16;
+  const int dq_mode = n_kvt == 1 ? 1 : (n_kvt == 2 ? 2 : 0);
+  if (dq_mode == 0) SFC_CUDA_OK(cudaMemsetAsync(scratch, 0, dq_bytes, stream));
   const long long rows = (long long)B * N;
   float* delta = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + dq_bytes);
   {
@@ -916,9 +957,6 @@ extern "C" int sfc_attn_bwd(const void* qkv, const void* out, const void* dout, 
     attn_bwd_prep_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, rows, N, H);
     SFC_LAUNCH_OK();
   }
-  // key tiles: equal sizes, multiple of 16, at most 128 (the M dimension of the dV / dK MMAs)
-  const int n_kvt = (N + 127) / 128;
-  const int bkv = ((N + n_kvt - 1) / n_kvt + 15) / 16 * 16;
   CUtensorMap tq, tkv, tdo;
   if (int e = sfc_make_tmap_2d(&tq, qkv, 2, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D * 2, DH, BQ, true)) return e;
   if (int e = sfc_make_tmap_2d(&tkv, qkv, 2, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D * 2, DH, (uint32_t)bkv, true)) return e;
@@ -926,7 +964,8 @@ extern "C" int sfc_attn_bwd(const void* qkv, const void* out, const void* dout, 
   AttnParams p{};
   p.B = B; p.H = H; p.N = N; p.D = D; p.scale = scale; p.drop_p = drop_p; p.drop_seed = drop_seed; p.drop_epoch = sfc_dropout_epoch_ptr();
   p.lse = const_cast<float*>(lse); p.o = (const __nv_bfloat16*)out; p.dout = (const __nv_bfloat16*)dout;
-  p.dqkv = (__nv_bfloat16*)dqkv; p.dq_acc = (float*)scratch; p.delta = delta; p.dbg = g_attn_dbg;
+  p.dqkv = (__nv_bfloat16*)dqkv; p.dq_acc = (float*)scratch; p.dq_part = (__nv_bfloat16*)scratch; p.dq_mode = dq_mode;
+  p.delta = delta; p.dbg = g_attn_dbg;
   static bool configured = false;
   if (!configured) {
     SFC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal));
@@ -936,10 +975,13 @@ extern "C" int sfc_attn_bwd(const void* qkv, const void* out, const void* dout, 
   const int grid = (int)(items < sfc_num_sms() ? items : sfc_num_sms());
   attn_bwd_kernel<<<grid, kBwdThreads, BwdSmem::kTotal, stream>>>(tq, tkv, tdo, p, bkv);
   SFC_LAUNCH_OK();
-  long long blocks = sfc_ceil_div64(rows * (D / 8), 256);
-  const long long cap = 16ll * sfc_num_sms();
-  if (blocks > cap) blocks = cap;
-  dq_finalize_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const float*)scratch, (__nv_bfloat16*)dqkv, rows, D);
+  if (dq_mode != 1) {
+    long long blocks = sfc_ceil_div64(rows * (D / 8), 256);
+    const long long cap = 16ll * sfc_num_sms();
+    if (blocks > cap) blocks = cap;
+    if (dq_mode == 0) dq_finalize_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const float*)scratch, (__nv_bfloat16*)dqkv, rows, D);
+    else dq_add_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)scratch, (__nv_bfloat16*)dqkv, rows, D);
+  }
   SFC_LAUNCH_OK();
   return 0;
 }
