@@ -894,18 +894,30 @@ __global__ void dq_finalize_kernel(const float* __restrict__ dq_acc, __nv_bfloat
 long long* g_attn_dbg = nullptr;
 
 int check_shape(int B, int H, int N, int D) {
-  SFC_REQUIRE(B > 0 && H > 0 && N > 0 && D == H * DH, "attention: only head_dim = 64 is supported (D=%d, heads=%d)", D, H);
+  SFC_REQUIRE(B > 0 && H > 0 && N > 0 && D > 0 && D % H == 0, "attention: bad shape (D=%d, heads=%d)", D, H);
   SFC_REQUIRE((long long)B * N < (1ll << 31), "attention: too many rows");
   return 0;
 }
 
 }  // namespace
 
+// attention_generic.cu: CUDA-core path for head dimensions other than 64 (small sequences)
+int sfc_attn_generic_supported(int N, int dh, bool bwd);
+int sfc_attn_generic_fwd(const void* qkv, void* out, float* lse, int B, int H, int N, int D, float scale, float drop_p,
+                         unsigned long long drop_seed, cudaStream_t stream);
+int sfc_attn_generic_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int H, int N,
+                         int D, float scale, float drop_p, unsigned long long drop_seed, cudaStream_t stream);
+
 extern "C" int sfc_attn_fwd(const void* qkv, void* out, float* lse, int B, int H, int N, int D, float scale, float drop_p,
                             unsigned long long drop_seed, cudaStream_t stream) {
   if (int e = check_shape(B, H, N, D)) return e;
   SFC_REQUIRE(qkv && out, "sfc_attn_fwd: null pointer");
   SFC_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "sfc_attn_fwd: dropout p out of range");
+  if (D / H != DH) {
+    SFC_REQUIRE(sfc_attn_generic_supported(N, D / H, false),
+                "sfc_attn_fwd: head_dim %d is served by the generic path only for N <= 128 within shared memory (N=%d)", D / H, N);
+    return sfc_attn_generic_fwd(qkv, out, lse, B, H, N, D, scale, drop_p, drop_seed, stream);
+  }
   const FwdLayout L = fwd_layout(N);
   SFC_REQUIRE(L.total <= 232448, "sfc_attn_fwd: shared-memory plan of %d bytes exceeds 227 KB (N=%d)", L.total, N);
   CUtensorMap tq, tkv;
@@ -929,7 +941,7 @@ extern "C" int sfc_attn_fwd(const void* qkv, void* out, float* lse, int B, int H
 }
 
 extern "C" size_t sfc_attn_bwd_scratch_bytes(int B, int N, int D) {
-  return (size_t)B * N * D * sizeof(float) + (size_t)B * (D / DH) * N * sizeof(float);
+  return (size_t)B * N * D * sizeof(float) + (size_t)B * ((D + DH - 1) / DH) * N * sizeof(float);
 }
 
 // scratch = dQ workspace [B*N, D] (fp32 accumulator for > 2 key tiles, bf16 partial of tile 0 for 2, unused for 1) +
@@ -940,6 +952,11 @@ extern "C" int sfc_attn_bwd(const void* qkv, const void* out, const void* dout, 
   if (int e = check_shape(B, H, N, D)) return e;
   SFC_REQUIRE(qkv && out && dout && lse && dqkv, "sfc_attn_bwd: null pointer");
   SFC_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "sfc_attn_bwd: dropout p out of range");
+  if (D / H != DH) {
+    SFC_REQUIRE(sfc_attn_generic_supported(N, D / H, true),
+                "sfc_attn_bwd: head_dim %d is served by the generic path only for N <= 128 within shared memory (N=%d)", D / H, N);
+    return sfc_attn_generic_bwd(qkv, out, dout, lse, dqkv, B, H, N, D, scale, drop_p, drop_seed, stream);
+  }
   const size_t dq_bytes = (size_t)B * N * D * sizeof(float);
   const size_t need = sfc_attn_bwd_scratch_bytes(B, N, D);
   SFC_REQUIRE(scratch && scratch_bytes >= need, "sfc_attn_bwd: scratch too small (%zu < %zu)", scratch_bytes, need);

@@ -50,3 +50,37 @@ def test_fused_clip_adamw_matches_torch(cuda_device):
     import kernel_selftest as ks
     r = ks.check_adamw()
     assert r["ok"], r
+
+
+@pytest.mark.parametrize("B,H,N,dh,drop", [(2, 4, 64, 192, 0.0), (3, 2, 50, 32, 0.0), (1, 3, 128, 96, 0.0), (2, 4, 64, 192, 0.1)])
+def test_attention_generic_head_dim(cuda_device, B, H, N, dh, drop):
+    """head_dim != 64 (main.py builds 768 / 4 heads = 192 on 64 tokens): CUDA-core path of attention_generic.cu."""
+    import torch
+    from sfcvit import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    D = H * dh
+    qkv = torch.randn(B * N, 3 * D, generator=g, device="cuda").bfloat16()
+    out, lse = ops.attn_fwd(qkv, B, H, N, drop_p=drop, drop_seed=11)
+    q, k, v = [t.reshape(B, N, H, dh).permute(0, 2, 1, 3).float().requires_grad_(True) for t in qkv.float().split(D, dim=1)]
+    s = (q @ k.transpose(-1, -2)) * dh ** -0.5
+    assert (lse - torch.logsumexp(s, dim=-1)).abs().max() < 2e-3
+    dout = torch.randn(B * N, D, generator=g, device="cuda").bfloat16()
+    dqkv = ops.attn_bwd(qkv, out, dout, lse, B, H, N, drop_p=drop, drop_seed=11)
+    if drop == 0.0:
+        ref = (torch.softmax(s, dim=-1) @ v).permute(0, 2, 1, 3).reshape(B * N, D)
+        rel = lambda a, b: float((a.float() - b).norm() / b.norm())
+        assert rel(out, ref) < 1e-2
+        ref.backward(dout.float())
+        ref_d = torch.cat([t.grad.permute(0, 2, 1, 3).reshape(B * N, D) for t in (q, k, v)], dim=1)
+        for i, name in enumerate("qkv"):
+            assert rel(dqkv[:, i * D:(i + 1) * D], ref_d[:, i * D:(i + 1) * D]) < 2e-2, name
+    else:
+        out2, _ = ops.attn_fwd(qkv, B, H, N, drop_p=drop, drop_seed=11)
+        assert torch.equal(out, out2)
+        # adjoint check along V: out is linear in V for a fixed mask, so <out(V'), dout> == <dV, V'>
+        vdir = torch.randn(B * N, D, generator=g, device="cuda").bfloat16()
+        qkv2 = qkv.clone(); qkv2[:, 2 * D:] = vdir
+        out_dir, _ = ops.attn_fwd(qkv2, B, H, N, drop_p=drop, drop_seed=11)
+        lhs = float((out_dir.float() * dout.float()).sum()); rhs = float((dqkv[:, 2 * D:].float() * vdir.float()).sum())
+        assert abs(lhs - rhs) / max(abs(lhs), 1e-6) < 3e-2
+        assert torch.isfinite(dqkv.float()).all()

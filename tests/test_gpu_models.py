@@ -121,3 +121,36 @@ def test_altvit_forward_backward_parity(cuda_device, name):
         gd, pd = g.detach().double().cpu().flatten(), p.grad.double().flatten()
         dot += float(gd @ pd); no += float(pd @ pd); ns += float(gd @ gd)
     assert dot / (no ** 0.5 * ns ** 0.5) > 0.999
+
+
+def test_main_py_configuration_trains(cuda_device):
+    """The model the reference driver actually builds (main.py:269-282): HierarchicalMortonEmbedding(32, 3, [16, 4, 1], 256)
+    -> VisionTransformer1D(depth 8, 4 heads -> head_dim 192, mlp 512, 10 classes), default dtype bf16 (main.py:157),
+    one mixup/cutmix training step through src.training with torch's own AdamW, then an evaluation pass."""
+    from src.models.vit import VisionTransformer1D
+    from src.tokenizers.multiscale.multi_morton import HierarchicalMortonEmbedding
+    from src.training.train import evaluate, train_with_mixup_or_cutmix
+    from src.training.losses import SoftTargetCrossEntropy
+    torch.manual_seed(42)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        pe = HierarchicalMortonEmbedding(img_size=32, in_channels=3, patch_size_list=[16, 4, 1], embed_dim=256)
+        model = VisionTransformer1D(patch_embed=pe, depth=8, n_heads=4, mlp_dim=512, num_classes=10).to(cuda_device)
+    finally:
+        torch.set_default_dtype(prev)
+    model = torch.compile(model, mode="reduce-overhead")             # main.py:284 (the forward runs the kernels eagerly)
+    opt = torch.optim.AdamW(model.parameters(), lr=3e-4, weight_decay=0.00005)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0)
+    g = torch.Generator().manual_seed(0)
+    data = [(torch.randn(16, 3, 32, 32, generator=g), torch.randint(0, 10, (16,), generator=g)) for _ in range(2)]
+
+    class _Loader(list):
+        dataset = list(range(32))
+
+    loss, acc = train_with_mixup_or_cutmix(model, _Loader(data), SoftTargetCrossEntropy(), opt, sched, cuda_device)
+    assert loss == loss and 0.5 < loss < 10.0 and 0.0 <= acc <= 1.0
+    tl, ta = evaluate(model, _Loader(data), torch.nn.CrossEntropyLoss(), cuda_device)
+    assert tl == tl and 0.0 <= ta <= 1.0
+    sd = model.state_dict()
+    assert any(k.startswith("_orig_mod.encoder.transformer.layers.7.self_attn.in_proj_weight") for k in sd)
