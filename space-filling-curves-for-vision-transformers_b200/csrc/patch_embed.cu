@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
 #include "sfcvit.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -329,6 +330,295 @@ patch_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchPa
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// TMEM-resident variant (K <= 768, vectorised gather): the gathered, converted patch rows of a 128-token tile are written
+// ONCE into tensor memory (tcgen05.st: token = TMEM lane, two bf16 per column, K / 2 <= 384 columns) and serve as the A
+// operand of every n-pass (tcgen05.mma with A from TMEM) — the image is gathered exactly once per token instead of once
+// per 256-column n-tile, and no shared memory is spent on A. D = 2 x 64 columns (one accumulator per MMA issuer), the
+// weights (B) stream through a 12-stage TMA ring of [64 features x 128 k] tiles (two 8 KB SWIZZLE_128B slabs).
+//   warp 0 : TMA (weights)   warps 1, 3 : MMA issuers (even / odd passes)   warp 2 : TMEM allocator   warps 4-7 : epilogue
+//   warps 8-15 : gather producers, warp w owns TMEM lane quarter w % 4; the two warps of a quarter alternate k-blocks
+// A 128 x 64 x 16 MMA keeps the tensor pipe busy for 32 clocks, far less than one thread needs to wait for a stage and
+// issue it, hence eight MMAs per barrier round trip and two issuers, each owning one accumulator and every other pass.
+// The epilogue releases its accumulator as soon as tcgen05.ld has landed in registers, before converting and storing.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kTmBN = 64;            // output columns per pass
+constexpr int kTmStages = 12;        // two passes of K = 768 in flight: one per MMA issuer
+constexpr int kTmMaxKb = 12;         // K <= 768
+constexpr int kTmDCol = 384;         // accumulators live in TMEM columns [384, 512)
+constexpr int kTmMaxD = 2048;        // bias is staged once as fp32
+
+struct PeTmSmem {
+  static constexpr int kSlabBytes = kTmBN * BK * 2;                    // 8 KB: 64 features x 64 k
+  static constexpr int kStageBytes = 2 * kSlabBytes;                   // two consecutive k-blocks
+  static constexpr int kBiasOffset = kTmStages * kStageBytes;
+  static constexpr int kBarOffset = kBiasOffset + kTmMaxD * 4;
+  static constexpr int kNumBars = 2 * kTmStages + 2 * kTmMaxKb + 4;    // b_full/empty, a_full/empty per k-block, d_full/empty[2]
+  static constexpr int kTblOffset = kBarOffset + kNumBars * 8 + 16;
+  static constexpr int kTotal = kTblOffset + kMaxTblKb * 9 * 4 + 1024;
+  static_assert(kTotal <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
+};
+
+template <bool BF16IN, int CL>
+__global__ void __launch_bounds__(kThreads, 1)
+patch_embed_tmem_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchParams pp) {
+  using L = PeTmSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* bias_s = reinterpret_cast<float*>(smem + L::kBiasOffset);
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* b_empty = b_full + kTmStages;
+  uint64_t* a_full = b_empty + kTmStages;      // [kTmMaxKb]
+  uint64_t* a_empty = a_full + kTmMaxKb;       // [kTmMaxKb]
+  uint64_t* d_full = a_empty + kTmMaxKb;       // [2]
+  uint64_t* d_empty = d_full + 2;              // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d_empty + 2);
+  int* tbl = reinterpret_cast<int*>(smem + L::kTblOffset);
+  int* tblq = tbl + kMaxTblKb * 8;
+
+  const int warp = threadIdx.x >> 5;
+  const int nkb = pp.num_k_blocks;
+  const int nst = (nkb + 1) >> 1;              // ring stages per pass (the last one holds a single k-block when nkb is odd)
+  const int npass = pp.num_n_tiles;            // D / 64, even
+  // every CTA of a cluster walks the same number of tiles: the weight stream is shared (multicast) and runs in lock step;
+  // a CTA whose tile index is past the end gathers zeros and stores nothing
+  const int rounds = (pp.num_m_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t crank = CL > 1 ? ptx::cluster_ctarank() : 0;
+  constexpr uint16_t kMcMask = (uint16_t)((1u << CL) - 1);
+  build_chunk_table(pp, tbl, tblq);
+  for (int i = threadIdx.x; i < pp.epi.N; i += kThreads) bias_s[i] = pp.epi.bias ? __bfloat162float(pp.epi.bias[i]) : 0.0f;
+  if (warp == 0 && ptx::elect_one()) ptx::prefetch_tmap(&tmap_w);
+  if (warp == 1 && ptx::elect_one()) {
+    for (int s = 0; s < kTmStages; ++s) { ptx::mbar_init(&b_full[s], 1); ptx::mbar_init(&b_empty[s], CL); }
+    for (int k = 0; k < kTmMaxKb; ++k) { ptx::mbar_init(&a_full[k], 4); ptx::mbar_init(&a_empty[k], 2); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&d_full[s], 1); ptx::mbar_init(&d_empty[s], kEpiThreads); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<512>(tmem_ptr);
+  ptx::tc_fence_before();
+  __syncthreads();
+  if constexpr (CL > 1) ptx::cluster_sync();   // peers' barriers are initialised before any multicast lands on them
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer: weight slabs [64 features x 64 k], each CTA multicasts its 64 / CL rows =====================
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int r = 0; r < rounds; ++r) {
+        for (int n = 0; n < npass; ++n) {
+          for (int st = 0; st < nst; ++st) {
+            const int nslab = (2 * st + 1 < nkb) ? 2 : 1;
+            ptx::mbar_wait_sleep(&b_empty[stage], phase ^ 1, 32);      // every CTA of the cluster has consumed this stage
+            ptx::mbar_expect_tx(&b_full[stage], nslab * L::kSlabBytes);
+            for (int h = 0; h < nslab; ++h) {
+              uint8_t* dst = smem + stage * L::kStageBytes + h * L::kSlabBytes;
+              if constexpr (CL > 1)
+                ptx::tma_load_2d_mc(&tmap_w, &b_full[stage], dst + crank * (L::kSlabBytes / CL), (2 * st + h) * BK,
+                                    n * kTmBN + (int)crank * (kTmBN / CL), kMcMask);
+              else
+                ptx::tma_load_2d(&tmap_w, &b_full[stage], dst, (2 * st + h) * BK, n * kTmBN);
+            }
+            if (++stage == kTmStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1 || warp == 3) {
+    // ===================== MMA issuers (A from TMEM): issuer i runs passes n = i, i + 2, ... into accumulator i =====================
+    if (ptx::elect_one()) {
+      const int iss = warp >> 1;
+      const uint32_t idesc = umma_idesc_bf16(BM, kTmBN, false, false);
+      const uint32_t tmem_d = tmem_base + kTmDCol + iss * kTmBN;
+      int stage = iss * nst;                     // ring slots are handed out pass-major, so the issuers leapfrog by nst
+      uint32_t phase = 0;
+      if (stage >= kTmStages) { stage -= kTmStages; phase ^= 1; }
+      int j = 0;                                 // passes issued by this thread
+      for (int it = 0; it < rounds; ++it) {
+        for (int n = iss; n < npass; n += 2, ++j) {
+          ptx::mbar_wait(&d_empty[iss], (j & 1) ^ 1);
+          ptx::tc_fence_after();
+          for (int st = 0; st < nst; ++st) {
+            const int nslab = (2 * st + 1 < nkb) ? 2 : 1;
+            if (n == iss) {                                               // this tile's rows of the k-blocks are in TMEM
+              ptx::mbar_wait(&a_full[2 * st], it & 1);
+              if (nslab == 2) ptx::mbar_wait(&a_full[2 * st + 1], it & 1);
+            }
+            ptx::mbar_wait(&b_full[stage], phase);
+            ptx::tc_fence_after();
+            const uint64_t db = umma_smem_desc_sw128(ptx::smem_u32(smem + stage * L::kStageBytes), 0, 1024);
+            const uint32_t ta = tmem_base + st * 64;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ptx::umma_f16_ts(tmem_d, ta + k * 8, db + (uint64_t)(k * 2), idesc, (st > 0 || k > 0) ? 1u : 0u);
+            if (nslab == 2) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) ptx::umma_f16_ts(tmem_d, ta + 32 + k * 8, db + (uint64_t)(L::kSlabBytes / 16 + k * 2), idesc, 1u);
+            }
+            if constexpr (CL > 1) ptx::umma_commit_mc(&b_empty[stage], kMcMask);
+            else ptx::umma_commit(&b_empty[stage]);
+            if (n >= npass - 2) {                                         // this issuer's last read of the tile's k-blocks
+              ptx::umma_commit(&a_empty[2 * st]);
+              if (nslab == 2) ptx::umma_commit(&a_empty[2 * st + 1]);
+            }
+            if (++stage == kTmStages) { stage = 0; phase ^= 1; }
+          }
+          ptx::umma_commit(&d_full[iss]);
+          stage += nst;                          // the other issuer's pass
+          if (stage >= kTmStages) { stage -= kTmStages; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== epilogue: lane = token row, 64 columns per pass =====================
+    const int ewarp = warp - 4;
+    const int lane = threadIdx.x & 31;
+    const EpiParams& e = pp.epi;
+    const bool has_res = e.residual != nullptr;
+    PeRowMap rm{pp.ntok, pp.rows_per_img, pp.tok_off};
+    int pass = 0;
+    for (int r = 0; r < rounds; ++r) {
+      const long long m = ((long long)blockIdx.x + (long long)r * gridDim.x) * BM + ewarp * 32 + lane;
+      const bool ok = m < pp.M;                                      // past-the-end tiles / rows store nothing
+      long long m_out, m_res;
+      rm.map(ok ? m : 0, m_out, m_res);
+      const uint4* resp = reinterpret_cast<const uint4*>(e.residual + m_res * e.ld_res);
+      uint4* outp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out) + m_out * e.ld_out);
+      for (int n = 0; n < npass; ++n, ++pass) {
+        const int acc = pass & 1;
+        uint4 pos[8];
+        if (has_res && ok) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) pos[q] = __ldg(resp + n * 8 + q);
+        }
+        ptx::mbar_wait_sleep(&d_full[acc], (pass >> 1) & 1, 32);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + kTmDCol + acc * kTmBN + ((uint32_t)(ewarp * 32) << 16);
+        uint32_t raw[64];
+        ptx::tmem_ld_x32(taddr, raw);
+        ptx::tmem_ld_x32(taddr + 32, raw + 32);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&d_empty[acc]);                             // the accumulator is in registers: release it now
+        if (ok) {
+          const float* bs = bias_s + n * kTmBN;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float v[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(bs + q * 8);         // broadcast reads
+            const float4 b1 = *reinterpret_cast<const float4*>(bs + q * 8 + 4);
+            v[0] = __uint_as_float(raw[q * 8 + 0]) + b0.x; v[1] = __uint_as_float(raw[q * 8 + 1]) + b0.y;
+            v[2] = __uint_as_float(raw[q * 8 + 2]) + b0.z; v[3] = __uint_as_float(raw[q * 8 + 3]) + b0.w;
+            v[4] = __uint_as_float(raw[q * 8 + 4]) + b1.x; v[5] = __uint_as_float(raw[q * 8 + 5]) + b1.y;
+            v[6] = __uint_as_float(raw[q * 8 + 6]) + b1.z; v[7] = __uint_as_float(raw[q * 8 + 7]) + b1.w;
+            if (has_res) {
+              float f[8];
+              epi_unpack8(pos[q], f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += f[i];
+            }
+            outp[n * 8 + q] = epi_pack8(v);
+          }
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== gather producers: image -> registers -> bf16 -> TMEM =====================
+    const int pw = warp - 8;
+    const int group = pw >> 2;                     // the two warps of a lane quarter alternate k-blocks
+    const int quarter = pw & 3;                    // == warp % 4: the TMEM lanes this warp may write
+    const int lane = threadIdx.x & 31;
+    const int row = quarter * 32 + lane;
+    const uint32_t t_a = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    for (int it = 0; it < rounds; ++it) {
+      const long long m = ((long long)blockIdx.x + (long long)it * gridDim.x) * BM + row;
+      const bool row_ok = m < pp.M;
+      int cur_q = -1;
+      long long origin = 0;
+      for (int kb = group; kb < nkb; kb += 2) {
+        const int q = tblq[kb];
+        if (row_ok && q != cur_q && q < pp.g) { origin = patch_origin(pp, m, q); cur_q = q; }
+        uint4 raw[8][BF16IN ? 1 : 2];
+        int off[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          off[j] = tbl[kb * 8 + j];
+          if (row_ok && off[j] >= 0) {
+            if constexpr (BF16IN) {
+              raw[j][0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(pp.img) + origin + off[j]));
+            } else {
+              const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(pp.img) + origin + off[j]);
+              raw[j][0] = __ldg(src);
+              raw[j][1] = __ldg(src + 1);
+            }
+          }
+        }
+        uint32_t packed[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 o = make_uint4(0, 0, 0, 0);
+          if (row_ok && off[j] >= 0) {
+            if constexpr (BF16IN) {
+              o = raw[j][0];
+            } else {
+              o.x = ptx::pack_bf16(__uint_as_float(raw[j][0].x), __uint_as_float(raw[j][0].y));
+              o.y = ptx::pack_bf16(__uint_as_float(raw[j][0].z), __uint_as_float(raw[j][0].w));
+              o.z = ptx::pack_bf16(__uint_as_float(raw[j][1].x), __uint_as_float(raw[j][1].y));
+              o.w = ptx::pack_bf16(__uint_as_float(raw[j][1].z), __uint_as_float(raw[j][1].w));
+            }
+          }
+          packed[j * 4 + 0] = o.x; packed[j * 4 + 1] = o.y; packed[j * 4 + 2] = o.z; packed[j * 4 + 3] = o.w;
+        }
+        ptx::mbar_wait_sleep(&a_empty[kb], (it & 1) ^ 1, 64);   // long wait (the previous tile's last passes)
+        ptx::tc_fence_after();
+        ptx::tmem_st_x32(t_a + kb * 32, packed);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&a_full[kb]);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if constexpr (CL > 1) ptx::cluster_sync();   // no CTA leaves while a peer may still multicast into it
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <bool BF16IN, int CL>
+int launch_pe_tmem(const void* Wk, int D, const PatchParams& pp, cudaStream_t stream) {
+  CUtensorMap tw;
+  if (int err = sfc_make_tmap_2d(&tw, Wk, 2, (uint64_t)pp.Kpad, (uint64_t)D, (uint64_t)pp.Kpad * 2, BK, (uint32_t)(kTmBN / CL), true)) return err;
+  auto kern = patch_embed_tmem_kernel<BF16IN, CL>;
+  static int max_clusters = 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = PeTmSmem::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters == 0) {
+    SFC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PeTmSmem::kTotal));
+    cfg.gridDim = dim3(sfc_num_sms() / CL * CL);
+    int n = 0;
+    SFC_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));     // GPC boundaries can leave a few SMs out of 4-CTA clusters
+    max_clusters = n > 0 ? n : 1;
+  }
+  const int want = sfc_ceil_div(pp.num_m_tiles, CL);
+  cfg.gridDim = dim3((want < max_clusters ? want : max_clusters) * CL);
+  SFC_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tw, pp));
+  return 0;
+}
+
 // A-only gather: writes the curve-ordered im2col matrix A[M, Kpad] (bf16). Used by the backward pass
 // (weight gradient) only; the forward never materialises it.
 template <bool BF16IN, bool VEC>
@@ -440,6 +730,15 @@ extern "C" int sfc_patch_embed_fwd(const void* img, int img_bf16, int B, int C, 
   const bool vec = (p % 8 == 0) && (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0) && (((long long)H * W) % 8 == 0) &&
                    pp.num_k_blocks <= kMaxTblKb && ((long long)C * H * W < (1ll << 31));
   const bool fast = epi_fast_ok(pp.epi);
+  static const bool tm_off = getenv("SFC_PE_NOTMEM") != nullptr;
+  if (vec && fast && !tm_off && pp.num_k_blocks <= kTmMaxKb && D % (2 * kTmBN) == 0 && D <= kTmMaxD) {
+    // TMEM-resident A: gather once per token, 64-column passes over the weights
+    pp.num_n_tiles = D / kTmBN;
+    static const int cl = getenv("SFC_PE_CLUSTER") ? atoi(getenv("SFC_PE_CLUSTER")) : 4;
+    if (cl == 4 && pp.num_m_tiles >= 4) return img_bf16 ? launch_pe_tmem<true, 4>(Wk, D, pp, stream) : launch_pe_tmem<false, 4>(Wk, D, pp, stream);
+    if (cl >= 2 && pp.num_m_tiles >= 2) return img_bf16 ? launch_pe_tmem<true, 2>(Wk, D, pp, stream) : launch_pe_tmem<false, 2>(Wk, D, pp, stream);
+    return img_bf16 ? launch_pe_tmem<true, 1>(Wk, D, pp, stream) : launch_pe_tmem<false, 1>(Wk, D, pp, stream);
+  }
 #define PE_DISPATCH2(BN_, ST_, F_)                                                              \
   do {                                                                                          \
     if (vec && img_bf16) return launch_pe<BN_, ST_, true, true, F_>(tw, pp, stream);            \

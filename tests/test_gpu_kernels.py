@@ -22,11 +22,14 @@ def test_attention_dropout_mask_consistent(cuda_device):
     assert r["ok"], r
 
 
-def test_attention_rejects_other_head_dims(cuda_device):
+def test_attention_rejects_unsupported_shapes(cuda_device):
+    """head_dim 64 runs on tensor cores for any N; other head dims need head_dim % 8 == 0 and N <= 128 (generic path)."""
     import torch
     from sfcvit import ops
-    with pytest.raises(RuntimeError):
-        ops.attn_fwd(torch.zeros(16, 3 * 96, dtype=torch.bfloat16, device="cuda"), 1, 3, 16)
+    with pytest.raises(RuntimeError):       # head_dim 20
+        ops.attn_fwd(torch.zeros(16, 3 * 60, dtype=torch.bfloat16, device="cuda"), 1, 3, 16)
+    with pytest.raises(RuntimeError):       # head_dim 32 with 196 tokens
+        ops.attn_fwd(torch.zeros(196, 3 * 96, dtype=torch.bfloat16, device="cuda"), 1, 3, 196)
 
 
 @pytest.mark.parametrize("args", [(3, 3, 224, 16, 1, 768, "hilbert", "fp32"), (3, 3, 224, 16, 1, 384, "hilbert", "bf16"),
@@ -37,6 +40,29 @@ def test_patch_embed(cuda_device, args):
     import kernel_selftest as ks
     r = ks.check_patch(*args)
     assert r["ok"], r
+
+
+# The TMEM-resident kernel (K <= 768, p % 8 == 0, D % 128 == 0): odd / even k-block counts, group changes inside a row,
+# one channel, partial last tile, fewer tiles than a cluster, several tiles per CTA (> 148 tiles), fused position
+# embedding behind a class-token row; cluster sizes 4 / 2 / 1 and the shared-memory kernel via the env switches.
+@pytest.mark.parametrize("args", [(4, 3, 64, 8, 1, 256, "hilbert", "fp32"), (2, 1, 64, 16, 1, 128, "z", "bf16"),
+                                  (1, 3, 32, 16, 1, 128, "hilbert", "fp32"), (3, 3, 64, 8, 4, 384, "moore", "fp32"),
+                                  (100, 3, 224, 16, 1, 256, "hilbert", "bf16"), (7, 3, 224, 16, 1, 768, "hilbert", "fp32")])
+def test_patch_embed_tmem_resident(cuda_device, args):
+    import kernel_selftest as ks
+    r = ks.check_patch(*args, pos_cls=True)
+    assert r["ok"], r
+
+
+@pytest.mark.parametrize("env", [{"SFC_PE_CLUSTER": "2"}, {"SFC_PE_CLUSTER": "1"}, {"SFC_PE_NOTMEM": "1"}])
+def test_patch_embed_variants_agree(cuda_device, env):
+    """The env switches are read once per process, so each variant runs in a child interpreter."""
+    import os, subprocess, sys
+    code = ("import sys; sys.path.insert(0, 'tools'); import kernel_selftest as ks; "
+            "r = ks.check_patch(7, 3, 224, 16, 1, 768, 'hilbert', 'fp32', pos_cls=True); "
+            "r2 = ks.check_patch(3, 3, 64, 8, 1, 256, 'peano', 'bf16', pos_cls=True); assert r['ok'] and r2['ok'], (r, r2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, "-c", code], cwd=root, env={**os.environ, **env}, check=True, timeout=300)
 
 
 @pytest.mark.parametrize("args", [(1000, 768), (333, 192), (77, 1024), (5, 2048)])

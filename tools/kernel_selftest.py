@@ -62,7 +62,7 @@ def check_attn(B=2, H=3, N=196, drop_p=0.0, bwd=True, seed=0):
     return res
 
 
-def check_patch(B=3, C=3, HW=224, p=16, g=1, D=768, curve="hilbert", dtype="fp32", seed=0):
+def check_patch(B=3, C=3, HW=224, p=16, g=1, D=768, curve="hilbert", dtype="fp32", seed=0, pos_cls=False):
     import numpy as np
     from oracle import curves as oc
     gen = torch.Generator(device="cuda").manual_seed(seed)
@@ -90,8 +90,16 @@ def check_patch(B=3, C=3, HW=224, p=16, g=1, D=768, curve="hilbert", dtype="fp32
     A_ref = x.reshape(B, C, n, p, n, p).permute(0, 2, 4, 1, 3, 5).reshape(B, n * n, C * p * p)[:, perm_ref].reshape(B * (n * n // g), K)
     res = dict(check="patch", B=B, HW=HW, p=p, g=g, D=D, curve=curve, dtype=dtype)
     res["out_rel"] = rel(out.reshape(-1, D), ref.reshape(-1, D))
+    if pos_cls:
+        # position embedding fused as a per-token residual, tokens written behind one class-token row of a wider buffer
+        ntok = n * n // g
+        pos = torch.randn(ntok, D, generator=gen, device="cuda").bfloat16()
+        buf = torch.full((B, ntok + 1, D), 7.0, dtype=torch.bfloat16, device="cuda")
+        ops.patch_embed_fwd(img, perm, wk, bias, p, g, pos=pos, out=buf, rows_per_img=ntok + 1, tok_off=1)
+        res["pos_rel"] = rel(buf[:, 1:].reshape(-1, D), (ref + pos.float()).reshape(-1, D))
+        res["cls_row_untouched"] = bool((buf[:, 0] == 7.0).all())
     res["gather_exact"] = bool(torch.equal(A[:, :K].float(), A_ref.bfloat16().float())) and bool((A[:, K:] == 0).all())
-    res["ok"] = bool(res["out_rel"] < 6e-3 and res["gather_exact"])
+    res["ok"] = bool(res["out_rel"] < 6e-3 and res["gather_exact"] and res.get("pos_rel", 0.0) < 6e-3 and res.get("cls_row_untouched", True))
     return res
 
 

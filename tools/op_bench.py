@@ -20,6 +20,20 @@ def timeit(fn, nrot, iters=12, warm=3):
     for i in range(warm):
         fn(i % nrot)
     torch.cuda.synchronize()
+    if os.environ.get("OPBENCH_GRAPH"):           # replay a captured rotation: no host launch cost in the number
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(nrot):
+                fn(i)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(4):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (4 * nrot)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(iters):
