@@ -326,7 +326,7 @@ def main():
     pe_flops = pe_prof[0][3] if pe_prof else 0
     pe_gbs = pe_bytes / (pe_ms * 1e-3) / 1e9 if pe_ms > 0 else 0.0
     t_roof_ms = max(pe_bytes / (peaks["hbm_gbs"] * 1e9), pe_flops / (peaks["tf_sustained"] * 1e12)) * 1e3
-    patch_embed = {"kernel": "patch_embed_fwd_kernel (curve-order gather fused into the tcgen05 patch-embedding GEMM)", "ms": pe_ms,
+    patch_embed = {"kernel": "patch_embed_tmem_kernel (curve-order gather written once into tensor memory, tcgen05 A-from-TMEM patch-embedding GEMM)", "ms": pe_ms,
                    "algorithmic_bytes": pe_bytes, "achieved_gbs": pe_gbs, "hbm_peak_gbs": peaks["hbm_gbs"],
                    "frac_hbm": pe_gbs / peaks["hbm_gbs"], "bound": "tensor at K = 768 (SURVEY.md §8d)",
                    "frac_of_max_hbm_tensor_roofline": t_roof_ms / pe_ms if pe_ms > 0 else 0.0, "input_dtype": "fp32"}
