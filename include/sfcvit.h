@@ -100,6 +100,17 @@ size_t sfc_colsum_scratch_bytes(long long rows, int N);
 int sfc_colsum(const void* x, long long ld, long long rows, int N, void* out, int out_fp32, int accumulate,
                void* scratch, size_t scratch_bytes, sfc_stream_t stream);
 
+/* ---- K7: linear resampling of a token stream into a column slice of the hierarchical tokenizers' concat buffer
+ *      (tokenizers/multiscale/multi_hilbert.py:30-40 HierarchicalHilbertEmbedding.forward and its copies:
+ *       F.interpolate(mode="linear", align_corners=False) along the token axis + torch.cat(dim=-1)) ----
+ * src: bf16 [B, Ns, D] with row stride ld_src; dst row b*Nd + t has stride ld_dst (the caller pre-offsets dst to
+ * the level's column slice). Ns == Nd is a strided copy. bwd is the transposed operator: dsrc = R^T ddst.
+ * D, ld_src, ld_dst multiples of 8 elements, pointers 16-byte aligned. */
+int sfc_interp_concat_fwd(const void* src, long long ld_src, int B, int Ns, int D, void* dst, long long ld_dst, int Nd,
+                          sfc_stream_t stream);
+int sfc_interp_concat_bwd(const void* ddst, long long ld_dst, int B, int Nd, int D, void* dsrc, long long ld_src, int Ns,
+                          sfc_stream_t stream);
+
 /* ---- K2: fused curve-order patch gather + patch-embedding GEMM
  *      (tokenizers: multiscale/multi_hilbert.py:74-84 SFCEmbedding1D.forward and its morton/peano/moore copies,
  *       _1D/hilbert_embedding1D.py:30-43, _2D/hilbert_embedding.py:80-91, _2D/zigzag_embedding.py:24-30) ----

@@ -39,6 +39,8 @@ SIGNATURES = {
     "sfc_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, ctypes.c_ulonglong, _vp, _vp, _vp, _i, _i, _vp, _sz, _ll, _i, _vp]),
     "sfc_colsum_scratch_bytes": (_sz, [_ll, _i]),
     "sfc_colsum": (_i, [_vp, _ll, _ll, _i, _vp, _i, _i, _vp, _sz, _vp]),
+    "sfc_interp_concat_fwd": (_i, [_vp, _ll, _i, _i, _i, _vp, _ll, _i, _vp]),
+    "sfc_interp_concat_bwd": (_i, [_vp, _ll, _i, _i, _i, _vp, _ll, _i, _vp]),
     "sfc_patch_embed_kpad": (_i, [_i, _i, _i]),
     "sfc_patch_embed_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _vp]),
     "sfc_patch_gather": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),

@@ -236,6 +236,40 @@ def patch_embed(img, w_ref, bias, perm32, p, g, k_order="p1p2c", pos=None):
     return PatchEmbedFn.apply(img, w_ref, bias, perm32, int(p), int(g), k_order, pos)
 
 
+class ConcatStreamsFn(Function):
+    """cat([resample(s, n_tokens) for s in streams], dim=-1) for bf16 [B, N_l, D_l] token streams (kernel K7); the
+    hierarchical tokenizers' interpolate + cat (reference multi_hilbert.py:30-40)."""
+
+    @staticmethod
+    def forward(ctx, n_tokens, *streams):
+        B = streams[0].shape[0]
+        dims = [s.shape[2] for s in streams]
+        out = torch.empty((B, n_tokens, sum(dims)), dtype=torch.bfloat16, device=streams[0].device)
+        off = 0
+        for s in streams:
+            ops.interp_concat_fwd(_bf16_act(s), out, off)
+            off += s.shape[2]
+        ctx.meta = [(s.shape[1], s.shape[2], s.dtype) for s in streams]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = _bf16_act(dout)
+        grads, off = [], 0
+        for i, (Ns, D, dt) in enumerate(ctx.meta):
+            grads.append(ops.interp_concat_bwd(dout, off, Ns, D).to(dt) if ctx.needs_input_grad[1 + i] else None)
+            off += D
+        return (None, *grads)
+
+
+def concat_streams(streams, n_tokens):
+    """Kernel path when every stream's feature size is a multiple of 8 (16-byte vectors); None otherwise (the caller
+    then uses torch's upsample + cat on the same device)."""
+    if any(s.shape[2] % 8 for s in streams):
+        return None
+    return ConcatStreamsFn.apply(n_tokens, *streams)
+
+
 class EncoderLayerFn(Function):
     """One post-norm ReLU transformer encoder layer (torch.nn.TransformerEncoderLayer defaults used by the reference,
     vit.py:197-206): x1 = LN1(x + drop(out_proj(MHA(x)))), x2 = LN2(x1 + drop(W2 drop(relu(W1 x1 + b1)) + b2)).

@@ -201,6 +201,36 @@ def colsum(x, out_dtype=torch.bfloat16):
     return out
 
 
+# ------------------------------------------------------------------ K7: token-axis linear resampling into a concat slice
+def interp_concat_fwd(src, dst, col_off):
+    """src bf16 [B, Ns, D] -> dst[:, :, col_off : col_off + D] of the bf16 [B, Nd, Dtot] concat buffer
+    (F.interpolate(mode='linear', align_corners=False) along tokens; a copy when Ns == Nd)."""
+    lib = _lib.load()
+    _require_cuda(src, dst)
+    assert src.dtype == dst.dtype == torch.bfloat16 and src.dim() == dst.dim() == 3 and src.shape[0] == dst.shape[0]
+    assert src.stride(2) == 1 and dst.stride(2) == 1 and src.stride(0) == src.shape[1] * src.stride(1) and dst.is_contiguous()
+    B, Ns, D = src.shape
+    with torch.cuda.device(src.device):
+        _lib.check(lib.sfc_interp_concat_fwd(_ptr(src), src.stride(1), B, Ns, D, ctypes.c_void_p(dst.data_ptr() + 2 * col_off),
+                                             dst.stride(1), dst.shape[1], _stream()), "sfc_interp_concat_fwd")
+    _count(1)
+    return dst
+
+
+def interp_concat_bwd(ddst, col_off, Ns, D):
+    """Transposed operator: gradient of the [B, Ns, D] stream from the concat buffer's gradient slice."""
+    lib = _lib.load()
+    _require_cuda(ddst)
+    assert ddst.dtype == torch.bfloat16 and ddst.dim() == 3 and ddst.is_contiguous()
+    B, Nd, _ = ddst.shape
+    dsrc = torch.empty((B, Ns, D), dtype=torch.bfloat16, device=ddst.device)
+    with torch.cuda.device(ddst.device):
+        _lib.check(lib.sfc_interp_concat_bwd(ctypes.c_void_p(ddst.data_ptr() + 2 * col_off), ddst.stride(1), B, Nd, D, _ptr(dsrc), D, Ns,
+                                             _stream()), "sfc_interp_concat_bwd")
+    _count(1)
+    return dsrc
+
+
 # ------------------------------------------------------------------ K2: fused patch embed
 def patch_embed_kpad(C, p, g):
     return _lib.load().sfc_patch_embed_kpad(C, p, g)

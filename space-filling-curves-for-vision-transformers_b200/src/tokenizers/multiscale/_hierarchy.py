@@ -78,10 +78,13 @@ class HierarchicalCurveEmbedding(nn.Module):
     def forward(self, x):
         streams = [level(x) for level in self.levels]
         n_tokens = self.patch_list[0]
-        for i in range(1, len(streams)):
-            if streams[i].shape[1] != n_tokens:
-                # general-length case: torch's linear interpolation, as in the reference
-                streams[i] = torch.nn.functional.interpolate(streams[i].transpose(1, 2), size=n_tokens, mode="linear",
-                                                             align_corners=False).transpose(1, 2)
-        cat = torch.cat(streams, dim=-1)
+        # general-length case: kernel K7 resamples each stream along the token axis straight into
+        # its column slice of the concat buffer (equal lengths degenerate to a copy)
+        cat = SF.concat_streams(streams, n_tokens)
+        if cat is None:                                   # feature size not a multiple of 8: torch ops on the same device
+            for i in range(len(streams)):
+                if streams[i].shape[1] != n_tokens:
+                    streams[i] = torch.nn.functional.interpolate(streams[i].transpose(1, 2), size=n_tokens, mode="linear",
+                                                                 align_corners=False).transpose(1, 2)
+            cat = torch.cat(streams, dim=-1)
         return SF.linear(cat, self.fusion.weight, self.fusion.bias)

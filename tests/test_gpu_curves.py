@@ -56,3 +56,21 @@ def test_bad_arguments_raise(cuda_device):
         ops.curve_perm("onion_curve", 4, 4)
     with pytest.raises(RuntimeError):
         ops.curve_perm("hilbert", 0, 4)
+
+
+def _hash(curve, n):
+    return hashlib.sha256(np.array([i * n + j for i, j in curve], "<i8").tobytes()).hexdigest()[:16]
+
+
+def test_block_stitch_and_hamiltonian_refinement_match_reference(cuda_device):
+    """Init-time host utilities of the reference (space_filling_curves.py:446-455, :513-591) on the 14 x 14 grid,
+    driven by the K1 curves; hashes generated from the live reference."""
+    from src.curves import space_filling_curves as sc
+    curve, blocks = sc.block_stitch_sfc(sc.hilbert_curve, 14, 14)
+    assert len(blocks) == 19 and sorted(curve) == [(i, j) for i in range(14) for j in range(14)]
+    assert _hash(curve, 14) == "69a853eea38654f4"
+    jumps = sum(1 for a, b in zip(curve, curve[1:]) if abs(a[0] - b[0]) + abs(a[1] - b[1]) != 1)
+    assert jumps == 3
+    ham = sc.refine_curve_to_hamiltonian(sc.embed_and_prune_sfc(sc.hilbert_curve, 14, 14), 14, 14)
+    assert _hash(ham, 14) == "4368ddfc2fd7a712"
+    assert all(abs(a[0] - b[0]) + abs(a[1] - b[1]) == 1 for a, b in zip(ham, ham[1:]))

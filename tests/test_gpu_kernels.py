@@ -110,3 +110,41 @@ def test_attention_generic_head_dim(cuda_device, B, H, N, dh, drop):
         lhs = float((out_dir.float() * dout.float()).sum()); rhs = float((dqkv[:, 2 * D:].float() * vdir.float()).sum())
         assert abs(lhs - rhs) / max(abs(lhs), 1e-6) < 3e-2
         assert torch.isfinite(dqkv.float()).all()
+
+
+# K7: token-axis linear resampling into a concat slice vs torch (F.interpolate(mode="linear", align_corners=False) on the
+# same bf16 inputs in fp32; output rounded to bf16: rel-L2 <= 4e-3), and the transposed operator vs autograd of torch's.
+@pytest.mark.parametrize("lens", [(64, [64, 16, 4]), (196, [196, 49, 7]), (49, [49, 196]), (100, [100, 37, 1]), (16, [16, 16])])
+def test_interp_concat_matches_torch(cuda_device, lens):
+    import torch
+    from sfcvit import functional as SF
+    n, ns = lens
+    B, dims = 3, [64, 32, 8][:len(ns)]
+    g = torch.Generator(device="cuda").manual_seed(1)
+    streams = [torch.randn(B, s, d, generator=g, device="cuda").bfloat16().requires_grad_(True) for s, d in zip(ns, dims)]
+    out = SF.concat_streams(streams, n)
+    ref_in = [s.detach().float().requires_grad_(True) for s in streams]
+    ref = torch.cat([r if r.shape[1] == n else torch.nn.functional.interpolate(r.transpose(1, 2), size=n, mode="linear",
+                                                                              align_corners=False).transpose(1, 2)
+                     for r in ref_in], dim=-1)
+    assert out.shape == ref.shape and out.dtype == torch.bfloat16
+    assert float((out.float() - ref).norm() / ref.norm()) < 4e-3
+    off = 0
+    for s in streams:                                      # equal-length streams are copied bit-exactly
+        if s.shape[1] == n:
+            assert torch.equal(out[:, :, off:off + s.shape[2]], s.detach())
+        off += s.shape[2]
+    w = torch.randn(ref.shape, generator=g, device="cuda").bfloat16()
+    (out.float() * w.float()).sum().backward()
+    (ref * w.float()).sum().backward()
+    for s, r in zip(streams, ref_in):
+        assert s.grad.dtype == torch.bfloat16
+        assert float((s.grad.float() - r.grad).norm() / r.grad.norm()) < 4e-3
+
+
+def test_interp_concat_rejects_bad_layout(cuda_device):
+    import torch
+    from sfcvit import ops
+    with pytest.raises(RuntimeError):
+        ops.interp_concat_fwd(torch.zeros(1, 4, 12, dtype=torch.bfloat16, device="cuda"),
+                              torch.zeros(1, 8, 12, dtype=torch.bfloat16, device="cuda"), 0)
