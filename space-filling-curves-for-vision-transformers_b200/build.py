@@ -22,7 +22,7 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
     "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-]
+] + (["-DSFC_ATTN_TIMELINE"] if os.environ.get("SFC_ATTN_TIMELINE") else [])   # debug stamps for tools/attn_timeline.py
 
 
 def _deps_mtime():

@@ -431,8 +431,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 //   dV += P^T dO, dK += dS^T Q, dQ(s) = dS K -> S[s&1] (dead by then)      after P / dS of step s are in smem
 //   dP(s+1) = dO V^T -> dP
 // and the warpgroups run  P = exp2(S - lse) (kept in registers)  ->  read dQ(s-1) out  ->  dS = P (dP - delta) scale.
+// Per-step clock64 stamps of CTA 0 (tools/attn_timeline.py): compiled in only with -DSFC_ATTN_TIMELINE, they cost
+// registers in a kernel that is 2 registers away from spilling.
+#ifdef SFC_ATTN_TIMELINE
+#define SFC_TL(...) __VA_ARGS__
+#else
+#define SFC_TL(...)
+#endif
 constexpr int kBwdEwWarps = 16;                 // element-wise warps: 4 per TMEM lane quarter, one 32-column chunk each
-constexpr int kBwdThreads = 128 + kBwdEwWarps * 32;
+constexpr int kBwdThreads = 64 + kBwdEwWarps * 32;   // warp 0: TMEM alloc + TMA, warp 1: MMA issuer; 18 warps leave 112 registers per thread
 constexpr int kQdoStages = 3;
 
 struct BwdSmem {
@@ -510,6 +517,24 @@ struct BwdCursor {
   }
 };
 
+// The element-wise warps' view of the same sequence: only what they use, so that the previous / current / next
+// positions do not push the 16 warps (96 registers each) into local-memory spills inside the step loop.
+struct EwPos {
+  int s, qt, jt, h, b;
+  __device__ __forceinline__ void advance(int dj, int dh, int db, int n_kvt, int H, int nq) {
+    ++s;
+    if (++qt == nq) {
+      qt = 0;
+      jt += dj; if (jt >= n_kvt) { jt -= n_kvt; ++h; }
+      h += dh; if (h >= H) { h -= H; ++b; }
+      b += db;
+    }
+  }
+  // two registers for the previous position: qt, jt < 65536; heads < 256; images < 2^23 (checked on the host)
+  __device__ __forceinline__ uint2 pack() const { return make_uint2((uint32_t)qt | ((uint32_t)jt << 16), (uint32_t)h | ((uint32_t)b << 8)); }
+  __device__ __forceinline__ void unpack(uint2 v, int s_) { s = s_; qt = v.x & 0xffff; jt = v.x >> 16; h = v.y & 255; b = (int)(v.y >> 8); }
+};
+
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                 const __grid_constant__ CUtensorMap tmap_do, const AttnParams p, const int bkv) {
@@ -544,7 +569,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     ptx::mbar_init(&bars[BwdBars::dq_empty], kBwdEwWarps * 32);
     ptx::fence_barrier_init();
   }
-  if (warp == 2) ptx::tmem_alloc<512>(tmem_ptr);
+  if (warp == 0) ptx::tmem_alloc<512>(tmem_ptr);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -639,7 +664,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         ptx::umma_commit(&bars[BwdBars::qdo_empty + st]);
         if (qt == nq - 1) ptx::umma_commit(&bars[BwdBars::kv_empty + kvst]);
       };
-      long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
+      SFC_TL(long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;)
       if (T > 0) {
         BwdCursor c0, c1;                                        // steps s and s + 1
         c0.init(n_kvt, p.H, nq);
@@ -648,25 +673,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         dp_issue(c0);
         c1.advance();
         for (int s = 0; s < T; ++s) {
-          if (dbg && s < 64) dbg[s * 16 + 8] = clock64();
+          SFC_TL(if (dbg && s < 64) dbg[s * 16 + 8] = clock64();)
           if (s + 1 < T) s_issue(c1);
-          if (dbg && s < 64) dbg[s * 16 + 9] = clock64();
+          SFC_TL(if (dbg && s < 64) dbg[s * 16 + 9] = clock64();)
           ptx::mbar_wait(&bars[BwdBars::pds_full], s & 1);       // P / dS of step s are in smem, dP(s) has been consumed
-          if (dbg && s < 64) dbg[s * 16 + 12] = clock64();
+          SFC_TL(if (dbg && s < 64) dbg[s * 16 + 12] = clock64();)
           ptx::tc_fence_after();
           if (s + 1 < T) dp_issue(c1);                           // first: it is the input the warpgroups wait for next
-          if (dbg && s < 64) dbg[s * 16 + 11] = clock64();
+          SFC_TL(if (dbg && s < 64) dbg[s * 16 + 11] = clock64();)
           grad_issue(c0);
-          if (dbg && s < 64) dbg[s * 16 + 10] = clock64();
+          SFC_TL(if (dbg && s < 64) dbg[s * 16 + 10] = clock64();)
           c0 = c1;
           c1.advance();
         }
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  } else if (warp >= 2) {
     // ===================== element-wise warpgroups =====================
-    const int ch = (warp - 4) >> 2;                // this warp's 32-column chunk of the S / dP tile (0..3)
+    const int ch = (warp - 2) >> 2;                // this warp's 32-column chunk of the S / dP tile (0..3)
     const int quarter = warp & 3;
     const int lane = tid & 31;
     const int r = quarter * 32 + lane;             // query row in tile == TMEM lane
@@ -679,7 +704,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int nch = (bkv + 31) / 32;
 
     // readout of step sp (its dQ; and dV / dK when it was the last step of its item)
-    auto readout = [&](const BwdCursor& cp) {
+    auto readout = [&](const EwPos& cp) {
       const int sp = cp.s, qt = cp.qt, jt = cp.jt, h = cp.h;
       const int row0 = cp.b * p.N;
       ptx::mbar_wait(&bars[BwdBars::dq_full], sp & 1);
@@ -740,7 +765,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
     // row statistics of a step: lse * log2e (+inf for rows past the sequence end, so that P = exp2(-inf) = 0 without a
     // branch) and delta. They are loaded one step ahead: the global-load latency hides behind the previous step.
-    auto load_stats = [&](const BwdCursor& cn, float& l2, float& dl) {
+    auto load_stats = [&](const EwPos& cn, float& l2, float& dl) {
       l2 = INFINITY; dl = 0.f;
       const int qi2 = cn.qt * BQ + r;
       if (cn.s < T && qi2 < p.N) {
@@ -751,14 +776,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(dl) : "l"(p.delta + si));
       }
     };
-    BwdCursor cur, nxt, prev;
-    cur.init(n_kvt, p.H, nq);
-    nxt = cur;
-    prev = cur;
+    EwPos cur;
+    int dj, dh, db;
+    {
+      const int item = (int)blockIdx.x, g = (int)gridDim.x;
+      cur.s = 0; cur.qt = 0;
+      cur.jt = item % n_kvt; cur.h = (item / n_kvt) % p.H; cur.b = item / (n_kvt * p.H);
+      dj = g % n_kvt; dh = (g / n_kvt) % p.H; db = g / (n_kvt * p.H);
+    }
+    uint2 prev_packed = make_uint2(0, 0);
     float lse2_next, delta_next;
     load_stats(cur, lse2_next, delta_next);
-    nxt.advance();
-    for (; cur.s < T; prev = cur, cur = nxt, nxt.advance()) {
+    for (; cur.s < T; prev_packed = cur.pack(), cur.advance(dj, dh, db, n_kvt, p.H, nq)) {
       {
         const int s = cur.s, qt = cur.qt, h = cur.h, b = cur.b;
         const int kv0 = cur.jt * bkv;
@@ -767,13 +796,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int q_valid = min(BQ, p.N - qt * BQ);
         const bool warp_active = quarter * 32 < ((q_valid + 15) / 16) * 16;   // rows read by the dV / dK MMAs
         const float lse2 = lse2_next * kLog2e, delta = delta_next;
-        load_stats(nxt, lse2_next, delta_next);
+        {
+          EwPos nxt = cur;                                   // recomputed here instead of carried through the step
+          nxt.advance(dj, dh, db, n_kvt, p.H, nq);
+          load_stats(nxt, lse2_next, delta_next);
+        }
         // ---- phase A: P = exp2(S * scale * log2e - lse * log2e), kept in registers (+ dropout keep bits)
         float pr[32];
-        long long* dbg = (blockIdx.x == 0 && tid == 128 && s < 64) ? p.dbg : nullptr;
-        if (dbg) dbg[s * 16 + 0] = clock64();
+        SFC_TL(long long* dbg = (blockIdx.x == 0 && tid == 64 && s < 64) ? p.dbg : nullptr;)
+        SFC_TL(if (dbg) dbg[s * 16 + 0] = clock64();)
         ptx::mbar_wait(&bars[BwdBars::s_full + (s & 1)], (s >> 1) & 1);
-        if (dbg) dbg[s * 16 + 1] = clock64();
+        SFC_TL(if (dbg) dbg[s * 16 + 1] = clock64();)
         ptx::tc_fence_after();
         const int c = ch;
         const bool chunk_active = warp_active && c < nch;
@@ -809,12 +842,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           }
         }
         // ---- dQ (and dV / dK) of the previous step leave TMEM; this also guarantees its MMAs no longer read P / dS smem
-        if (dbg) dbg[s * 16 + 2] = clock64();
-        if (s > 0) readout(prev);
-        if (dbg) dbg[s * 16 + 3] = clock64();
+        SFC_TL(if (dbg) dbg[s * 16 + 2] = clock64();)
+        if (s > 0) {
+          EwPos prev;
+          prev.unpack(prev_packed, s - 1);
+          readout(prev);
+        }
+        SFC_TL(if (dbg) dbg[s * 16 + 3] = clock64();)
         // ---- phase B: dS = P * (dP - delta) * scale; P (dropped) and dS -> shared memory
         ptx::mbar_wait(&bars[BwdBars::dp_full], s & 1);
-        if (dbg) dbg[s * 16 + 4] = clock64();
+        SFC_TL(if (dbg) dbg[s * 16 + 4] = clock64();)
         ptx::tc_fence_after();
         if (chunk_active) {
 #pragma unroll
@@ -841,18 +878,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             store_p_half(smem + BwdSmem::kDS, r, c * 2 + hf, dsv);
           }
         }
-        if (dbg) dbg[s * 16 + 5] = clock64();
+        SFC_TL(if (dbg) dbg[s * 16 + 5] = clock64();)
         ptx::tc_fence_before();
         ptx::fence_proxy_async_smem();
+        SFC_TL(if (dbg) dbg[s * 16 + 6] = clock64();)
         ptx::mbar_arrive(&bars[BwdBars::pds_full]);
+        SFC_TL(if (dbg) dbg[s * 16 + 7] = clock64();)
       }
     }
-    if (T > 0) readout(prev);
+    if (T > 0) {
+      EwPos prev;
+      prev.unpack(prev_packed, T - 1);
+      readout(prev);
+    }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 0) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem_base);
   }
@@ -957,6 +1000,7 @@ extern "C" int sfc_attn_bwd(const void* qkv, const void* out, const void* dout, 
                 "sfc_attn_bwd: head_dim %d is served by the generic path only for N <= 128 within shared memory (N=%d)", D / H, N);
     return sfc_attn_generic_bwd(qkv, out, dout, lse, dqkv, B, H, N, D, scale, drop_p, drop_seed, stream);
   }
+  SFC_REQUIRE(H < 256 && B < (1 << 23) && N <= 65536 * 16, "sfc_attn_bwd: heads < 256, images < 2^23 (H=%d, B=%d)", H, B);
   const size_t dq_bytes = (size_t)B * N * D * sizeof(float);
   const size_t need = sfc_attn_bwd_scratch_bytes(B, N, D);
   SFC_REQUIRE(scratch && scratch_bytes >= need, "sfc_attn_bwd: scratch too small (%zu < %zu)", scratch_bytes, need);

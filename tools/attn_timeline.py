@@ -23,6 +23,6 @@ t0 = int(t[4, 0])
 print("step | WG: start s_full(wait) phaseA_end readout_end dp_wait_end phaseB_end | MMA: loop_start s_issued pds_seen grads_issued dp_issued   (cycles rel. to step 4 start)")
 for s in range(4, 24):
     r = [int(x) - t0 for x in t[s]]
-    print(s, "| WG", r[0], r[1], r[2], r[3], r[4], r[5], "| MMA", r[8], r[9], r[12], r[11], r[10])
+    print(s, "| WG", r[0], r[1], r[2], r[3], r[4], r[5], "fence", r[6], "arrive", r[7], "| MMA", r[8], r[9], r[12], r[11], r[10])
 d = t[8:40, 0][1:] - t[8:40, 0][:-1]
 print("mean cycles per step:", float(d.float().mean()))
