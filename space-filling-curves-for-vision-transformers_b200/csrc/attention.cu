@@ -701,7 +701,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const DropKey dkey = drop_key(p.drop_seed, p.drop_p, p.drop_epoch);
     const bool has_drop = p.drop_p > 0.f;
     const uint32_t thr_hi = dkey.thr16 << 16;
-    const int nch = (bkv + 31) / 32;
 
     // readout of step sp (its dQ; and dV / dK when it was the last step of its item)
     auto readout = [&](const EwPos& cp) {
@@ -809,7 +808,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         SFC_TL(if (dbg) dbg[s * 16 + 1] = clock64();)
         ptx::tc_fence_after();
         const int c = ch;
-        const bool chunk_active = warp_active && c < nch;
+        const bool chunk_active = warp_active && c * 32 < bkv;   // against the kernel parameter: no live register
         if (chunk_active) {
           uint32_t rs[32];
           ptx::tmem_ld_x32(tmem_base + (s & 1) * 128 + lane_off + c * 32, rs);
