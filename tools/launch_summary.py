@@ -1,5 +1,5 @@
 """Summarise an ncu launch list (--metrics gpu__time_duration.sum --csv) per kernel over one training step
-(the window between two consecutive patch_embed_fwd_kernel launches). usage: launch_summary.py file.csv"""
+(the window between two consecutive patch-embed launches). usage: launch_summary.py file.csv"""
 import collections
 import csv
 import re
@@ -21,7 +21,7 @@ def main(path):
     with open(path) as f:
         lines = [l for l in f if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
-    idx = [i for i, r in enumerate(rows) if "patch_embed_fwd" in r["Kernel Name"]]
+    idx = [i for i, r in enumerate(rows) if "patch_embed_" in r["Kernel Name"]]
     a, b = idx[0], idx[1]
     agg = collections.defaultdict(lambda: [0, 0.0])
     for r in rows[a:b]:
