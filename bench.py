@@ -181,7 +181,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="vit_b16_224", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: config)")
-    ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the CPU baseline sample")
+    ap.add_argument("--cpu-batch", type=int, default=16, help="batch of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dropout", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
