@@ -497,12 +497,14 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16*
 // five warps per scheduler each scalar instruction of a role costs several cycles of wall time.
 struct BwdCursor {
   int s, ii, qt, jt, h, b, st3, ph3;     // step, local item, query tile, (key tile, head, image), Q/dO stage and its phase
-  int dj, dh, db, n_kvt, H, nq;
+  int dh, db, n_kvt, H, nq;
+  // head-major: the CTAs stride over heads, and the items of a CTA are (head, key tile 0), (head, key tile 1), ..., next
+  // head — so that with two key tiles the second read-out can add the first one's dQ (see readout)
   __device__ __forceinline__ void init(int n_kvt_, int H_, int nq_) {
     n_kvt = n_kvt_; H = H_; nq = nq_;
-    const int item = (int)blockIdx.x, g = (int)gridDim.x;
-    jt = item % n_kvt; h = (item / n_kvt) % H; b = item / (n_kvt * H);
-    dj = g % n_kvt; dh = (g / n_kvt) % H; db = g / (n_kvt * H);
+    const int head = (int)blockIdx.x, g = (int)gridDim.x;
+    jt = 0; h = head % H; b = head / H;
+    dh = g % H; db = g / H;
     s = 0; ii = 0; qt = 0; st3 = 0; ph3 = 0;
   }
   __device__ __forceinline__ void advance() {
@@ -510,9 +512,11 @@ struct BwdCursor {
     if (++st3 == kQdoStages) { st3 = 0; ph3 ^= 1; }
     if (++qt == nq) {
       qt = 0; ++ii;
-      jt += dj; if (jt >= n_kvt) { jt -= n_kvt; ++h; }
-      h += dh; if (h >= H) { h -= H; ++b; }
-      b += db;
+      if (++jt == n_kvt) {
+        jt = 0;
+        h += dh; if (h >= H) { h -= H; ++b; }
+        b += db;
+      }
     }
   }
 };
@@ -521,13 +525,15 @@ struct BwdCursor {
 // positions do not push the 16 warps (96 registers each) into local-memory spills inside the step loop.
 struct EwPos {
   int s, qt, jt, h, b;
-  __device__ __forceinline__ void advance(int dj, int dh, int db, int n_kvt, int H, int nq) {
+  __device__ __forceinline__ void advance(int dh, int db, int n_kvt, int H, int nq) {
     ++s;
     if (++qt == nq) {
       qt = 0;
-      jt += dj; if (jt >= n_kvt) { jt -= n_kvt; ++h; }
-      h += dh; if (h >= H) { h -= H; ++b; }
-      b += db;
+      if (++jt == n_kvt) {
+        jt = 0;
+        h += dh; if (h >= H) { h -= H; ++b; }
+        b += db;
+      }
     }
   }
   // two registers for the previous position: qt, jt < 65536; heads < 256; images < 2^23 (checked on the host)
@@ -546,8 +552,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int tid = threadIdx.x, warp = tid >> 5;
   const int nq = (p.N + BQ - 1) / BQ;                       // steps per item
   const int n_kvt = (p.N + bkv - 1) / bkv;
-  const int n_items = p.B * p.H * n_kvt;
-  const int my_items = (int)blockIdx.x < n_items ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int n_heads = p.B * p.H;                              // the CTAs stride over heads
+  const int my_heads = (int)blockIdx.x < n_heads ? (n_heads - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int my_items = my_heads * n_kvt;
   const int T = my_items * nq;                              // steps of this CTA
 
   if (tid == 0) {
@@ -720,17 +727,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             for (int e = 0; e < 16; e += 4)
               red_add_v4(dst + e, __uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3]));
           } else {
-            // one or two key tiles per head: every dQ element has at most two contributions, each written exactly once as
-            // bf16 (tile 0 of two -> scratch, otherwise -> dqkv); dq_add_kernel sums them. No memset, no atomics.
-            __nv_bfloat16* dst = (p.dq_mode == 2 && jt == 0) ? p.dq_part + (long long)(row0 + qi) * p.D + h * DH + ch * 16
-                                                              : p.dqkv + (long long)(row0 + qi) * (3 * p.D) + h * DH + ch * 16;
+            // one or two key tiles per head, no memset, no atomics: with two tiles the CTA walks them back to back
+            // (head-major item order), the first tile's dQ goes to scratch as bf16 and the second tile's read-out — the
+            // same thread, two steps later — adds it back and writes the final value
+            const bool first_of_two = p.dq_mode == 2 && jt == 0;
+            __nv_bfloat16* part = p.dq_part + (long long)(row0 + qi) * p.D + h * DH + ch * 16;
+            __nv_bfloat16* dst = first_of_two ? part : p.dqkv + (long long)(row0 + qi) * (3 * p.D) + h * DH + ch * 16;
+            const bool second = p.dq_mode == 2 && jt != 0;
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(rr[q * 8 + e]);
+              if (second) {
+                const uint4 a = reinterpret_cast<const uint4*>(part)[q];
+                v[0] += ptx::bf16_lo(a.x); v[1] += ptx::bf16_hi(a.x); v[2] += ptx::bf16_lo(a.y); v[3] += ptx::bf16_hi(a.y);
+                v[4] += ptx::bf16_lo(a.z); v[5] += ptx::bf16_hi(a.z); v[6] += ptx::bf16_lo(a.w); v[7] += ptx::bf16_hi(a.w);
+              }
               uint4 o;
-              o.x = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 0]), __uint_as_float(rr[q * 8 + 1]));
-              o.y = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 2]), __uint_as_float(rr[q * 8 + 3]));
-              o.z = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 4]), __uint_as_float(rr[q * 8 + 5]));
-              o.w = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 6]), __uint_as_float(rr[q * 8 + 7]));
+              o.x = ptx::pack_bf16(v[0], v[1]); o.y = ptx::pack_bf16(v[2], v[3]);
+              o.z = ptx::pack_bf16(v[4], v[5]); o.w = ptx::pack_bf16(v[6], v[7]);
               reinterpret_cast<uint4*>(dst)[q] = o;
             }
           }
@@ -776,17 +792,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     };
     EwPos cur;
-    int dj, dh, db;
+    int dh, db;
     {
-      const int item = (int)blockIdx.x, g = (int)gridDim.x;
-      cur.s = 0; cur.qt = 0;
-      cur.jt = item % n_kvt; cur.h = (item / n_kvt) % p.H; cur.b = item / (n_kvt * p.H);
-      dj = g % n_kvt; dh = (g / n_kvt) % p.H; db = g / (n_kvt * p.H);
+      const int head = (int)blockIdx.x, g = (int)gridDim.x;
+      cur.s = 0; cur.qt = 0; cur.jt = 0;
+      cur.h = head % p.H; cur.b = head / p.H;
+      dh = g % p.H; db = g / p.H;
     }
     uint2 prev_packed = make_uint2(0, 0);
     float lse2_next, delta_next;
     load_stats(cur, lse2_next, delta_next);
-    for (; cur.s < T; prev_packed = cur.pack(), cur.advance(dj, dh, db, n_kvt, p.H, nq)) {
+    for (; cur.s < T; prev_packed = cur.pack(), cur.advance(dh, db, n_kvt, p.H, nq)) {
       {
         const int s = cur.s, qt = cur.qt, h = cur.h, b = cur.b;
         const int kv0 = cur.jt * bkv;
@@ -797,7 +813,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const float lse2 = lse2_next * kLog2e, delta = delta_next;
         {
           EwPos nxt = cur;                                   // recomputed here instead of carried through the step
-          nxt.advance(dj, dh, db, n_kvt, p.H, nq);
+          nxt.advance(dh, db, n_kvt, p.H, nq);
           load_stats(nxt, lse2_next, delta_next);
         }
         // ---- phase A: P = exp2(S * scale * log2e - lse * log2e), kept in registers (+ dropout keep bits)
@@ -897,24 +913,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == 0) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem_base);
-  }
-}
-
-// dqkv[:, 0:D] += dq_part   (two key tiles per head: the second tile's partial is already in dqkv)
-__global__ void dq_add_kernel(const __nv_bfloat16* __restrict__ part, __nv_bfloat16* __restrict__ dqkv, long long rows, int D) {
-  const long long total = rows * (D / 8);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long m = i / (D / 8);
-    const int c = (int)(i % (D / 8)) * 8;
-    const uint4 a = *reinterpret_cast<const uint4*>(part + m * D + c);
-    uint4* dst = reinterpret_cast<uint4*>(dqkv + m * (3ll * D) + c);
-    const uint4 b = *dst;
-    uint4 o;
-    o.x = ptx::pack_bf16(ptx::bf16_lo(a.x) + ptx::bf16_lo(b.x), ptx::bf16_hi(a.x) + ptx::bf16_hi(b.x));
-    o.y = ptx::pack_bf16(ptx::bf16_lo(a.y) + ptx::bf16_lo(b.y), ptx::bf16_hi(a.y) + ptx::bf16_hi(b.y));
-    o.z = ptx::pack_bf16(ptx::bf16_lo(a.z) + ptx::bf16_lo(b.z), ptx::bf16_hi(a.z) + ptx::bf16_hi(b.z));
-    o.w = ptx::pack_bf16(ptx::bf16_lo(a.w) + ptx::bf16_lo(b.w), ptx::bf16_hi(a.w) + ptx::bf16_hi(b.w));
-    *dst = o;
   }
 }
 
@@ -1031,16 +1029,15 @@ extern "C" int sfc_attn_bwd(const void* qkv, const void* out, const void* dout, 
     SFC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal));
     configured = true;
   }
-  const long long items = (long long)B * H * ((N + bkv - 1) / bkv);
+  const long long items = (long long)B * H;                  // the CTAs stride over heads (all key tiles of a head on one CTA)
   const int grid = (int)(items < sfc_num_sms() ? items : sfc_num_sms());
   attn_bwd_kernel<<<grid, kBwdThreads, BwdSmem::kTotal, stream>>>(tq, tkv, tdo, p, bkv);
   SFC_LAUNCH_OK();
-  if (dq_mode != 1) {
+  if (dq_mode == 0) {
     long long blocks = sfc_ceil_div64(rows * (D / 8), 256);
     const long long cap = 16ll * sfc_num_sms();
     if (blocks > cap) blocks = cap;
-    if (dq_mode == 0) dq_finalize_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const float*)scratch, (__nv_bfloat16*)dqkv, rows, D);
-    else dq_add_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)scratch, (__nv_bfloat16*)dqkv, rows, D);
+    dq_finalize_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const float*)scratch, (__nv_bfloat16*)dqkv, rows, D);
   }
   SFC_LAUNCH_OK();
   return 0;
