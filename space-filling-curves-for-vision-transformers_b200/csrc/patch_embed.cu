@@ -7,12 +7,15 @@
 //
 //   out[b, t, :] = W . concat_{q<g} patchvec(b, perm[t*g+q]) + bias (+ pos[t, :])
 //
-// A operand (tokens x K): gathered straight from the NCHW image by 8 producer warps (two groups that
-// alternate pipeline stages), converted fp32->bf16 in registers and written to shared memory in the
-// 128-byte-swizzled K-major layout that tcgen05.mma reads. K is ordered (q, c, p1, p2) — the image's own
-// memory order, so every gathered run is a contiguous row segment of a patch — and the weight's K axis is
-// permuted once on the host to match (never the data).
-// B operand (D x Kpad weights): TMA, K-major. Accumulators: double-buffered TMEM. Epilogue: shared with gemm.cu.
+// K is ordered (q, c, p1, p2) — the image's own memory order, so every gathered run is a contiguous row segment of a
+// patch — and the weight's K axis is permuted once on the host to match (never the data). Two kernels:
+//  * patch_embed_tmem_kernel (K <= 768, p % 8 == 0, D % 128 == 0: every ViT-*/16 configuration): the gathered bf16 rows of
+//    a 128-token tile are written ONCE into tensor memory (tcgen05.st) and are the A operand of all D / 64 column passes
+//    (tcgen05.mma with A from TMEM); weights stream through a TMA ring, multicast inside a 4-CTA cluster.
+//  * patch_embed_fwd_kernel (everything else: pixel-level p = 1 tokenizers, small pre-patches, long K): A tiles gathered
+//    by 8 producer warps (two groups alternating pipeline stages) into the 128-byte-swizzled K-major shared-memory
+//    layout, weights by TMA, double-buffered TMEM accumulators.
+// Both convert fp32 -> bf16 in registers and fuse bias (+ position rows) in a row-per-lane epilogue.
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
 #include "sfcvit.h"
