@@ -102,14 +102,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_b200_model(c, device):
+def build_b200_model(c, device, curve="hilbert"):
+    from src.curves import space_filling_curves as sc
     from src.models.vit import VisionTransformer
     from src.tokenizers.multiscale.multi_hilbert import SFCEmbedding1D
+    from src.tokenizers.multiscale.multi_zigzag import RasterScan1DGroupedEmbedding
     torch.manual_seed(42)                                    # main.py:151-152
     prev = torch.get_default_dtype()
     torch.set_default_dtype(torch.bfloat16)                  # main.py:157: parameters, buffers and optimizer state in bf16
     try:
-        tok = SFCEmbedding1D(c["img"], c["patch"], 1, 3, c["D"])          # embed-and-prune Hilbert on the patch grid
+        if curve == "raster":
+            tok = RasterScan1DGroupedEmbedding(c["img"], c["patch"], 1, 3, c["D"])
+        else:                                                             # embed-and-prune curve on the patch grid
+            fn = {"hilbert": sc.hilbert_curve, "morton": sc.z_curve, "peano": sc.peano_curve, "moore": sc.moore_curve}[curve]
+            tok = SFCEmbedding1D(c["img"], c["patch"], 1, 3, c["D"], curve_fn=fn)
         model = VisionTransformer(patch_embed=tok, depth=c["depth"], n_heads=c["heads"], mlp_dim=c["mlp"],
                                   num_classes=c["classes"]).to(device)
     finally:
@@ -180,6 +186,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="vit_b16_224", choices=sorted(CONFIGS))
+    ap.add_argument("--curve", default="hilbert", choices=["hilbert", "morton", "peano", "moore", "raster"],
+                    help="token order (BASELINE.json config 3: Hilbert vs Morton vs raster); the headline metric is hilbert")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: config)")
     ap.add_argument("--cpu-batch", type=int, default=16, help="batch of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -207,7 +215,7 @@ def main():
     B = args.batch or c["batch"]
     classes = c["classes"]
 
-    model = build_b200_model(c, device)
+    model = build_b200_model(c, device, args.curve)
     if args.no_dropout:
         for m in model.modules():
             if isinstance(m, torch.nn.Dropout):
@@ -381,7 +389,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.config} generalised-Hilbert (embed-and-prune) tokens, training step fwd+bwd+clip+AdamW",
+            "config": {"workload": f"{args.config} " + ("generalised-Hilbert (embed-and-prune)" if args.curve == "hilbert" else args.curve) + " tokens, training step fwd+bwd+clip+AdamW",
                        "batch_per_gpu": B, "global_batch": B * world, "tokens": (c["img"] // c["patch"]) ** 2,
                        "dropout": not args.no_dropout, "params_dtype": "bf16", "parallelism": f"dp{world}",
                        "launch": "eager" if graphed is None else "forward+backward replayed from one CUDA graph; optimizer eager",
