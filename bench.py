@@ -35,6 +35,8 @@ CONFIGS = {
     "vit_s16_224": dict(img=224, patch=16, D=384, depth=12, heads=6, mlp=1536, classes=1000, batch=256),
     "vit_l16_384": dict(img=384, patch=16, D=1024, depth=24, heads=16, mlp=4096, classes=1000, batch=64),
     "vit_tiny4_32": dict(img=32, patch=4, D=192, depth=12, heads=3, mlp=768, classes=10, batch=1024),
+    # BASELINE.json configs[4]: 64 x 64 patch grid, 4096 tokens per image — inference only (--mode infer)
+    "vit_b16_1024": dict(img=1024, patch=16, D=768, depth=12, heads=12, mlp=3072, classes=1000, batch=4),
 }
 METRIC = "ViT-B/16 224px Hilbert images/sec fwd+bwd"
 
@@ -164,12 +166,16 @@ def run_reference_arm(args, c):
     if rank != 0:
         return
     batch = args.cpu_batch
-    ips, sec, threads = cpu_reference_throughput(c, max(1, args.steps), max(0, min(args.warmup, 1)), batch)
+    infer = args.mode == "infer"
+    if infer:
+        ips, sec, threads, batch = cpu_reference_forward(c, max(1, args.steps), max(0, min(args.warmup, 1)), batch)
+    else:
+        ips, sec, threads = cpu_reference_throughput(c, max(1, args.steps), max(0, min(args.warmup, 1)), batch)
     line = {
-        "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "metric": f"{args.config} {args.curve} images/sec fwd (bf16 inference)" if infer else METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": "reference",
-        "config": {"workload": f"{args.config} Hilbert(embed-and-prune) train step fwd+bwd+clip+AdamW, CPU oracle port of the reference path",
+        "config": {"workload": f"{args.config} Hilbert(embed-and-prune) " + ("inference forward" if infer else "train step fwd+bwd+clip+AdamW") + ", CPU oracle port of the reference path",
                    "batch_per_step": batch},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} steps of batch {batch} (fp32, {threads} threads)"},
@@ -179,6 +185,191 @@ def run_reference_arm(args, c):
     print(json.dumps(line), flush=True)
 
 
+def run_infer(args, c):
+    """`--mode infer`: forward only (eval, no_grad, bf16 parameters), BASELINE.json configs[1] (ViT-S/16 224) and
+    configs[4] (ViT-B/16 1024 px, 4096 tokens). Replicas only for N > 1 (no collective on the data path). The forward is
+    replayed from one CUDA graph over rotating input batches; `roofline` is per kernel family (GEMM, attention, patch
+    embed) from an eager replica timed with CUDA events around each launch."""
+    import torch.distributed as dist
+    from sfcvit import ops
+    from src.training import distributed as D
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (B200); there is no CPU fallback")
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    rank, world = D.init_from_env("nccl")
+    B = args.batch or c["batch"]
+    N = (c["img"] // c["patch"]) ** 2
+    model = build_b200_model(c, device, args.curve).eval()
+    g = torch.Generator(device=device).manual_seed(1234 + rank)
+    img_bytes = B * 3 * c["img"] ** 2 * 4
+    n_bufs = max(4, -(-3 * 126_000_000 // img_bytes))                  # rotating inputs: together > 3 x L2
+    n_bufs = min(n_bufs, 64)
+    dev_imgs = [torch.randn(B, 3, c["img"], c["img"], generator=g, device=device) for _ in range(n_bufs)]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(args.warmup):
+            model(dev_imgs[i % n_bufs])
+        sync_all()
+        ops.GEMM_PROFILE, ops.PE_PROFILE, ops.ATTN_PROFILE = [], [], []
+        roof_steps = min(3, max(1, args.steps))
+        l0 = ops.LAUNCHES
+        for i in range(roof_steps):
+            model(dev_imgs[i % n_bufs])
+        sync_all()
+        launches_per_step = (ops.LAUNCHES - l0) // roof_steps
+        gprof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+        pprof, ops.PE_PROFILE = ops.PE_PROFILE, None
+        aprof, ops.ATTN_PROFILE = ops.ATTN_PROFILE, None
+
+        static_in = torch.empty_like(dev_imgs[0])
+        graph = None
+        if not args.no_graph:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                model(static_in.normal_())
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = model(static_in)
+
+        def step(images):
+            if graph is None:
+                return model(images)
+            static_in.copy_(images, non_blocking=True)
+            graph.replay()
+            return static_out
+
+        for i in range(2):
+            step(dev_imgs[i % n_bufs])
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        for i in range(args.steps):
+            out = step(dev_imgs[i % n_bufs])
+        e1.record()
+        sync_all()
+        clocks = sampler.stop() if rank == 0 else None
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        value = world * B * args.steps / (ms_total * 1e-3)
+
+        # end to end: pinned host images -> H2D, logits -> host, every step
+        host_imgs = [torch.randn(B, 3, c["img"], c["img"]).pin_memory() for _ in range(2)]
+        host_out = torch.empty(B, c["classes"], dtype=torch.bfloat16).pin_memory()
+        stage = [torch.empty_like(static_in) for _ in range(2)]
+        copy_stream = torch.cuda.Stream()
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def prefetch(i):
+            k = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[k])
+                stage[k].copy_(host_imgs[k], non_blocking=True)
+                ready[k].record(copy_stream)
+
+        for k in range(2):
+            consumed[k].record()
+        e2e_steps = max(3, args.steps)
+        sync_all()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        prefetch(0)
+        for i in range(e2e_steps):
+            if i + 1 < e2e_steps:
+                prefetch(i + 1)
+            k = i % 2
+            torch.cuda.current_stream().wait_event(ready[k])
+            out = step(stage[k])
+            consumed[k].record()
+            host_out.copy_(out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()                 # the caller consumes the logits every step
+        t1.record()
+        sync_all()
+        tt = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * e2e_steps / (float(tt.item()) * 1e-3), "unit": "images/s", "h2d_bytes_per_step": img_bytes,
+               "d2h_bytes_per_step": B * c["classes"] * 2, "steps": e2e_steps}
+
+    peaks = load_peaks()
+
+    def fam(prof, name):
+        ms = sum(a.elapsed_time(b) for a, b, *_ in prof)
+        fl = sum(r[-1] for r in prof)
+        tf = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        return {"kernel": name, "ms_per_step": ms / roof_steps, "launches_per_step": len(prof) / roof_steps,
+                "achieved": tf, "frac": tf / peaks["tf_sustained"]}
+    gem = fam(gprof, "gemm_bf16_kernel (tcgen05)")
+    att = fam(aprof, "attn_fwd_kernel (tcgen05 flash attention)")
+    dominant = att if att["ms_per_step"] > gem["ms_per_step"] else gem
+    step_flops = fwd_flops_per_image(c) * B
+    roofline = {"bound": "tensor", "kernel": dominant["kernel"], "achieved": dominant["achieved"], "peak": peaks["tf_sustained"],
+                "unit": "TFLOP/s", "frac": dominant["frac"], "peak_source": peaks["source"] + " (sustained)", "traffic": None,
+                "families": [gem, att],
+                "timed_in": "eager replica of the forward (CUDA events around each launch) run before the timed region",
+                "whole_step_tflops": step_flops / (ms_total / args.steps * 1e-3) / 1e12,
+                "whole_step_frac_of_peak": step_flops / (ms_total / args.steps * 1e-3) / 1e12 / peaks["tf_sustained"]}
+    pe_ms = sum(a.elapsed_time(b_) for a, b_, _, _ in pprof) / max(1, len(pprof))
+    pe_bytes, pe_flops = (pprof[0][2], pprof[0][3]) if pprof else (0, 0)
+    t_roof_ms = max(pe_bytes / (peaks["hbm_gbs"] * 1e9), pe_flops / (peaks["tf_sustained"] * 1e12)) * 1e3
+    patch_embed = {"ms": pe_ms, "algorithmic_bytes": pe_bytes, "achieved_gbs": pe_bytes / (pe_ms * 1e-3) / 1e9 if pe_ms > 0 else 0.0,
+                   "hbm_peak_gbs": peaks["hbm_gbs"], "frac_hbm": (pe_bytes / (pe_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if pe_ms > 0 else 0.0,
+                   "frac_of_max_hbm_tensor_roofline": t_roof_ms / pe_ms if pe_ms > 0 else 0.0, "input_dtype": "fp32"}
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ips, sec, threads, cb = cpu_reference_forward(c, 2, 1, args.cpu_batch)
+        cpu_baseline = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                        "sample": f"2 timed forwards (+1 warm-up) of batch {cb}, fp32, {threads} threads, same model"}
+    if rank == 0:
+        print(json.dumps({
+            "metric": f"{args.config} {args.curve} images/sec fwd (bf16 inference)", "value": value, "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.config} {args.curve} tokens, inference forward (eval, no_grad)", "batch_per_gpu": B,
+                       "global_batch": B * world, "tokens": N, "params_dtype": "bf16", "parallelism": f"replicas x{world}",
+                       "launch": "eager" if graph is None else "forward replayed from one CUDA graph",
+                       "l2_policy": f"{n_bufs} rotating input batches of {img_bytes / 1e6:.0f} MB (together > L2)"},
+            "roofline": roofline, "patch_embed": patch_embed, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step, "clocks": clocks}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_reference_forward(c, steps, warmup, batch):
+    """Forward of the CPU oracle port (stock torch fp32), all host threads; the batch shrinks for long sequences."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    N = (c["img"] // c["patch"]) ** 2
+    batch = max(1, min(batch, 16 * 196 // N)) if N > 196 else batch
+    model = build_oracle_model(c).eval()
+    x = torch.randn(batch, 3, c["img"], c["img"], generator=torch.Generator().manual_seed(0))
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            model(x)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return batch / sec, sec, torch.get_num_threads(), batch
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -186,6 +377,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="vit_b16_224", choices=sorted(CONFIGS))
+    ap.add_argument("--mode", default="train", choices=["train", "infer"],
+                    help="train = the headline metric (fwd+bwd+optimizer); infer = forward only (BASELINE.json configs[1], [4])")
     ap.add_argument("--curve", default="hilbert", choices=["hilbert", "morton", "peano", "moore", "raster"],
                     help="token order (BASELINE.json config 3: Hilbert vs Morton vs raster); the headline metric is hilbert")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: config)")
@@ -195,10 +388,14 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     c = dict(CONFIGS[args.config])
+    if args.config == "vit_b16_1024":
+        args.mode = "infer"                                           # 4096-token config is an inference sweep
     if args.impl == "reference":
         return run_reference_arm(args, c)
     if args.warmup < 3:
         args.warmup = 3
+    if args.mode == "infer":
+        return run_infer(args, c)
 
     import torch.distributed as dist
     from sfcvit import ops

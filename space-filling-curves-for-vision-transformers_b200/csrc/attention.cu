@@ -59,6 +59,19 @@ __device__ __forceinline__ void store_p_chunk(uint8_t* buf, int r, int c32, cons
   }
 }
 
+// same, through a 32-bit shared-window address (st.shared.v4: no generic-address arithmetic in the exp loop)
+__device__ __forceinline__ void store_p_chunk_s32(uint32_t buf, int r, int c32, const float* v) {
+  const uint32_t row = buf + (uint32_t)((c32 >> 1) * kTile + r * 128);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int j8 = (c32 & 1) * 4 + q;                              // 16-byte slot inside the 128-byte row of this atom
+    const uint32_t x = ptx::pack_bf16(v[q * 8 + 0], v[q * 8 + 1]), y = ptx::pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+    const uint32_t z = ptx::pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), w = ptx::pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (uint32_t)((j8 ^ (r & 7)) << 4)), "r"(x), "r"(y), "r"(z), "r"(w)
+                 : "memory");
+  }
+}
+
 // 16 consecutive values (columns c16*16 .. +15 of row r) into the same layout
 __device__ __forceinline__ void store_p_half(uint8_t* buf, int r, int c16, const float* v) {
 #pragma unroll
@@ -116,7 +129,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <bool kSingle>
+template <bool kSingle, bool kDrop>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, const AttnParams p,
                 const FwdLayout L) {
@@ -153,6 +166,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // TMEM region w = columns [w * 256, w * 256 + 256). Single pass: S in [0, bkv <= 208), O overwrites [0, 64).
+  // Multi-tile (bkv <= 192): S in [0, 192), O RESIDENT in [192, 256) across the key tiles of an item.
+  constexpr uint32_t kOCol = kSingle ? 0u : 192u;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -191,7 +207,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int j = g % nkv, ii = g / nkv, st = g % stages;
         if (j == 0) ptx::mbar_wait(&bars[FwdBars::q_full + w], ii & 1);
         ptx::mbar_wait(&bars[FwdBars::k_full + st], (g / stages) & 1);
-        ptx::mbar_wait(&bars[FwdBars::o_empty + w], (g & 1) ^ 1);          // TMEM region w free (O of step g-1 read out)
+        // single pass: S overwrites the columns O(g-1) was read from. Multi-tile: S has its own columns, which are free
+        // once P(g-1) is complete — issue_pv(w, g-1) waited for that just before this call.
+        if constexpr (kSingle) ptx::mbar_wait(&bars[FwdBars::o_empty + w], (g & 1) ^ 1);
         ptx::tc_fence_after();
         const uint64_t dq = umma_smem_desc_sw128(ptx::smem_u32(smem + w * kTile), 0, 1024);
         const uint64_t dk = umma_smem_desc_sw128(ptx::smem_u32(smem + L.off_k + st * kv_bytes), 0, 1024);
@@ -204,9 +222,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       };
       auto issue_pv = [&](int w, int g) {
         const int st = g % stages;
-        ptx::mbar_wait(&bars[FwdBars::p_full + w], g & 1);
+        const int j = g % nkv, ii = g / nkv;
+        if constexpr (kSingle) ptx::mbar_wait(&bars[FwdBars::p_full + w], g & 1);   // multi-tile: the caller waited (once)
         ptx::mbar_wait(&bars[FwdBars::v_full + st], (g / stages) & 1);
+        if constexpr (!kSingle) {
+          if (j == 0) ptx::mbar_wait(&bars[FwdBars::o_empty + w], (ii & 1) ^ 1);   // previous item's O has been read out
+        }
         ptx::tc_fence_after();
+        const uint32_t acc0 = (!kSingle && j > 0) ? 1u : 0u;          // multi-tile: O accumulates in TMEM across key tiles
         const uint32_t sp = ptx::smem_u32(smem + L.off_p + w * L.p_atoms * kTile);
         const uint32_t sv = ptx::smem_u32(smem + L.off_v + st * kv_bytes);
         const uint64_t da0 = umma_smem_desc_sw128(sp, 0, 1024);
@@ -216,8 +239,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
         for (int k = 0; k < 13; ++k)                 // bkv <= 208; descriptor advances are compile-time constants
           if (k < nk)
-            ptx::umma_f16_lohi(tmem_base + w * 256, a_lo + (uint32_t)((k >> 2) * (kTile >> 4) + (k & 3) * 2), a_hi,
-                               b_lo + (uint32_t)(k * 128), b_hi, idesc_o, k > 0 ? 1u : 0u);
+            ptx::umma_f16_lohi(tmem_base + w * 256 + kOCol, a_lo + (uint32_t)((k >> 2) * (kTile >> 4) + (k & 3) * 2), a_hi,
+                               b_lo + (uint32_t)(k * 128), b_hi, idesc_o, k > 0 ? 1u : acc0);
         ptx::umma_commit(&bars[FwdBars::o_full + w]);
         if (w == 1) ptx::umma_commit(&bars[FwdBars::v_empty + st]);
       };
@@ -225,10 +248,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         issue_s(0, 0);
         issue_s(1, 0);
         for (int g = 0; g < total; ++g) {
-          issue_pv(0, g);
-          if (g + 1 < total) issue_s(0, g + 1);
-          issue_pv(1, g);
-          if (g + 1 < total) issue_s(1, g + 1);
+          if constexpr (kSingle) {
+            issue_pv(0, g);
+            if (g + 1 < total) issue_s(0, g + 1);
+            issue_pv(1, g);
+            if (g + 1 < total) issue_s(1, g + 1);
+          } else {
+            // P(g) complete = the S columns are free: the next S goes FIRST (the softmax warps wait for nothing else),
+            // the PV product follows; O lives in its own columns
+            for (int w = 0; w < 2; ++w) {
+              ptx::mbar_wait(&bars[FwdBars::p_full + w], g & 1);
+              if (g + 1 < total) issue_s(w, g + 1);
+              issue_pv(w, g);
+            }
+          }
         }
       }
     }
@@ -243,34 +276,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     uint8_t* p_smem = smem + L.off_p + w * L.p_atoms * kTile;
     const float sl2 = p.scale * kLog2e;
     const DropKey dkey = drop_key(p.drop_seed, p.drop_p, p.drop_epoch);
-    const bool has_drop = p.drop_p > 0.f;
-    int g = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const uint32_t p_s32 = ptx::smem_u32(p_smem);                  // 32-bit shared address: st.shared, no 64-bit address math
+    int g = 0, ii = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ii) {
       const int qp = item % nqp, h = (item / nqp) % p.H, b = item / (nqp * p.H);
       const int q_tile0 = qp * 2 * BQ + w * BQ;
       const int qi = q_tile0 + r;
       const bool warp_active = q_tile0 + quarter * 32 < p.N;     // warp-uniform: at least one valid query row
+      // m_run = the row maximum the probabilities are scaled by. Multi-tile: it is raised (and O, l rescaled) only when
+      // the true maximum exceeds it by more than 2^8 — P stays <= 256, the final O / l is unchanged.
       float m_run = -INFINITY, l_run = 0.f;
-      float o_acc[kSingle ? 1 : DH];
-      if constexpr (!kSingle) {
-#pragma unroll
-        for (int d = 0; d < DH; ++d) o_acc[d] = 0.f;
-      }
       for (int j = 0; j < nkv; ++j, ++g) {
         ptx::mbar_wait(&bars[FwdBars::s_full + w], g & 1);
         ptx::tc_fence_after();
-        float alpha = 1.f;
         if (warp_active) {
           const int kv_valid = min(bkv, p.N - j * bkv);
           const int nch = (kv_valid + 31) / 32;
           // Both passes keep the TMEM load of the next 32-column chunk in flight while the current one is processed
           // (two register buffers, loop unrolled by two so that they stay in registers).
-          float mx = -INFINITY;
+          float mx = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;   // four chains: issue-bound, not latency-bound
           uint32_t ra[32], rb[32];
           auto max_chunk = [&](const uint32_t (&rr)[32], int c) {
             if (c * 32 + 32 <= kv_valid) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rr[i]));
+              for (int i = 0; i < 32; i += 8) {
+                mx = fmaxf(mx, fmaxf(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1])));
+                mx1 = fmaxf(mx1, fmaxf(__uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3])));
+                mx2 = fmaxf(mx2, fmaxf(__uint_as_float(rr[i + 4]), __uint_as_float(rr[i + 5])));
+                mx3 = fmaxf(mx3, fmaxf(__uint_as_float(rr[i + 6]), __uint_as_float(rr[i + 7])));
+              }
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
@@ -278,33 +312,48 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             }
           };
           ptx::tmem_ld_x32(t_s, ra);
-          if constexpr (kSingle) {
 #pragma unroll 1
-            for (int c = 0; c < nch; c += 2) {
+          for (int c = 0; c < nch; c += 2) {
+            ptx::tmem_ld_wait();
+            if (c + 1 < nch) ptx::tmem_ld_x32(t_s + (c + 1) * 32, rb);
+            max_chunk(ra, c);
+            if (c + 1 < nch) {
               ptx::tmem_ld_wait();
-              if (c + 1 < nch) ptx::tmem_ld_x32(t_s + (c + 1) * 32, rb);
-              max_chunk(ra, c);
-              if (c + 1 < nch) {
-                ptx::tmem_ld_wait();
-                if (c + 2 < nch) ptx::tmem_ld_x32(t_s + (c + 2) * 32, ra);
-                max_chunk(rb, c + 1);
-              }
+              if (c + 2 < nch) ptx::tmem_ld_x32(t_s + (c + 2) * 32, ra);
+              max_chunk(rb, c + 1);
             }
-          } else {                                      // o_acc[64] is live here: one buffer only
-#pragma unroll 1
-            for (int c = 0; c < nch; ++c) {
-              ptx::tmem_ld_wait();
-              max_chunk(ra, c);
-              if (c + 1 < nch) ptx::tmem_ld_x32(t_s + (c + 1) * 32, ra);
+          }
+          mx = fmaxf(fmaxf(mx, mx1), fmaxf(mx2, mx3));
+          if constexpr (kSingle) {
+            m_run = mx;
+          } else {
+            if (j == 0) {
+              m_run = mx;
+            } else {
+              // PV(g-1) was issued right after S(g): every o_full phase is consumed exactly once, here or at the item's end
+              ptx::mbar_wait(&bars[FwdBars::o_full + w], (g - 1) & 1);
+              ptx::tc_fence_after();
+              const bool need = (mx - m_run) * sl2 > 8.0f;
+              if (__any_sync(0xffffffffu, need)) {
+                const float alpha = need ? ex2_approx((m_run - mx) * sl2) : 1.0f;
+#pragma unroll
+                for (int c = 0; c < DH / 32; ++c) {
+                  ptx::tmem_ld_x32(t_s + kOCol + c * 32, ra);
+                  ptx::tmem_ld_wait();
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) ra[i] = __float_as_uint(__uint_as_float(ra[i]) * alpha);
+                  ptx::tmem_st_x32(t_s + kOCol + c * 32, ra);
+                  ptx::tmem_st_wait();
+                }
+                l_run *= alpha;
+                if (need) m_run = mx;
+              }
             }
           }
           ptx::tmem_ld_x32(t_s, ra);                    // first chunk of pass 2, in flight during the scalar work below
-          const float m_new = fmaxf(m_run, mx);
-          alpha = ex2_approx((m_run - m_new) * sl2);   // m_run = -inf on the first tile -> 0
-          const float mb = m_new * sl2;
+          const float mb = m_run * sl2;
           float psum = 0.f;
           // dropout index space: (probability row) x (key index, row pitch padded to 16 so that 16-key groups are aligned)
-          const unsigned long long drop_row = (((unsigned long long)(b * p.H + h) * p.N + (unsigned long long)qi) * (unsigned long long)((p.N + 15) & ~15)) + (unsigned long long)(j * bkv);
           const int nch_all = (bkv + 31) / 32;         // P columns read by the PV MMA: [0, bkv)
           auto exp_chunk = [&](const uint32_t (&rr)[32], int c) {
             float pv[32];
@@ -318,95 +367,66 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 psum += pv[i];
               }
             }
-            if (has_drop) drop_apply<32, 16>(pv, dkey, drop_row + (unsigned long long)(c * 32));
-            store_p_chunk(p_smem, r, c, pv);
-          };
-          if constexpr (kSingle) {
-#pragma unroll 1
-            for (int c = 0; c < nch; c += 2) {
-              ptx::tmem_ld_wait();
-              if (c + 1 < nch) ptx::tmem_ld_x32(t_s + (c + 1) * 32, rb);
-              exp_chunk(ra, c);
-              if (c + 1 < nch) {
-                ptx::tmem_ld_wait();
-                if (c + 2 < nch) ptx::tmem_ld_x32(t_s + (c + 2) * 32, ra);
-                exp_chunk(rb, c + 1);
-              }
+            if constexpr (kDrop) {
+              const unsigned long long drop_row = (((unsigned long long)(b * p.H + h) * p.N + (unsigned long long)qi) * (unsigned long long)((p.N + 15) & ~15)) + (unsigned long long)(j * bkv);
+              drop_apply<32, 16>(pv, dkey, drop_row + (unsigned long long)(c * 32));
             }
-          } else {
+            store_p_chunk_s32(p_s32, r, c, pv);
+          };
 #pragma unroll 1
-            for (int c = 0; c < nch; ++c) {
+          for (int c = 0; c < nch; c += 2) {
+            ptx::tmem_ld_wait();
+            if (c + 1 < nch) ptx::tmem_ld_x32(t_s + (c + 1) * 32, rb);
+            exp_chunk(ra, c);
+            if (c + 1 < nch) {
               ptx::tmem_ld_wait();
-              exp_chunk(ra, c);
-              if (c + 1 < nch) ptx::tmem_ld_x32(t_s + (c + 1) * 32, ra);
+              if (c + 2 < nch) ptx::tmem_ld_x32(t_s + (c + 2) * 32, ra);
+              exp_chunk(rb, c + 1);
             }
           }
           for (int c = nch; c < nch_all; ++c) {        // key columns past the sequence end inside [0, bkv)
             float pv[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) pv[i] = 0.f;
-            store_p_chunk(p_smem, r, c, pv);
+            store_p_chunk_s32(p_s32, r, c, pv);
           }
-          l_run = l_run * alpha + psum;
-          m_run = m_new;
+          l_run += psum;
         }
         ptx::tc_fence_before();
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&bars[FwdBars::p_full + w]);
+        // The softmax warps do not stall on a PV product between key tiles: S(g+1) goes to its own columns and O stays in
+        // TMEM; the finished O is normalised and stored from TMEM after the item's last PV.
+        if constexpr (!kSingle) {
+          if (j < nkv - 1) continue;
+        }
         ptx::mbar_wait(&bars[FwdBars::o_full + w], g & 1);
         ptx::tc_fence_after();
         if (warp_active) {
-          if constexpr (kSingle) {
-            // single key tile: O is final, normalise and store straight from TMEM
-            const float inv_l = 1.0f / l_run;
+          const float inv_l = 1.0f / l_run;
 #pragma unroll
-            for (int c = 0; c < DH / 32; ++c) {
-              uint32_t rr[32];
-              ptx::tmem_ld_x32(t_s + c * 32, rr);
-              ptx::tmem_ld_wait();
-              if (qi < p.N) {
-                __nv_bfloat16* op = p.out + (long long)(b * p.N + qi) * p.D + h * DH + c * 32;
+          for (int c = 0; c < DH / 32; ++c) {
+            uint32_t rr[32];
+            ptx::tmem_ld_x32(t_s + kOCol + c * 32, rr);
+            ptx::tmem_ld_wait();
+            if (qi < p.N) {
+              __nv_bfloat16* op = p.out + (long long)(b * p.N + qi) * p.D + h * DH + c * 32;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  uint4 o;
-                  o.x = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 0]) * inv_l, __uint_as_float(rr[q * 8 + 1]) * inv_l);
-                  o.y = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 2]) * inv_l, __uint_as_float(rr[q * 8 + 3]) * inv_l);
-                  o.z = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 4]) * inv_l, __uint_as_float(rr[q * 8 + 5]) * inv_l);
-                  o.w = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 6]) * inv_l, __uint_as_float(rr[q * 8 + 7]) * inv_l);
-                  reinterpret_cast<uint4*>(op)[q] = o;
-                }
+              for (int q = 0; q < 4; ++q) {
+                uint4 o;
+                o.x = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 0]) * inv_l, __uint_as_float(rr[q * 8 + 1]) * inv_l);
+                o.y = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 2]) * inv_l, __uint_as_float(rr[q * 8 + 3]) * inv_l);
+                o.z = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 4]) * inv_l, __uint_as_float(rr[q * 8 + 5]) * inv_l);
+                o.w = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 6]) * inv_l, __uint_as_float(rr[q * 8 + 7]) * inv_l);
+                reinterpret_cast<uint4*>(op)[q] = o;
               }
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < DH / 32; ++c) {
-              uint32_t rr[32];
-              ptx::tmem_ld_x32(t_s + c * 32, rr);
-              ptx::tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha, __uint_as_float(rr[i]));
             }
           }
         }
         ptx::tc_fence_before();
         ptx::mbar_arrive(&bars[FwdBars::o_empty + w]);
       }
-      if (qi < p.N) {
-        if constexpr (!kSingle) {
-          const float inv_l = 1.0f / l_run;
-          __nv_bfloat16* op = p.out + (long long)(b * p.N + qi) * p.D + h * DH;
-#pragma unroll
-          for (int q = 0; q < DH / 8; ++q) {
-            uint4 o;
-            o.x = ptx::pack_bf16(o_acc[q * 8 + 0] * inv_l, o_acc[q * 8 + 1] * inv_l);
-            o.y = ptx::pack_bf16(o_acc[q * 8 + 2] * inv_l, o_acc[q * 8 + 3] * inv_l);
-            o.z = ptx::pack_bf16(o_acc[q * 8 + 4] * inv_l, o_acc[q * 8 + 5] * inv_l);
-            o.w = ptx::pack_bf16(o_acc[q * 8 + 6] * inv_l, o_acc[q * 8 + 7] * inv_l);
-            reinterpret_cast<uint4*>(op)[q] = o;
-          }
-        }
-        if (p.lse) p.lse[((long long)b * p.H + h) * p.N + qi] = m_run * p.scale + logf(l_run);
-      }
+      if (qi < p.N && p.lse) p.lse[((long long)b * p.H + h) * p.N + qi] = m_run * p.scale + logf(l_run);
     }
   }
 
@@ -968,14 +988,19 @@ extern "C" int sfc_attn_fwd(const void* qkv, void* out, float* lse, int B, int H
   p.out = (__nv_bfloat16*)out; p.lse = lse;
   static bool configured = false;
   if (!configured) {
-    SFC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    SFC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    SFC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    SFC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    SFC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    SFC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     configured = true;
   }
   const long long items = (long long)B * H * ((N + 2 * BQ - 1) / (2 * BQ));
   const int grid = (int)(items < sfc_num_sms() ? items : sfc_num_sms());
-  if (L.nkv == 1) attn_fwd_kernel<true><<<grid, kFwdThreads, L.total, stream>>>(tq, tkv, p, L);
-  else attn_fwd_kernel<false><<<grid, kFwdThreads, L.total, stream>>>(tq, tkv, p, L);
+  const bool drop = drop_p > 0.f;
+  if (L.nkv == 1 && drop) attn_fwd_kernel<true, true><<<grid, kFwdThreads, L.total, stream>>>(tq, tkv, p, L);
+  else if (L.nkv == 1) attn_fwd_kernel<true, false><<<grid, kFwdThreads, L.total, stream>>>(tq, tkv, p, L);
+  else if (drop) attn_fwd_kernel<false, true><<<grid, kFwdThreads, L.total, stream>>>(tq, tkv, p, L);
+  else attn_fwd_kernel<false, false><<<grid, kFwdThreads, L.total, stream>>>(tq, tkv, p, L);
   SFC_LAUNCH_OK();
   return 0;
 }

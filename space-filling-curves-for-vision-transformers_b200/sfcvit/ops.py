@@ -15,6 +15,7 @@ CURVE_IDS = {"hilbert_curve": 0, "z_curve": 1, "peano_curve": 2, "moore_curve": 
 LAUNCHES = 0            # kernels launched through the C ABI by this process
 GEMM_PROFILE = None     # when a list: (start_event, end_event, flops) appended per sfc_gemm_bf16 call
 PE_PROFILE = None       # when a list: (start_event, end_event, algorithmic_bytes, flops) per sfc_patch_embed_fwd call
+ATTN_PROFILE = None     # when a list: (start_event, end_event, flops = 4 B H N^2 dh) per sfc_attn_fwd call
 
 
 def _count(n):
@@ -297,9 +298,17 @@ def attn_fwd(qkv, B, H, N, *, scale=None, drop_p=0.0, drop_seed=0):
         scale = (D // H) ** -0.5
     out = torch.empty((B * N, D), dtype=torch.bfloat16, device=qkv.device)
     lse = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)
+    prof = ATTN_PROFILE
     with torch.cuda.device(qkv.device):
-        _lib.check(lib.sfc_attn_fwd(_ptr(qkv), _ptr(out), _ptr(lse), B, H, N, D, float(scale), float(drop_p),
-                                    int(drop_seed) & 0xFFFFFFFFFFFFFFFF, _stream()), "sfc_attn_fwd")
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        rc = lib.sfc_attn_fwd(_ptr(qkv), _ptr(out), _ptr(lse), B, H, N, D, float(scale), float(drop_p),
+                              int(drop_seed) & 0xFFFFFFFFFFFFFFFF, _stream())
+        if prof is not None:
+            e1.record()
+            prof.append((e0, e1, 4.0 * B * N * N * D))
+    _lib.check(rc, "sfc_attn_fwd")
     _count(1)
     return out, lse
 
