@@ -114,10 +114,16 @@ int sfc_interp_concat_bwd(const void* ddst, long long ld_dst, int B, int Nd, int
 /* ---- K2: fused curve-order patch gather + patch-embedding GEMM
  *      (tokenizers: multiscale/multi_hilbert.py:74-84 SFCEmbedding1D.forward and its morton/peano/moore copies,
  *       _1D/hilbert_embedding1D.py:30-43, _2D/hilbert_embedding.py:80-91, _2D/zigzag_embedding.py:24-30) ----
- * img: NCHW fp32 (img_bf16 = 0) or bf16 (1). p = pre-patch size, g = group size, perm = int32 [n_perm] flat
+ * img: NCHW fp32 (img_bf16 = SFC_IMG_F32_NCHW = 0), NCHW bf16 (SFC_IMG_BF16_NCHW = 1) or decoded image bytes, uint8 NHWC
+ * (SFC_IMG_U8_NHWC = 2: the stage before the path, main.py:174-178 ToDtype + Normalize, is then folded into Wk / bias by
+ * the caller; K axis of Wk ordered (q, p1, p2, c) — the reference's own order — and (p*C) % 8 == 0 required).
+ * p = pre-patch size, g = group size, perm = int32 [n_perm] flat
  * pre-patch indices r*(W/p)+c in curve order (n_perm <= (H/p)*(W/p), tokens per image = n_perm / g). Wk: bf16 [D, Kpad], K axis ordered (q, c, p1, p2) and zero padded to
  * Kpad = sfc_patch_embed_kpad(C,p,g). out row of token t of image b: b*rows_per_img + tok_off + t, row stride ld_out
  * (the caller may pre-offset `out` to write a column slice of a wider matrix). pos: optional bf16 [ntok, ld_pos]. */
+#define SFC_IMG_F32_NCHW 0
+#define SFC_IMG_BF16_NCHW 1
+#define SFC_IMG_U8_NHWC 2
 int sfc_patch_embed_kpad(int C, int p, int g);
 int sfc_patch_embed_fwd(const void* img, int img_bf16, int B, int C, int H, int W, int p, int g, const int32_t* perm,
                         int n_perm, const void* Wk, const void* bias, const void* pos, long long ld_pos, void* out, long long ld_out,

@@ -102,9 +102,11 @@ struct FwdLayout {          // runtime shared-memory map (bytes), all tile bases
 
 inline FwdLayout fwd_layout(int N) {
   FwdLayout L;
-  if (N <= 208) { L.bkv = (N + 15) / 16 * 16; L.nkv = 1; L.stages = 1; }
+  static const int max_single = getenv("SFC_ATTN_FWD_MAXSINGLE") ? atoi(getenv("SFC_ATTN_FWD_MAXSINGLE")) : 208;   // tuning knob
+  if (N <= max_single) { L.bkv = (N + 15) / 16 * 16; L.nkv = 1; L.stages = 1; }
   else {
     L.nkv = (N + 191) / 192;
+    if (L.nkv < 2) L.nkv = 2;
     L.bkv = ((N + L.nkv - 1) / L.nkv + 15) / 16 * 16;
     L.stages = 2;
   }
@@ -294,7 +296,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const int nch = (kv_valid + 31) / 32;
           // Both passes keep the TMEM load of the next 32-column chunk in flight while the current one is processed
           // (two register buffers, loop unrolled by two so that they stay in registers).
-          float mx = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;   // four chains: issue-bound, not latency-bound
+          float mx = -INFINITY, mx1 = -INFINITY;   // two chains of 3-input maxima: issue-bound, not latency-bound
           uint32_t ra[32], rb[32];
           auto max_chunk = [&](const uint32_t (&rr)[32], int c) {
             if (c * 32 + 32 <= kv_valid) {
@@ -302,8 +304,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               for (int i = 0; i < 32; i += 8) {
                 mx = fmaxf(mx, fmaxf(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1])));
                 mx1 = fmaxf(mx1, fmaxf(__uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3])));
-                mx2 = fmaxf(mx2, fmaxf(__uint_as_float(rr[i + 4]), __uint_as_float(rr[i + 5])));
-                mx3 = fmaxf(mx3, fmaxf(__uint_as_float(rr[i + 6]), __uint_as_float(rr[i + 7])));
+                mx = fmaxf(mx, fmaxf(__uint_as_float(rr[i + 4]), __uint_as_float(rr[i + 5])));
+                mx1 = fmaxf(mx1, fmaxf(__uint_as_float(rr[i + 6]), __uint_as_float(rr[i + 7])));
               }
             } else {
 #pragma unroll
@@ -323,7 +325,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               max_chunk(rb, c + 1);
             }
           }
-          mx = fmaxf(fmaxf(mx, mx1), fmaxf(mx2, mx3));
+          mx = fmaxf(mx, mx1);
           if constexpr (kSingle) {
             m_run = mx;
           } else {
@@ -354,6 +356,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const float mb = m_run * sl2;
           float psum = 0.f;
           // dropout index space: (probability row) x (key index, row pitch padded to 16 so that 16-key groups are aligned)
+          unsigned long long drop_row = 0;
+          if constexpr (kDrop)
+            drop_row = (((unsigned long long)(b * p.H + h) * p.N + (unsigned long long)qi) * (unsigned long long)((p.N + 15) & ~15)) + (unsigned long long)(j * bkv);
           const int nch_all = (bkv + 31) / 32;         // P columns read by the PV MMA: [0, bkv)
           auto exp_chunk = [&](const uint32_t (&rr)[32], int c) {
             float pv[32];
@@ -367,10 +372,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 psum += pv[i];
               }
             }
-            if constexpr (kDrop) {
-              const unsigned long long drop_row = (((unsigned long long)(b * p.H + h) * p.N + (unsigned long long)qi) * (unsigned long long)((p.N + 15) & ~15)) + (unsigned long long)(j * bkv);
-              drop_apply<32, 16>(pv, dkey, drop_row + (unsigned long long)(c * 32));
-            }
+            if constexpr (kDrop) drop_apply<32, 16>(pv, dkey, drop_row + (unsigned long long)(c * 32));
             store_p_chunk_s32(p_s32, r, c, pv);
           };
 #pragma unroll 1

@@ -254,15 +254,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
-// out[m,n] (bf16 or fp32) = (accumulate ? out : 0) + sum_s ws[s,m,n]
+// out[m,n] (bf16 or fp32) = (accumulate ? out : 0) + act(alpha * sum_s ws[s,m,n] + bias[n])
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, long long split_stride, int splits, void* __restrict__ out,
-                                     long long ld_out, int M, int N, int out_fp32, int accumulate) {
+                                     long long ld_out, int M, int N, int out_fp32, int accumulate, float alpha,
+                                     const __nv_bfloat16* __restrict__ bias, int act) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)M * N;
   if (idx >= total) return;
   const long long m = idx / N, n = idx % N;
   float s = 0.f;
   for (int k = 0; k < splits; ++k) s += ws[k * split_stride + idx];
+  s *= alpha;
+  if (bias) s += __bfloat162float(bias[n]);
+  if (act == SFC_ACT_RELU) s = fmaxf(s, 0.f);
+  else if (act == SFC_ACT_GELU) s = gelu_erf(s);
   if (out_fp32) {
     float* o = reinterpret_cast<float*>(out) + m * ld_out + n;
     *o = accumulate ? (*o + s) : s;
@@ -371,8 +376,11 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
 
   GemmParams pk = p;
   if (splits > 1) {
-    SFC_REQUIRE(!e.bias && !e.residual && e.aux_mode == SFC_AUX_NONE && e.act == SFC_ACT_NONE && !e.out_pre && e.drop_p == 0.f,
-                "sfc_gemm_bf16: split-K supports only a plain (optionally accumulating) epilogue");
+    // bias and activation are applied by the reduce kernel (skinny weight-streaming GEMMs: the factorised head at small
+    // batch); residual / aux / dropout / pre-activation copies stay single-pass only
+    SFC_REQUIRE(!e.residual && e.aux_mode == SFC_AUX_NONE && !e.out_pre && e.drop_p == 0.f && !(ep->accumulate && (e.bias || e.act != SFC_ACT_NONE)),
+                "sfc_gemm_bf16: split-K supports alpha, bias and an activation (or plain accumulation) only");
+    pk.epi.bias = nullptr; pk.epi.act = SFC_ACT_NONE; pk.epi.alpha = 1.0f;
     const size_t need = (size_t)splits * (size_t)M * (size_t)N * sizeof(float);
     SFC_REQUIRE(workspace && workspace_bytes >= need, "sfc_gemm_bf16: split-K workspace too small (%zu < %zu)", workspace_bytes, need);
     pk.epi.out = workspace; pk.epi.out_fp32 = 1; pk.epi.ld_out = N; pk.epi.split_stride = (long long)M * N;
@@ -435,7 +443,8 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
     const long long total = (long long)M * N;
     const int threads = 256;
     splitk_reduce_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(
-        (const float*)workspace, (long long)M * N, splits, ep->out, ep->ld_out, M, N, ep->out_fp32, ep->accumulate);
+        (const float*)workspace, (long long)M * N, splits, ep->out, ep->ld_out, M, N, ep->out_fp32, ep->accumulate, ep->alpha,
+        (const __nv_bfloat16*)ep->bias, ep->act);
     SFC_LAUNCH_OK();
   }
   return 0;

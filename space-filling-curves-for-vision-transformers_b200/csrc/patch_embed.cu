@@ -34,6 +34,7 @@ struct PatchParams {
   const void* img;
   const int* perm;       // [ntok * g] flat pre-patch index r*gw + c in curve order
   int B, C, H, W, p, g, gw;
+  int in_fmt;            // SFC_IMG_F32_NCHW / SFC_IMG_BF16_NCHW / SFC_IMG_U8_NHWC
   int ntok, K, Kpad;
   long long M;           // B * ntok
   int num_m_tiles, num_n_tiles, num_k_blocks;
@@ -70,6 +71,50 @@ __device__ __forceinline__ uint4 pack8f(const float* f) {
   return u;
 }
 
+// Input formats (template parameter IN): 0 = fp32 NCHW, 1 = bf16 NCHW, 2 = uint8 NHWC (decoded image bytes; the
+// (x / 255 - mean) / std normalisation is folded into the weight and bias on the host, the kernel converts exactly).
+constexpr int IN_F32 = 0, IN_BF16 = 1, IN_U8 = 2;
+
+struct ChunkRaw { uint4 a, b; };      // 8 consecutive K elements as loaded: fp32 a+b, bf16 a, uint8 a.x / a.y
+
+template <int IN>
+__device__ __forceinline__ void chunk_load(ChunkRaw& r, const void* img, long long off) {
+  if constexpr (IN == IN_BF16) {
+    r.a = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(img) + off));
+  } else if constexpr (IN == IN_F32) {
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(img) + off);
+    r.a = __ldg(src);
+    r.b = __ldg(src + 1);
+  } else {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(img) + off));
+    r.a.x = v.x; r.a.y = v.y;
+  }
+}
+
+// byte k of w as an exact float: 0x4B000000 | byte is 2^23 + byte
+__device__ __forceinline__ float u8_to_f32(uint32_t w, uint32_t sel) {
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f;
+}
+
+template <int IN>
+__device__ __forceinline__ uint4 chunk_pack(const ChunkRaw& r) {
+  uint4 o;
+  if constexpr (IN == IN_BF16) {
+    o = r.a;
+  } else if constexpr (IN == IN_F32) {
+    o.x = ptx::pack_bf16(__uint_as_float(r.a.x), __uint_as_float(r.a.y));
+    o.y = ptx::pack_bf16(__uint_as_float(r.a.z), __uint_as_float(r.a.w));
+    o.z = ptx::pack_bf16(__uint_as_float(r.b.x), __uint_as_float(r.b.y));
+    o.w = ptx::pack_bf16(__uint_as_float(r.b.z), __uint_as_float(r.b.w));
+  } else {
+    o.x = ptx::pack_bf16(u8_to_f32(r.a.x, 0x7650u), u8_to_f32(r.a.x, 0x7651u));
+    o.y = ptx::pack_bf16(u8_to_f32(r.a.x, 0x7652u), u8_to_f32(r.a.x, 0x7653u));
+    o.z = ptx::pack_bf16(u8_to_f32(r.a.y, 0x7650u), u8_to_f32(r.a.y, 0x7651u));
+    o.w = ptx::pack_bf16(u8_to_f32(r.a.y, 0x7652u), u8_to_f32(r.a.y, 0x7653u));
+  }
+  return o;
+}
+
 // Chunk-offset table (vectorised path, p % 8 == 0): K is ordered (q, c, p1, p2), so the image offset of the 8-element
 // chunk j of k-block kb relative to the origin of pre-patch q is the same for EVERY token:
 //   tbl[kb * 8 + j] = c * H * W + p1 * W + p2   (or -1 past K),   tblq[kb] = q   (p * p % 64 == 0: one (q, c) per k-block)
@@ -80,8 +125,13 @@ __device__ __forceinline__ void build_chunk_table(const PatchParams& pp, int* tb
     const int k0 = i * 8;
     int v = -1;
     if (k0 < pp.K) {
-      const int p2 = k0 % p, t1 = k0 / p, p1 = t1 % p, t2 = t1 / p, c = t2 % pp.C;
-      v = c * pp.H * pp.W + p1 * pp.W + p2;
+      if (pp.in_fmt == SFC_IMG_U8_NHWC) {            // K ordered (q, p1, p2, c): a patch row is p * C contiguous bytes
+        const int rl = p * pp.C, e = k0 % rl, p1 = (k0 / rl) % p;
+        v = p1 * pp.W * pp.C + e;
+      } else {
+        const int p2 = k0 % p, t1 = k0 / p, p1 = t1 % p, t2 = t1 / p, c = t2 % pp.C;
+        v = c * pp.H * pp.W + p1 * pp.W + p2;
+      }
     }
     tbl[i] = v;
   }
@@ -94,51 +144,37 @@ __device__ __forceinline__ long long patch_origin(const PatchParams& pp, long lo
   const int t = (int)(m % pp.ntok);
   const int idx = __ldg(pp.perm + t * pp.g + q);
   const int r = idx / pp.gw, cc = idx % pp.gw;
+  if (pp.in_fmt == SFC_IMG_U8_NHWC) return ((long long)b * pp.H * pp.W + (long long)(r * pp.p) * pp.W + cc * pp.p) * pp.C;
   return (long long)b * pp.C * pp.H * pp.W + (long long)(r * pp.p) * pp.W + cc * pp.p;
 }
 
 // Gathers the 64 K-elements [kb*64, kb*64+64) of one token row into its 128-byte swizzled smem row (vectorised path).
 // `origin` = patch_origin of the k-block's q for this row (ignored when !row_ok).
-template <bool BF16IN>
+template <int IN>
 __device__ __forceinline__ void gather_row_vec(const PatchParams& pp, bool row_ok, long long origin, int row, int kb, const int* tbl,
                                                uint8_t* smem_a) {
   uint8_t* srow = smem_a + row * 128;
   const int sw = row & 7;
-  uint4 raw[8][BF16IN ? 1 : 2];
+  ChunkRaw raw[8];
   int off[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     off[j] = tbl[kb * 8 + j];                     // broadcast shared-memory read
-    if (row_ok && off[j] >= 0) {
-      if constexpr (BF16IN) {
-        raw[j][0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(pp.img) + origin + off[j]));
-      } else {
-        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(pp.img) + origin + off[j]);
-        raw[j][0] = __ldg(src);
-        raw[j][1] = __ldg(src + 1);
-      }
-    }
+    if (row_ok && off[j] >= 0) chunk_load<IN>(raw[j], pp.img, origin + off[j]);
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     uint4 o = make_uint4(0, 0, 0, 0);
-    if (row_ok && off[j] >= 0) {
-      if constexpr (BF16IN) {
-        o = raw[j][0];
-      } else {
-        o.x = ptx::pack_bf16(__uint_as_float(raw[j][0].x), __uint_as_float(raw[j][0].y));
-        o.y = ptx::pack_bf16(__uint_as_float(raw[j][0].z), __uint_as_float(raw[j][0].w));
-        o.z = ptx::pack_bf16(__uint_as_float(raw[j][1].x), __uint_as_float(raw[j][1].y));
-        o.w = ptx::pack_bf16(__uint_as_float(raw[j][1].z), __uint_as_float(raw[j][1].w));
-      }
-    }
+    if (row_ok && off[j] >= 0) o = chunk_pack<IN>(raw[j]);
     *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = o;
   }
 }
 
 // Generic element-wise gather (any p, g): pixel-level tokenizers (p = 1) and small pre-patches.
-template <bool BF16IN>
+template <int IN>
 __device__ __forceinline__ void gather_row(const PatchParams& pp, long long m, int row, int kb, uint8_t* smem_a) {
+  static_assert(IN != IN_U8, "uint8 NHWC input is served by the vectorised paths only");
+  constexpr bool BF16IN = IN == IN_BF16;
   uint8_t* srow = smem_a + row * 128;
   const int sw = row & 7;
   if (m >= pp.M) {
@@ -192,7 +228,7 @@ __device__ __forceinline__ void gather_row(const PatchParams& pp, long long m, i
   }
 }
 
-template <int BN, int kStages, bool VEC, bool BF16IN, bool FAST_EPI>
+template <int BN, int kStages, bool VEC, int IN, bool FAST_EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 patch_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchParams pp) {
   static_assert(kStages % 2 == 0, "producer groups alternate stages by parity");
@@ -316,8 +352,8 @@ patch_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchPa
           if (row_ok && q != cur_q && q < pp.g) { origin = patch_origin(pp, m, q); cur_q = q; }
         }
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-        if constexpr (VEC) gather_row_vec<BF16IN>(pp, row_ok, origin, row, kb, tbl, smem + stage * L::kStageBytes);
-        else gather_row<BF16IN>(pp, m, row, kb, smem + stage * L::kStageBytes);
+        if constexpr (VEC) gather_row_vec<IN>(pp, row_ok, origin, row, kb, tbl, smem + stage * L::kStageBytes);
+        else if constexpr (IN != IN_U8) gather_row<IN>(pp, m, row, kb, smem + stage * L::kStageBytes);
         ptx::fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (ptx::elect_one()) ptx::mbar_arrive(&full_bar[stage]);
@@ -362,7 +398,7 @@ struct PeTmSmem {
   static_assert(kTotal <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
 };
 
-template <bool BF16IN, int CL>
+template <int IN, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 patch_embed_tmem_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchParams pp) {
   using L = PeTmSmem;
@@ -543,35 +579,18 @@ patch_embed_tmem_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchP
       for (int kb = group; kb < nkb; kb += 2) {
         const int q = tblq[kb];
         if (row_ok && q != cur_q && q < pp.g) { origin = patch_origin(pp, m, q); cur_q = q; }
-        uint4 raw[8][BF16IN ? 1 : 2];
+        ChunkRaw raw[8];
         int off[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           off[j] = tbl[kb * 8 + j];
-          if (row_ok && off[j] >= 0) {
-            if constexpr (BF16IN) {
-              raw[j][0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(pp.img) + origin + off[j]));
-            } else {
-              const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(pp.img) + origin + off[j]);
-              raw[j][0] = __ldg(src);
-              raw[j][1] = __ldg(src + 1);
-            }
-          }
+          if (row_ok && off[j] >= 0) chunk_load<IN>(raw[j], pp.img, origin + off[j]);
         }
         uint32_t packed[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           uint4 o = make_uint4(0, 0, 0, 0);
-          if (row_ok && off[j] >= 0) {
-            if constexpr (BF16IN) {
-              o = raw[j][0];
-            } else {
-              o.x = ptx::pack_bf16(__uint_as_float(raw[j][0].x), __uint_as_float(raw[j][0].y));
-              o.y = ptx::pack_bf16(__uint_as_float(raw[j][0].z), __uint_as_float(raw[j][0].w));
-              o.z = ptx::pack_bf16(__uint_as_float(raw[j][1].x), __uint_as_float(raw[j][1].y));
-              o.w = ptx::pack_bf16(__uint_as_float(raw[j][1].z), __uint_as_float(raw[j][1].w));
-            }
-          }
+          if (row_ok && off[j] >= 0) o = chunk_pack<IN>(raw[j]);
           packed[j * 4 + 0] = o.x; packed[j * 4 + 1] = o.y; packed[j * 4 + 2] = o.z; packed[j * 4 + 3] = o.w;
         }
         ptx::mbar_wait_sleep(&a_empty[kb], (it & 1) ^ 1, 64);   // long wait (the previous tile's last passes)
@@ -594,11 +613,11 @@ patch_embed_tmem_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchP
   }
 }
 
-template <bool BF16IN, int CL>
+template <int IN, int CL>
 int launch_pe_tmem(const void* Wk, int D, const PatchParams& pp, cudaStream_t stream) {
   CUtensorMap tw;
   if (int err = sfc_make_tmap_2d(&tw, Wk, 2, (uint64_t)pp.Kpad, (uint64_t)D, (uint64_t)pp.Kpad * 2, BK, (uint32_t)(kTmBN / CL), true)) return err;
-  auto kern = patch_embed_tmem_kernel<BF16IN, CL>;
+  auto kern = patch_embed_tmem_kernel<IN, CL>;
   static int max_clusters = 0;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(kThreads);
@@ -624,8 +643,9 @@ int launch_pe_tmem(const void* Wk, int D, const PatchParams& pp, cudaStream_t st
 
 // A-only gather: writes the curve-ordered im2col matrix A[M, Kpad] (bf16). Used by the backward pass
 // (weight gradient) only; the forward never materialises it.
-template <bool BF16IN, bool VEC>
+template <int IN, bool VEC>
 __global__ void __launch_bounds__(256) patch_gather_kernel(const PatchParams pp, __nv_bfloat16* __restrict__ A) {
+  constexpr bool BF16IN = IN == IN_BF16;
   const int cpr = pp.Kpad / 8;                                   // 8-element chunks per row
   const long long total = pp.M * (long long)cpr;
   const int p = pp.p;
@@ -638,22 +658,23 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const PatchParams pp,
     if constexpr (VEC) {
       // p % 8 == 0: the chunk is one contiguous run inside a patch row
       if (k0 < pp.K) {
-        const int p2 = k0 % p, t1 = k0 / p, p1 = t1 % p, t2 = t1 / p, c = t2 % pp.C, q = t2 / pp.C;
-        const int idx = __ldg(pp.perm + t * pp.g + q);
-        const int r = idx / pp.gw, cc = idx - r * pp.gw;
-        const long long off = ((long long)b * pp.C + c) * plane + (long long)(r * p + p1) * pp.W + cc * p + p2;
-        if constexpr (BF16IN) {
-          o = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(pp.img) + off));
+        long long off;
+        if constexpr (IN == IN_U8) {                  // K ordered (q, p1, p2, c), image NHWC
+          const int rl = p * pp.C, e = k0 % rl, t1 = k0 / rl, p1 = t1 % p, q = t1 / p;
+          const int idx = __ldg(pp.perm + t * pp.g + q);
+          const int r = idx / pp.gw, cc = idx - r * pp.gw;
+          off = (((long long)b * pp.H + (r * p + p1)) * pp.W + cc * p) * pp.C + e;
         } else {
-          const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(pp.img) + off);
-          const uint4 lo = __ldg(src), hi = __ldg(src + 1);
-          o.x = ptx::pack_bf16(__uint_as_float(lo.x), __uint_as_float(lo.y));
-          o.y = ptx::pack_bf16(__uint_as_float(lo.z), __uint_as_float(lo.w));
-          o.z = ptx::pack_bf16(__uint_as_float(hi.x), __uint_as_float(hi.y));
-          o.w = ptx::pack_bf16(__uint_as_float(hi.z), __uint_as_float(hi.w));
+          const int p2 = k0 % p, t1 = k0 / p, p1 = t1 % p, t2 = t1 / p, c = t2 % pp.C, q = t2 / pp.C;
+          const int idx = __ldg(pp.perm + t * pp.g + q);
+          const int r = idx / pp.gw, cc = idx - r * pp.gw;
+          off = ((long long)b * pp.C + c) * plane + (long long)(r * p + p1) * pp.W + cc * p + p2;
         }
+        ChunkRaw raw;
+        chunk_load<IN>(raw, pp.img, off);
+        o = chunk_pack<IN>(raw);
       }
-    } else {
+    } else if constexpr (IN != IN_U8) {
       float f[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -674,9 +695,21 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const PatchParams pp,
   }
 }
 
+// vectorised gather: every 8-element K chunk is one contiguous, aligned run of the image
+bool pe_vec_ok(const void* img, int fmt, int C, int H, int W, int p) {
+  if (fmt == SFC_IMG_U8_NHWC)
+    return ((p * C) % 8 == 0) && ((p * p * C) % 64 == 0) && ((W * C) % 8 == 0) && ((reinterpret_cast<uintptr_t>(img) & 7) == 0) &&
+           ((long long)H * W * C < (1ll << 31));
+  return (p % 8 == 0) && (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0) && (((long long)H * W) % 8 == 0) &&
+         ((long long)C * H * W < (1ll << 31));
+}
+
 int fill_params(PatchParams& pp, const void* img, int img_bf16, int B, int C, int H, int W, int p, int g, const int32_t* perm,
                 int n_perm, int D) {
   SFC_REQUIRE(img && perm, "patch_embed: null pointer");
+  SFC_REQUIRE(img_bf16 == SFC_IMG_F32_NCHW || img_bf16 == SFC_IMG_BF16_NCHW || img_bf16 == SFC_IMG_U8_NHWC,
+              "patch_embed: unknown image format %d", img_bf16);
+  pp.in_fmt = img_bf16;
   SFC_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && p > 0 && g > 0 && D > 0, "patch_embed: bad shape");
   SFC_REQUIRE(H % p == 0 && W % p == 0, "patch_embed: image %dx%d not divisible by pre-patch size %d", H, W, p);
   const int gh = H / p, gw = W / p;
@@ -690,14 +723,16 @@ int fill_params(PatchParams& pp, const void* img, int img_bf16, int B, int C, in
   pp.num_m_tiles = (int)sfc_ceil_div64(pp.M, BM);
   pp.num_k_blocks = pp.Kpad / BK;
   pp.rows_per_img = pp.ntok; pp.tok_off = 0;
-  (void)img_bf16;
+  if (img_bf16 == SFC_IMG_U8_NHWC)
+    SFC_REQUIRE(pe_vec_ok(img, img_bf16, C, H, W, p),
+                "patch_embed: uint8 NHWC input needs (p * C) %% 8 == 0, (p * p * C) %% 64 == 0, (W * C) %% 8 == 0 and an 8-byte aligned buffer (p=%d C=%d W=%d)", p, C, W);
   return 0;
 }
 
-template <int BN, int kStages, bool VEC, bool BF16IN, bool FAST_EPI>
+template <int BN, int kStages, bool VEC, int IN, bool FAST_EPI>
 int launch_pe(const CUtensorMap& tw, const PatchParams& pp, cudaStream_t stream) {
   using L = PeSmem<BN, kStages>;
-  auto kern = patch_embed_fwd_kernel<BN, kStages, VEC, BF16IN, FAST_EPI>;
+  auto kern = patch_embed_fwd_kernel<BN, kStages, VEC, IN, FAST_EPI>;
   static bool configured = false;
   if (!configured) {
     SFC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -730,24 +765,32 @@ extern "C" int sfc_patch_embed_fwd(const void* img, int img_bf16, int B, int C, 
   e.alpha = 1.0f; e.act = SFC_ACT_NONE; e.aux_mode = SFC_AUX_NONE; e.out_fp32 = 0; e.drop_p = 0.f; e.drop_seed = 0; e.drop_epoch = nullptr;
   CUtensorMap tw;
   if (int err = sfc_make_tmap_2d(&tw, Wk, 2, (uint64_t)pp.Kpad, (uint64_t)D, (uint64_t)pp.Kpad * 2, BK, (uint32_t)BN, true)) return err;
-  const bool vec = (p % 8 == 0) && (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0) && (((long long)H * W) % 8 == 0) &&
-                   pp.num_k_blocks <= kMaxTblKb && ((long long)C * H * W < (1ll << 31));
+  const bool vec = pe_vec_ok(img, img_bf16, C, H, W, p) && pp.num_k_blocks <= kMaxTblKb;
+  const bool u8 = img_bf16 == SFC_IMG_U8_NHWC;
+  SFC_REQUIRE(!u8 || vec, "sfc_patch_embed_fwd: uint8 NHWC input with K = %d exceeds the chunk table", pp.K);
   const bool fast = epi_fast_ok(pp.epi);
   static const bool tm_off = getenv("SFC_PE_NOTMEM") != nullptr;
   if (vec && fast && !tm_off && pp.num_k_blocks <= kTmMaxKb && D % (2 * kTmBN) == 0 && D <= kTmMaxD) {
     // TMEM-resident A: gather once per token, 64-column passes over the weights
     pp.num_n_tiles = D / kTmBN;
     static const int cl = getenv("SFC_PE_CLUSTER") ? atoi(getenv("SFC_PE_CLUSTER")) : 4;
-    if (cl == 4 && pp.num_m_tiles >= 4) return img_bf16 ? launch_pe_tmem<true, 4>(Wk, D, pp, stream) : launch_pe_tmem<false, 4>(Wk, D, pp, stream);
-    if (cl >= 2 && pp.num_m_tiles >= 2) return img_bf16 ? launch_pe_tmem<true, 2>(Wk, D, pp, stream) : launch_pe_tmem<false, 2>(Wk, D, pp, stream);
-    return img_bf16 ? launch_pe_tmem<true, 1>(Wk, D, pp, stream) : launch_pe_tmem<false, 1>(Wk, D, pp, stream);
+#define PE_TMEM(CL_)                                                                            \
+  do {                                                                                          \
+    if (u8) return launch_pe_tmem<IN_U8, CL_>(Wk, D, pp, stream);                               \
+    return img_bf16 ? launch_pe_tmem<IN_BF16, CL_>(Wk, D, pp, stream) : launch_pe_tmem<IN_F32, CL_>(Wk, D, pp, stream); \
+  } while (0)
+    if (cl == 4 && pp.num_m_tiles >= 4) PE_TMEM(4);
+    if (cl >= 2 && pp.num_m_tiles >= 2) PE_TMEM(2);
+    PE_TMEM(1);
+#undef PE_TMEM
   }
 #define PE_DISPATCH2(BN_, ST_, F_)                                                              \
   do {                                                                                          \
-    if (vec && img_bf16) return launch_pe<BN_, ST_, true, true, F_>(tw, pp, stream);            \
-    if (vec && !img_bf16) return launch_pe<BN_, ST_, true, false, F_>(tw, pp, stream);          \
-    if (!vec && img_bf16) return launch_pe<BN_, ST_, false, true, F_>(tw, pp, stream);          \
-    return launch_pe<BN_, ST_, false, false, F_>(tw, pp, stream);                               \
+    if (u8) return launch_pe<BN_, ST_, true, IN_U8, F_>(tw, pp, stream);                        \
+    if (vec && img_bf16) return launch_pe<BN_, ST_, true, IN_BF16, F_>(tw, pp, stream);         \
+    if (vec && !img_bf16) return launch_pe<BN_, ST_, true, IN_F32, F_>(tw, pp, stream);         \
+    if (!vec && img_bf16) return launch_pe<BN_, ST_, false, IN_BF16, F_>(tw, pp, stream);       \
+    return launch_pe<BN_, ST_, false, IN_F32, F_>(tw, pp, stream);                              \
   } while (0)
 #define PE_DISPATCH(BN_, ST_)                                                                   \
   do {                                                                                          \
@@ -768,12 +811,13 @@ extern "C" int sfc_patch_gather(const void* img, int img_bf16, int B, int C, int
   long long blocks = sfc_ceil_div64(total, 256);
   const long long cap = 32ll * sfc_num_sms();
   if (blocks > cap) blocks = cap;
-  const bool vec = (p % 8 == 0) && (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0) && (((long long)H * W) % 8 == 0);
+  const bool vec = pe_vec_ok(img, img_bf16, C, H, W, p);
   const unsigned nb = (unsigned)blocks;
-  if (img_bf16 && vec) patch_gather_kernel<true, true><<<nb, 256, 0, stream>>>(pp, (__nv_bfloat16*)A);
-  else if (img_bf16) patch_gather_kernel<true, false><<<nb, 256, 0, stream>>>(pp, (__nv_bfloat16*)A);
-  else if (vec) patch_gather_kernel<false, true><<<nb, 256, 0, stream>>>(pp, (__nv_bfloat16*)A);
-  else patch_gather_kernel<false, false><<<nb, 256, 0, stream>>>(pp, (__nv_bfloat16*)A);
+  if (img_bf16 == SFC_IMG_U8_NHWC) patch_gather_kernel<IN_U8, true><<<nb, 256, 0, stream>>>(pp, (__nv_bfloat16*)A);
+  else if (img_bf16 && vec) patch_gather_kernel<IN_BF16, true><<<nb, 256, 0, stream>>>(pp, (__nv_bfloat16*)A);
+  else if (img_bf16) patch_gather_kernel<IN_BF16, false><<<nb, 256, 0, stream>>>(pp, (__nv_bfloat16*)A);
+  else if (vec) patch_gather_kernel<IN_F32, true><<<nb, 256, 0, stream>>>(pp, (__nv_bfloat16*)A);
+  else patch_gather_kernel<IN_F32, false><<<nb, 256, 0, stream>>>(pp, (__nv_bfloat16*)A);
   SFC_LAUNCH_OK();
   return 0;
 }

@@ -94,9 +94,13 @@ class LinearFn(Function):
             res2 = _bf16_act(residual).reshape(-1, N)
             if not res2.is_contiguous():
                 res2 = res2.contiguous()
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad)   # needs_input_grad ignores no_grad()
         want_pre = act == ACT_GELU and need_grad
-        r = ops.gemm(x2, wb, bias=bb, act=act, residual=res2, want_pre=want_pre, drop_p=drop_p, drop_seed=seed)
+        # skinny weight-streaming GEMM (the factorised head at small batch: M = B rows against W_seq [2D, N * 64]): a single
+        # pass would leave all but N / 256 SMs idle, so K is split (auto factor) and bias + activation run in the reduce
+        skinny = x2.shape[0] <= 128 and K >= 8192 and res2 is None and drop_p == 0.0 and not want_pre
+        r = ops.gemm(x2, wb, bias=bb, act=act, residual=res2, want_pre=want_pre, drop_p=drop_p, drop_seed=seed,
+                     splits=0 if skinny else 1)
         out, pre = r if want_pre else (r, None)
         ctx.act, ctx.drop_p, ctx.seed, ctx.xs = act, drop_p, seed, xs
         ctx.has_res = residual is not None
@@ -168,17 +172,25 @@ class PatchEmbedFn(Function):
     'cp1p2' -> Conv2d weight [D, C, p, p] (_2D/hilbert_embedding.py:18-23)."""
 
     @staticmethod
-    def forward(ctx, img, w_ref, bias, perm32, p, g, k_order, pos):
+    def forward(ctx, img, w_ref, bias, perm32, p, g, k_order, pos, norm=None):
         if not img.is_cuda:
             raise RuntimeError("sfcvit: CUDA tensors only (the B200 path has no CPU fallback)")
-        if img.dtype not in (torch.float32, torch.bfloat16):
+        u8 = img.dtype == torch.uint8
+        if not u8 and img.dtype not in (torch.float32, torch.bfloat16):
             img = img.float()
         img = img.contiguous()
-        B, C, H, W = img.shape
+        C = img.shape[3] if u8 else img.shape[1]
         D = w_ref.shape[0]
         K = g * p * p * C
-        wk = kernel_weight(w_ref, C, p, g, k_order)
-        out = ops.patch_embed_fwd(img, perm32, wk, as_bf16(bias), p, g, pos=as_bf16(pos))
+        if u8:
+            # decoded bytes, NHWC: tokens = W . ((x / 255 - mean) / std) + b  ==  (W * s) . x + (b - W . t) with per-channel
+            # s = 1 / (255 std), t = mean / std — folded into the weight and bias, the kernel reads the bytes as they are
+            wk, bias_k, scale_k, shift_k = kernel_weight_u8(w_ref, bias, C, p, g, k_order, norm)
+            ctx.u8 = (scale_k, shift_k)
+        else:
+            wk, bias_k = kernel_weight(w_ref, C, p, g, k_order), as_bf16(bias)
+            ctx.u8 = None
+        out = ops.patch_embed_fwd(img, perm32, wk, bias_k, p, g, pos=as_bf16(pos))
         ctx.save_for_backward(img, perm32)
         ctx.cfg = (p, g, k_order, C, D, K, w_ref.dtype, tuple(w_ref.shape), bias is not None, pos is not None)
         return out
@@ -193,18 +205,30 @@ class PatchEmbedFn(Function):
         if not d2.is_contiguous():
             d2 = d2.contiguous()
         dw = db = dpos = None
+        if has_bias and ctx.needs_input_grad[2] or (ctx.u8 is not None and ctx.needs_input_grad[1]):
+            db = ops.colsum(d2, w_dtype)
         if ctx.needs_input_grad[1]:
             A = ops.patch_gather(img, perm32, p, g)                       # [M, Kpad] curve-ordered im2col (backward only)
-            dwk = ops.gemm(d2, A, a_mn=True, b_mn=True, out_dtype=w_dtype, splits=0)[:, :K]
-            if k_order == "p1p2c":
-                dw = dwk.reshape(D, g, C, p, p).permute(0, 1, 3, 4, 2).reshape(w_shape)
+            if ctx.u8 is None:
+                dwk = ops.gemm(d2, A, a_mn=True, b_mn=True, out_dtype=w_dtype, splits=0)[:, :K]
+                if k_order == "p1p2c":
+                    dw = dwk.reshape(D, g, C, p, p).permute(0, 1, 3, 4, 2).reshape(w_shape)
+                else:
+                    dw = dwk.reshape(w_shape)
             else:
-                dw = dwk.reshape(w_shape)
-        if has_bias and ctx.needs_input_grad[2]:
-            db = ops.colsum(d2, w_dtype)
+                # A holds the raw bytes (K order q, p1, p2, c): dW[d, k] = s_k * (dOut^T A)[d, k] - t_k * db[d]
+                scale_k, shift_k = ctx.u8
+                G = ops.gemm(d2, A, a_mn=True, b_mn=True, out_dtype=torch.float32, splits=0)[:, :K]
+                dwk = (G * scale_k - db.float()[:, None] * shift_k).to(w_dtype)
+                if k_order == "p1p2c":
+                    dw = dwk.reshape(w_shape)
+                else:                                                    # Conv2d weight [D, C, p, p]
+                    dw = dwk.reshape(D, p, p, C).permute(0, 3, 1, 2).reshape(w_shape)
+        if not (has_bias and ctx.needs_input_grad[2]):
+            db = None
         if has_pos and ctx.needs_input_grad[7]:
             dpos = dout.sum(0)
-        return None, dw, db, None, None, None, None, dpos
+        return None, dw, db, None, None, None, None, dpos, None
 
 
 _wk_cache = {}
@@ -232,8 +256,42 @@ def kernel_weight(w_ref, C, p, g, k_order):
     return wk
 
 
-def patch_embed(img, w_ref, bias, perm32, p, g, k_order="p1p2c", pos=None):
-    return PatchEmbedFn.apply(img, w_ref, bias, perm32, int(p), int(g), k_order, pos)
+_wk_u8_cache = {}
+
+
+def kernel_weight_u8(w_ref, bias, C, p, g, k_order, norm):
+    """uint8 NHWC input: kernel weight bf16 [D, Kpad] with K ordered (q, p1, p2, c) and the per-channel value
+    normalisation folded in, the matching bias, and the fp32 per-k scale / shift vectors the backward needs."""
+    mean, std = norm if norm is not None else (None, None)
+    key = id(w_ref)
+    ver = (w_ref._version, bias._version if bias is not None else -1, id(mean), id(std))
+    ent = _wk_u8_cache.get(key)
+    if ent is not None and ent[0]() is w_ref and ent[1] == ver and ent[2][0].device == w_ref.device:
+        return ent[2]
+    D = w_ref.shape[0]
+    K = g * p * p * C
+    dev = w_ref.device
+    mean_t = torch.zeros(C, device=dev) if mean is None else torch.as_tensor(mean, dtype=torch.float32, device=dev).reshape(C)
+    std_t = torch.ones(C, device=dev) if std is None else torch.as_tensor(std, dtype=torch.float32, device=dev).reshape(C)
+    w = w_ref.detach().float()
+    if k_order == "p1p2c":
+        w = w.reshape(D, K)                                               # already (q, p1, p2, c)
+    else:
+        assert g == 1
+        w = w.reshape(D, C, p, p).permute(0, 2, 3, 1).reshape(D, K)
+    scale_k = (1.0 / (255.0 * std_t)).repeat(K // C)                      # c is the fastest K index
+    shift_k = (mean_t / std_t).repeat(K // C)
+    wk = torch.zeros((D, ops.patch_embed_kpad(C, p, g)), dtype=torch.bfloat16, device=dev)
+    wk[:, :K] = w * scale_k
+    b0 = bias.detach().float() if bias is not None else torch.zeros(D, device=dev)
+    bias_k = (b0 - w @ shift_k).to(torch.bfloat16)
+    out = (wk, bias_k, scale_k, shift_k)
+    _wk_u8_cache[key] = (weakref.ref(w_ref), ver, out)
+    return out
+
+
+def patch_embed(img, w_ref, bias, perm32, p, g, k_order="p1p2c", pos=None, norm=None):
+    return PatchEmbedFn.apply(img, w_ref, bias, perm32, int(p), int(g), k_order, pos, norm)
 
 
 class ConcatStreamsFn(Function):

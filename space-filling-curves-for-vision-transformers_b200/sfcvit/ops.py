@@ -237,14 +237,27 @@ def patch_embed_kpad(C, p, g):
     return _lib.load().sfc_patch_embed_kpad(C, p, g)
 
 
+IMG_F32_NCHW, IMG_BF16_NCHW, IMG_U8_NHWC = 0, 1, 2      # include/sfcvit.h SFC_IMG_*
+
+
+def _img_format(img):
+    """(format code, (B, C, H, W)): float images are NCHW, uint8 images are decoded bytes in NHWC."""
+    if img.dtype == torch.uint8:
+        B, H, W, C = img.shape
+        return IMG_U8_NHWC, (B, C, H, W)
+    B, C, H, W = img.shape
+    return (IMG_BF16_NCHW if img.dtype == torch.bfloat16 else IMG_F32_NCHW), (B, C, H, W)
+
+
 def patch_embed_fwd(img, perm, wk, bias, p, g, *, pos=None, out=None, col_off=0, rows_per_img=None, tok_off=0):
-    """img: [B,C,H,W] fp32/bf16 contiguous; perm int32 [(H/p)*(W/p)]; wk bf16 [D, Kpad] (K order q,c,p1,p2).
+    """img: [B,C,H,W] fp32/bf16 contiguous, or uint8 [B,H,W,C] (then wk's K order is q,p1,p2,c and the value
+    normalisation is folded into wk / bias by the caller); perm int32 [(H/p)*(W/p)]; wk bf16 [D, Kpad] (K order q,c,p1,p2).
     Writes out[b, tok_off + t, col_off : col_off + D]; returns out ([B, rows_per_img, ld] bf16)."""
     lib = _lib.load()
     _require_cuda(img, perm, wk, bias, pos, out)
-    assert img.dim() == 4 and img.is_contiguous() and img.dtype in (torch.float32, torch.bfloat16)
+    assert img.dim() == 4 and img.is_contiguous() and img.dtype in (torch.float32, torch.bfloat16, torch.uint8)
     assert perm.dtype == torch.int32 and wk.dtype == torch.bfloat16 and wk.is_contiguous()
-    B, C, H, W = img.shape
+    fmt, (B, C, H, W) = _img_format(img)
     D, Kpad = wk.shape
     assert Kpad == lib.sfc_patch_embed_kpad(C, p, g)
     ntok = perm.numel() // g
@@ -260,7 +273,7 @@ def patch_embed_fwd(img, perm, wk, bias, p, g, *, pos=None, out=None, col_off=0,
         if prof is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        rc = lib.sfc_patch_embed_fwd(_ptr(img), 1 if img.dtype == torch.bfloat16 else 0, B, C, H, W, p, g, _ptr(perm),
+        rc = lib.sfc_patch_embed_fwd(_ptr(img), fmt, B, C, H, W, p, g, _ptr(perm),
                                      perm.numel(), _ptr(wk), _ptr(bias), _ptr(pos), pos.stride(0) if pos is not None else 0, out_ptr,
                                      out.stride(1), D, rows_per_img, tok_off, _stream())
         if prof is not None:
@@ -275,12 +288,12 @@ def patch_gather(img, perm, p, g):
     """Curve-ordered im2col A[B*ntok, Kpad] bf16 (backward helper)."""
     lib = _lib.load()
     _require_cuda(img, perm)
-    B, C, H, W = img.shape
+    fmt, (B, C, H, W) = _img_format(img)
     Kpad = lib.sfc_patch_embed_kpad(C, p, g)
     ntok = perm.numel() // g
     A = torch.empty((B * ntok, Kpad), dtype=torch.bfloat16, device=img.device)
     with torch.cuda.device(img.device):
-        _lib.check(lib.sfc_patch_gather(_ptr(img), 1 if img.dtype == torch.bfloat16 else 0, B, C, H, W, p, g, _ptr(perm),
+        _lib.check(lib.sfc_patch_gather(_ptr(img), fmt, B, C, H, W, p, g, _ptr(perm),
                                         perm.numel(), _ptr(A), _stream()), "sfc_patch_gather")
     _count(1)
     return A

@@ -23,6 +23,10 @@ class ZigzagEmbedding(BasePatchEmbedding, CurveGatherEmbedding):
 
     def forward(self, x):
         H, W, p = x.shape[-2], x.shape[-1], self.patch_size
-        if H % p or W % p:                       # Conv2d(stride=p) silently drops the ragged border
+        if x.dtype == torch.uint8:                  # decoded bytes [B, H, W, C] (set_uint8_normalization): no ragged border
+            H, W = x.shape[1], x.shape[2]
+            if H % p or W % p:
+                x = x[:, : H // p * p, : W // p * p].contiguous()
+        elif H % p or W % p:                       # Conv2d(stride=p) silently drops the ragged border
             x = x[..., : H // p * p, : W // p * p].contiguous()
         return self._curve_forward(x, self.proj.weight, self.proj.bias, p, 1)

@@ -40,7 +40,18 @@ class CurveGatherEmbedding(nn.Module):
         object.__setattr__(self, "_perm_cache", (src, src._version, perm))
         return perm
 
+    _u8_norm = None          # (mean, std) per channel for uint8 input; None = x / 255
+
+    def set_uint8_normalization(self, mean, std):
+        """Addition to the reference API: lets ``forward`` take the DECODED image bytes — uint8 ``[B, H, W, C]``, what the
+        DataLoader holds before ``ToDtype(float32, scale=True)`` + ``Normalize(mean, std)`` (main.py:174-178). That
+        stage is folded into the projection weight / bias, the kernel gathers the bytes themselves (4x fewer image
+        bytes over PCIe and out of HBM than the fp32 NCHW tensor)."""
+        self._u8_norm = (torch.as_tensor(mean, dtype=torch.float32), torch.as_tensor(std, dtype=torch.float32))
+        return self
+
     def _curve_forward(self, x, weight, bias, pre_patch, group):
         if x.dim() != 4:
-            raise ValueError(f"expected [B, C, H, W], got {tuple(x.shape)}")
-        return SF.patch_embed(x, weight, bias, self._perm32(x.device), pre_patch, group, self._k_order)
+            raise ValueError(f"expected [B, C, H, W] (or uint8 [B, H, W, C]), got {tuple(x.shape)}")
+        return SF.patch_embed(x, weight, bias, self._perm32(x.device), pre_patch, group, self._k_order,
+                              norm=self._u8_norm if x.dtype == torch.uint8 else None)

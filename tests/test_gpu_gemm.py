@@ -39,3 +39,25 @@ def test_gemm_splitk_wgrad_shape(cuda_device, splits):
     assert r["ok"], r
     r = gemm_selftest.run(256, 768, 3000 - 3000 % 8, True, True, "none", splits)
     assert r["ok"], r
+
+
+@pytest.mark.parametrize("act", ["none", "relu", "gelu"])
+def test_gemm_skinny_splitk_bias_activation(cuda_device, act):
+    """Weight-streaming shape of the factorised head at small batch (M = 4 rows, long K): split-K with alpha, bias and
+    the activation applied by the reduce kernel == the single-pass fused epilogue == torch fp32."""
+    import torch
+    from sfcvit import ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    M, N, K = 4, 512, 16384
+    a = (torch.randn(M, K, generator=g, device="cuda") * 0.05).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g, device="cuda") * 0.05).to(torch.bfloat16)
+    b = torch.randn(N, generator=g, device="cuda").to(torch.bfloat16)
+    code = {"none": ops.ACT_NONE, "relu": ops.ACT_RELU, "gelu": ops.ACT_GELU}[act]
+    ref = 0.5 * (a.float() @ w.float().t()) + b.float()
+    ref = {"none": lambda t: t, "relu": torch.relu, "gelu": torch.nn.functional.gelu}[act](ref)
+    from sfcvit import _lib
+    assert _lib.load().sfc_gemm_suggest_splits(M, N, K) > 1
+    y_split = ops.gemm(a, w, bias=b, act=code, alpha=0.5, splits=0)
+    y_one = ops.gemm(a, w, bias=b, act=code, alpha=0.5, splits=1)
+    rel = lambda x: float((x.float() - ref).norm() / ref.norm())
+    assert rel(y_split) < 6e-3 and rel(y_one) < 6e-3, (rel(y_split), rel(y_one))
