@@ -81,7 +81,7 @@ class LinearFn(Function):
     """y = dropout(act(x W^T + b)) (+ residual). Generic building block (mixer, head, fusion layers)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, act, residual, drop_p, seed):
+    def forward(ctx, x, w, b, act, residual, drop_p, seed, grad_mode=True):
         xs = x.shape
         K = xs[-1]
         x2 = _bf16_act(x).reshape(-1, K)
@@ -94,7 +94,7 @@ class LinearFn(Function):
             res2 = _bf16_act(residual).reshape(-1, N)
             if not res2.is_contiguous():
                 res2 = res2.contiguous()
-        need_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad)   # needs_input_grad ignores no_grad()
+        need_grad = grad_mode and any(ctx.needs_input_grad)   # needs_input_grad ignores no_grad(); the caller passes the mode
         want_pre = act == ACT_GELU and need_grad
         # skinny weight-streaming GEMM (the factorised head at small batch: M = B rows against W_seq [2D, N * 64]): a single
         # pass would leave all but N / 256 SMs idle, so K is split (auto factor) and bias + activation run in the reduce
@@ -132,11 +132,11 @@ class LinearFn(Function):
                                      ctx.has_bias and ctx.needs_input_grad[2])
         if dx is not None:
             dx = dx.reshape(ctx.xs)
-        return dx, dw, db, None, d_res, None, None
+        return dx, dw, db, None, d_res, None, None, None
 
 
 def linear(x, w, b=None, act=ACT_NONE, residual=None, drop_p=0.0, seed=0):
-    return LinearFn.apply(x, w, b, act, residual, float(drop_p), int(seed))
+    return LinearFn.apply(x, w, b, act, residual, float(drop_p), int(seed), torch.is_grad_enabled())
 
 
 class LayerNormFn(Function):

@@ -99,3 +99,27 @@ def test_bucketing_and_sharding():
     x = torch.arange(10)
     assert D.shard(x, 1, 2).tolist() == [1, 3, 5, 7, 9] and D.shard(x, 0, 3).tolist() == [0, 3, 6]
     assert D.world() == (0, 1)
+
+
+@pytest.mark.parametrize("k_order", ["p1p2c", "cp1p2"])
+def test_uint8_normalisation_folding(k_order):
+    """Host routine behind the uint8 NHWC input (sfcvit.functional.kernel_weight_u8): (W * s) . bytes + (b - W . t) equals
+    W . ((bytes / 255 - mean) / std) + b, with the K axis in (p1, p2, c) order for both reference weight layouts."""
+    from sfcvit import functional as SF
+    g = torch.Generator().manual_seed(0)
+    D, C, p = 16, 3, 8
+    K = C * p * p
+    mean, std = torch.tensor([0.485, 0.456, 0.406]), torch.tensor([0.229, 0.224, 0.225])
+    w = torch.randn((D, K) if k_order == "p1p2c" else (D, C, p, p), generator=g)
+    b = torch.randn(D, generator=g)
+    wk, bias_k, scale_k, shift_k = SF.kernel_weight_u8(w, b, C, p, 1, k_order, (mean, std))
+    assert wk.dtype == torch.bfloat16 and wk.shape[1] % 64 == 0 and bias_k.dtype == torch.bfloat16
+    patch = torch.randint(0, 256, (5, p, p, C), generator=g).float()            # bytes of 5 patches, (p1, p2, c) order
+    norm = (patch / 255.0 - mean) / std
+    if k_order == "p1p2c":
+        ref = norm.reshape(5, K) @ w.t() + b
+    else:
+        ref = torch.einsum("npqc,dcpq->nd", norm, w) + b
+    got = patch.reshape(5, K) @ wk[:, :K].float().t() + bias_k.float()
+    assert float((got - ref).norm() / ref.norm()) < 1e-2                         # bf16 rounding of the folded weight
+    assert torch.allclose(scale_k.reshape(-1, C)[0], 1.0 / (255.0 * std)) and torch.allclose(shift_k.reshape(-1, C)[0], mean / std)
