@@ -277,6 +277,46 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, long long spl
   }
 }
 
+// the common case (weight gradients: no bias / activation, N and ld_out multiples of 4): 4 columns per thread, 16-byte
+// loads, four independent partial sums so that the loads of a thread are all in flight together
+__global__ void __launch_bounds__(256) splitk_reduce_vec4_kernel(const float4* __restrict__ ws, long long split_stride4, int splits,
+                                                                 void* __restrict__ out, long long ld_out, int M, int N4, int out_fp32,
+                                                                 int accumulate) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * N4) return;
+  const long long m = idx / N4, n = (idx % N4) * 4;
+  float4 a[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int k = 0;
+  for (; k + 4 <= splits; k += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float4 v = __ldg(ws + (long long)(k + u) * split_stride4 + idx);
+      a[u].x += v.x; a[u].y += v.y; a[u].z += v.z; a[u].w += v.w;
+    }
+  }
+  for (; k < splits; ++k) {
+    const float4 v = __ldg(ws + (long long)k * split_stride4 + idx);
+    a[0].x += v.x; a[0].y += v.y; a[0].z += v.z; a[0].w += v.w;
+  }
+  float4 t;
+  t.x = (a[0].x + a[1].x) + (a[2].x + a[3].x); t.y = (a[0].y + a[1].y) + (a[2].y + a[3].y);
+  t.z = (a[0].z + a[1].z) + (a[2].z + a[3].z); t.w = (a[0].w + a[1].w) + (a[2].w + a[3].w);
+  if (out_fp32) {
+    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + m * ld_out + n);
+    if (accumulate) { const float4 p = *o; t.x += p.x; t.y += p.y; t.z += p.z; t.w += p.w; }
+    *o = t;
+  } else {
+    uint2* o = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + m * ld_out + n);
+    if (accumulate) {
+      const uint2 p = *o;
+      t.x += ptx::bf16_lo(p.x); t.y += ptx::bf16_hi(p.x); t.z += ptx::bf16_lo(p.y); t.w += ptx::bf16_hi(p.y);
+    }
+    *o = make_uint2(ptx::pack_bf16(t.x, t.y), ptx::pack_bf16(t.z, t.w));
+  }
+}
+
 // smem ring depth: stage = 48 KB (CL 1) / 32 KB (CL 2) at BN 256, half of the B part at BN 128; EPI >= 3 needs 32 KB more
 constexpr int gemm_stages(int bn, int cl, int epi) {
   const int stage_kb = 16 + (bn / cl) / 8;
@@ -442,7 +482,13 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
   if (splits > 1) {
     const long long total = (long long)M * N;
     const int threads = 256;
-    splitk_reduce_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(
+    const bool vec4 = N % 4 == 0 && ep->ld_out % 4 == 0 && !ep->bias && ep->act == SFC_ACT_NONE && ep->alpha == 1.0f &&
+                      (reinterpret_cast<uintptr_t>(ep->out) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0;
+    if (vec4)
+      splitk_reduce_vec4_kernel<<<(unsigned)((total / 4 + threads - 1) / threads), threads, 0, stream>>>(
+          (const float4*)workspace, (long long)M * N / 4, splits, ep->out, ep->ld_out, M, N / 4, ep->out_fp32, ep->accumulate);
+    else
+      splitk_reduce_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(
         (const float*)workspace, (long long)M * N, splits, ep->out, ep->ld_out, M, N, ep->out_fp32, ep->accumulate, ep->alpha,
         (const __nv_bfloat16*)ep->bias, ep->act);
     SFC_LAUNCH_OK();

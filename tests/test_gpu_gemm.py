@@ -61,3 +61,20 @@ def test_gemm_skinny_splitk_bias_activation(cuda_device, act):
     y_one = ops.gemm(a, w, bias=b, act=code, alpha=0.5, splits=1)
     rel = lambda x: float((x.float() - ref).norm() / ref.norm())
     assert rel(y_split) < 6e-3 and rel(y_one) < 6e-3, (rel(y_split), rel(y_one))
+
+
+@pytest.mark.parametrize("out_dtype", ["fp32", "bf16"])
+def test_gemm_splitk_accumulate(cuda_device, out_dtype):
+    """Split-K with accumulate (out += A^T B, the gradient-accumulation form) through the vectorised reduce kernel."""
+    import torch
+    from sfcvit import ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    M, N, K = 256, 384, 4096
+    a = (torch.randn(K, M, generator=g, device="cuda") * 0.1).to(torch.bfloat16)      # MN-major operands (wgrad shape)
+    b = (torch.randn(K, N, generator=g, device="cuda") * 0.1).to(torch.bfloat16)
+    dt = torch.float32 if out_dtype == "fp32" else torch.bfloat16
+    base = torch.randn(M, N, generator=g, device="cuda").to(dt)
+    out = base.clone()
+    ops.gemm(a, b, a_mn=True, b_mn=True, out=out, splits=4, accumulate=True)
+    ref = base.float() + a.float().t() @ b.float()
+    assert float((out.float() - ref).norm() / ref.norm()) < (1e-4 if out_dtype == "fp32" else 6e-3)
