@@ -72,15 +72,16 @@ __device__ __forceinline__ void store_p_chunk_s32(uint32_t buf, int r, int c32, 
   }
 }
 
-// 16 consecutive values (columns c16*16 .. +15 of row r) into the same layout
-__device__ __forceinline__ void store_p_half(uint8_t* buf, int r, int c16, const float* v) {
+// 16 consecutive values (columns c16*16 .. +15 of row r) into the same layout (buf = 32-bit shared-window address)
+__device__ __forceinline__ void store_p_half(uint32_t buf, int r, int c16, const float* v) {
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     const int j8 = c16 * 2 + q;
-    uint4 o;
-    o.x = ptx::pack_bf16(v[q * 8 + 0], v[q * 8 + 1]); o.y = ptx::pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-    o.z = ptx::pack_bf16(v[q * 8 + 4], v[q * 8 + 5]); o.w = ptx::pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-    *reinterpret_cast<uint4*>(buf + (j8 >> 3) * kTile + r * 128 + (((j8 & 7) ^ (r & 7)) << 4)) = o;
+    const uint32_t x = ptx::pack_bf16(v[q * 8 + 0], v[q * 8 + 1]), y = ptx::pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+    const uint32_t z = ptx::pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), w = ptx::pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + (uint32_t)((j8 >> 3) * kTile + r * 128 + (((j8 & 7) ^ (r & 7)) << 4))),
+                 "r"(x), "r"(y), "r"(z), "r"(w)
+                 : "memory");
   }
 }
 
@@ -372,7 +373,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 psum += pv[i];
               }
             }
-            if constexpr (kDrop) drop_apply<32, 16>(pv, dkey, drop_row + (unsigned long long)(c * 32));
+            if constexpr (kDrop) drop_zero<32, 16>(pv, dkey, drop_row + (unsigned long long)(c * 32));   // 1 / keep: in inv_l below
             store_p_chunk_s32(p_s32, r, c, pv);
           };
 #pragma unroll 1
@@ -405,7 +406,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         ptx::mbar_wait(&bars[FwdBars::o_full + w], g & 1);
         ptx::tc_fence_after();
         if (warp_active) {
-          const float inv_l = 1.0f / l_run;
+          const float inv_l = (kDrop ? dkey.inv_keep : 1.0f) / l_run;   // O = (keep . P / keep_prob) V / l: the mask zeroes, this scales
 #pragma unroll
           for (int c = 0; c < DH / 32; ++c) {
             uint32_t rr[32];
@@ -911,8 +912,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 dsv[e] = pe * scale_ * (dp - delta);       // pe == 0 outside the valid region
               }
             }
-            store_p_half(smem + BwdSmem::kP, r, c * 2 + hf, pv);
-            store_p_half(smem + BwdSmem::kDS, r, c * 2 + hf, dsv);
+            store_p_half(ptx::smem_u32(smem) + BwdSmem::kP, r, c * 2 + hf, pv);
+            store_p_half(ptx::smem_u32(smem) + BwdSmem::kDS, r, c * 2 + hf, dsv);
           }
         }
         SFC_TL(if (dbg) dbg[s * 16 + 5] = clock64();)

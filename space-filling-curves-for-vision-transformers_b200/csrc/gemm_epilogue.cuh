@@ -106,6 +106,27 @@ __device__ __forceinline__ void drop_apply(float* v, const DropKey& k, unsigned 
   }
 }
 
+// mask only: v[i] = keep(base + i) ? v[i] : 0 (the caller applies 1 / keep_prob once, downstream of a linear op)
+template <int NV, int G>
+__device__ __forceinline__ void drop_zero(float* v, const DropKey& k, unsigned long long base) {
+  static_assert(NV % G == 0, "NV must be a multiple of the group size");
+  const uint32_t thr_hi = k.thr16 << 16;
+  if (base % G == 0) {
+#pragma unroll
+    for (int g = 0; g < NV / G; ++g) {
+      const uint32_t seed = drop_hash2(k, base / G + g);
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const uint32_t x = seed * lcg_mul(i + 1) + lcg_add(i + 1);
+        v[g * G + i] = (x >= thr_hi) ? v[g * G + i] : 0.f;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = drop_keep<G>(k, base + i) ? v[i] : 0.f;
+  }
+}
+
 __device__ __forceinline__ void epi_unpack8(const uint4& b, float* f) {
   f[0] = ptx::bf16_lo(b.x); f[1] = ptx::bf16_hi(b.x); f[2] = ptx::bf16_lo(b.y); f[3] = ptx::bf16_hi(b.y);
   f[4] = ptx::bf16_lo(b.z); f[5] = ptx::bf16_hi(b.z); f[6] = ptx::bf16_lo(b.w); f[7] = ptx::bf16_hi(b.w);
