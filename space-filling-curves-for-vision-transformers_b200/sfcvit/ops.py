@@ -267,6 +267,17 @@ def patch_embed_fwd(img, perm, wk, bias, p, g, *, pos=None, out=None, col_off=0,
         out = torch.empty((B, rows_per_img, D), dtype=torch.bfloat16, device=img.device)
     assert out.dtype == torch.bfloat16 and out.stride(-1) == 1 and out.shape[0] == B and out.shape[1] == rows_per_img
     assert out.stride(0) == rows_per_img * out.stride(1)
+    # Pixel-level tokenizers (p = 1, _1D/*_embedding1D.py: a token is g curve-consecutive pixels, K = g * C scalars that
+    # are NOT contiguous in the image): the fused kernel re-gathers a tile for each of its D / 256 column tiles through
+    # per-element loads behind a permutation lookup (1.08 ms at 224 px, 256 px / token, B = 256). Gathering the
+    # curve-ordered bf16 rows ONCE (sfc_patch_gather, consecutive lanes = consecutive curve pixels) and running one K3
+    # GEMM on them takes 0.19 + 0.05 ms and gives bit-identical tokens (tools/pixel_tok_probe.py).
+    if (p == 1 and g * C >= 256 and fmt != IMG_U8_NHWC and pos is None and tok_off == 0 and rows_per_img == ntok
+            and PE_PROFILE is None):
+        A = patch_gather(img, perm, p, g)
+        out2 = out.as_strided((B * ntok, D), (out.stride(1), 1), out.storage_offset() + col_off)
+        gemm(A, wk, bias=bias, out=out2)
+        return out
     out_ptr = ctypes.c_void_p(out.data_ptr() + 2 * col_off)
     prof = PE_PROFILE
     with torch.cuda.device(img.device):

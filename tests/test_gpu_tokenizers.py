@@ -73,3 +73,36 @@ def test_cpu_input_raises(cuda_device):
     sm = cases.build_src_tokenizer(kind, kw)
     with pytest.raises(RuntimeError):
         sm(cases.make_input(shape))
+
+
+@pytest.mark.parametrize("curve,img,px,D", [("hilbert", 64, 128, 256), ("peano", 54, 108, 128), ("z", 224, 256, 768)])
+def test_large_pixel_level_tokenizer(cuda_device, curve, img, px, D):
+    """Pixel-level tokenizers with long tokens (g * C >= 256; the 224-px / 256-pixels-per-token ViT-B equivalent of
+    SURVEY.md §8a a8) run as one curve-ordered gather + one GEMM: tokens and gradients vs the fp32 oracle, and the
+    result is independent of that routing (bit-identical to the fused kernel, which the profiling hook forces)."""
+    from sfcvit import ops
+    kw = dict(curve=curve, img_size=img, patch_size=px, C=3, D=D)
+    torch.manual_seed(cases.INIT_SEED)
+    om = cases.build_oracle_tokenizer("pix", kw)
+    sm = cases.build_src_tokenizer("pix", kw)
+    sm.load_state_dict(om.state_dict())
+    sm = sm.to(cuda_device)
+    B = 2
+    x = cases.make_input((B, 3, img, img))
+    y = sm(x.to(cuda_device))
+    yo = om(x)
+    assert tuple(y.shape) == tuple(yo.shape) == (B, img * img // px, D)
+    assert cases.rel_l2(y, yo) < 6e-3
+    ops.PE_PROFILE = []                                   # the hook times the fused kernel -> forces that path
+    try:
+        with torch.no_grad():
+            y_fused = sm(x.to(cuda_device))
+    finally:
+        ops.PE_PROFILE = None
+    assert torch.equal(y_fused, y)
+    r = cases.make_input(tuple(yo.shape), seed=11)
+    (yo * r).sum().backward()
+    (y.float() * r.to(cuda_device)).sum().backward()
+    go = dict(om.named_parameters())
+    for n, p in sm.named_parameters():
+        assert cases.rel_l2(p.grad, go[n].grad) < 2e-2, n
