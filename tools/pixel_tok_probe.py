@@ -65,5 +65,24 @@ def two_pass(B=256):
     print(f"two-pass: gather {ms_g:.4f} ms + GEMM {ms_m:.4f} ms; max |diff| vs fused {float((got - ref).abs().max()):.3e}")
 
 
+def byte_input(B=256):
+    """The ViT-B/16 patch tokenizer fed fp32 NCHW, bf16 NCHW and the decoded bytes (uint8 NHWC)."""
+    from src.tokenizers.multiscale.multi_hilbert import SFCEmbedding1D
+    dev = torch.device("cuda")
+    tok = SFCEmbedding1D(224, 16, 1, 3, 768).to(dev).to(torch.bfloat16)
+    tok.set_uint8_normalization((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))
+    xs = [torch.randn(B, 3, 224, 224, device=dev) for _ in range(4)]
+    ins = {"fp32 NCHW": xs, "bf16 NCHW": [x.to(torch.bfloat16) for x in xs],
+           "uint8 NHWC": [torch.randint(0, 256, (B, 224, 224, 3), device=dev, dtype=torch.uint8) for _ in range(4)]}
+    with torch.no_grad():
+        for name, arr in ins.items():
+            it = iter(range(10 ** 9))
+            ms = timeit(lambda: tok(arr[next(it) % 4]), iters=20)
+            nbytes = arr[0].numel() * arr[0].element_size() + B * 196 * 768 * 2
+            print(f"patch embed ViT-B/16, {name} input: {ms:.4f} ms  {nbytes / ms / 1e6:.0f} GB/s algorithmic ({nbytes / B} B / image)")
+
+
 if __name__ == "__main__" and os.environ.get("TWO_PASS"):
     two_pass()
+if __name__ == "__main__" and os.environ.get("BYTE_INPUT"):
+    byte_input()
