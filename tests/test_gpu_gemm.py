@@ -8,7 +8,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
 
-SHAPES = [(128, 128, 64), (256, 256, 128), (392, 768, 768), (1000, 2304, 768), (200, 192, 48 + 16), (77, 40, 72)]
+SHAPES = [(128, 128, 64), (256, 256, 128), (392, 768, 768), (1000, 2304, 768), (200, 192, 48 + 16), (77, 40, 72),
+          (392, 384, 384), (264, 640, 128)]      # the last two: several 128-wide column tiles (ViT-S widths)
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
@@ -25,7 +26,7 @@ def test_gemm_layouts(cuda_device, shape, a_mn, b_mn):
 @pytest.mark.parametrize("epi", ["bias_relu", "bias_gelu_pre", "bias_res", "relu_mask_res", "gelu_grad", "fp32"])
 def test_gemm_epilogues(cuda_device, epi):
     import gemm_selftest
-    for (M, N, K) in [(392, 768, 256), (130, 200, 64)]:
+    for (M, N, K) in [(392, 768, 256), (130, 200, 64), (392, 384, 256)]:
         r = gemm_selftest.run(M, N, K, False, False, epi)
         assert r["ok"], r
         if "pre_rel_l2" in r:
