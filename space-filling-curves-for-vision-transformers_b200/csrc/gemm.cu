@@ -365,15 +365,16 @@ extern "C" size_t sfc_gemm_workspace_bytes(int M, int N, int K, int splits) {
 // Column-tile width: 256 (CTA pairs: 256 x 256 per pair) unless more than 15 % of a 256-wide tiling would be padding and a
 // 128-wide one pads less (N = 384, ViT-S: 2 x 256 wastes a quarter of the MMAs and epilogue rows, 3 x 128 none). The
 // ViT-B / ViT-L widths (768, 1024, 2304, 3072, 4096, 1000, 1536) keep 256.
-static int gemm_pick_bn(int N) {
+static int gemm_pick_bn(int N, int K) {
   if (N <= 128) return 128;
+  if (K < 256) return 256;     // very short K (ViT-Tiny, K = 192): per-tile fixed costs dominate, fewer larger tiles win (measured)
   static const bool off = getenv("SFC_GEMM_BN256") != nullptr;
   const long long pad256 = (long long)sfc_ceil_div(N, 256) * 256, pad128 = (long long)sfc_ceil_div(N, 128) * 128;
   return (!off && pad128 < pad256 && pad256 * 100 > (long long)N * 115) ? 128 : 256;
 }
 
 extern "C" int sfc_gemm_suggest_splits(int M, int N, int K) {
-  const int bn = gemm_pick_bn(N);
+  const int bn = gemm_pick_bn(N, K);
   const int mt = sfc_ceil_div(M, BM), nt = sfc_ceil_div(N, bn);
   const int kblocks = sfc_ceil_div(K, BK);
   const int cl = mt >= 2 ? 2 : 1;
@@ -399,7 +400,7 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
   SFC_REQUIRE(M > 0 && N > 0 && K > 0, "sfc_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
   SFC_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "sfc_gemm_bf16: leading dimensions must be multiples of 8 elements (lda=%lld ldb=%lld)", lda, ldb);
   if (splits < 1) splits = 1;
-  const int BN = gemm_pick_bn(N);
+  const int BN = gemm_pick_bn(N, K);
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
   p.num_m_tiles = sfc_ceil_div(M, BM);
