@@ -38,7 +38,16 @@ CONFIGS = {
     # BASELINE.json configs[4]: 64 x 64 patch grid, 4096 tokens per image — inference only (--mode infer)
     "vit_b16_1024": dict(img=1024, patch=16, D=768, depth=12, heads=12, mlp=3072, classes=1000, batch=4),
 }
-METRIC = "ViT-B/16 224px Hilbert images/sec fwd+bwd"
+METRIC = "ViT-B/16 224px Hilbert images/sec fwd+bwd"       # BASELINE.json's metric, quoted on vit_b16_224
+CONFIG_LABEL = {"vit_b16_224": "ViT-B/16 224px", "vit_s16_224": "ViT-S/16 224px", "vit_l16_384": "ViT-L/16 384px",
+                "vit_tiny4_32": "ViT-Tiny/4 32px", "vit_b16_1024": "ViT-B/16 1024px"}
+
+
+def metric_name(config, curve, infer=False):
+    """The metric string names the configuration it was measured on (only vit_b16_224 + hilbert is BASELINE.json's)."""
+    if infer:
+        return f"{CONFIG_LABEL[config]} {curve} images/sec fwd (bf16 inference)"
+    return f"{CONFIG_LABEL[config]} {'Hilbert' if curve == 'hilbert' else curve} images/sec fwd+bwd"
 
 
 def fwd_flops_per_image(c):
@@ -172,7 +181,7 @@ def run_reference_arm(args, c):
     else:
         ips, sec, threads = cpu_reference_throughput(c, max(1, args.steps), max(0, min(args.warmup, 1)), batch)
     line = {
-        "metric": f"{args.config} {args.curve} images/sec fwd (bf16 inference)" if infer else METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_name(args.config, args.curve, infer), "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": "reference",
         "config": {"workload": f"{args.config} Hilbert(embed-and-prune) " + ("inference forward" if infer else "train step fwd+bwd+clip+AdamW") + ", CPU oracle port of the reference path",
@@ -338,7 +347,7 @@ def run_infer(args, c):
                         "sample": f"2 timed forwards (+1 warm-up) of batch {cb}, fp32, {threads} threads, same model"}
     if rank == 0:
         print(json.dumps({
-            "metric": f"{args.config} {args.curve} images/sec fwd (bf16 inference)", "value": value, "unit": "images/s",
+            "metric": metric_name(args.config, args.curve, True), "value": value, "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{args.config} {args.curve} tokens, inference forward (eval, no_grad)", "batch_per_gpu": B,
@@ -350,6 +359,87 @@ def run_infer(args, c):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def check_dp(c, device, rank, world, curve):
+    """Data-parallel correctness on the hardware the scaling run uses (N > 1, default on): the SAME code path as the timed
+    step — GraphedStep with FusedAdamW inside the graph, gradients written into the flat bucket, bucket ranges all-reduced
+    on the side stream — on a depth-2 model of the config's width with dropout off and lr = 0, then rank 0 alone runs
+    the full global batch eagerly. Asserts: mean of the ranks' first-step losses == full-batch loss, the all-reduced
+    gradient / world == the full-batch gradient (norm and rel-L2, bf16 tolerance), identical buckets on every rank."""
+    import torch.distributed as dist
+    from src.training import distributed as D
+    from src.training.graphs import GraphedStep
+    from src.training.losses import SoftTargetCrossEntropy
+    from src.training.optim import FusedAdamW
+    cc = dict(c, depth=2)
+    per = 8
+
+    def build():
+        m = build_b200_model(cc, device, curve)
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+            if isinstance(mod, torch.nn.MultiheadAttention):
+                mod.dropout = 0.0
+        return m
+    g = torch.Generator(device=device).manual_seed(99)                # the same global batch on every rank
+    x = torch.randn(per * world, 3, cc["img"], cc["img"], generator=g, device=device)
+    la = torch.randint(0, cc["classes"], (per * world,), generator=g, device=device)
+    tgt = soft_targets(la, la.roll(1), 0.3, cc["classes"])
+    crit = SoftTargetCrossEntropy()
+    model = build()
+    D.sync_module(model)
+    opt = FusedAdamW(model.parameters(), lr=0.0, weight_decay=0.0, max_grad_norm=1.0)
+    xs, ts = D.shard(x, rank, world), D.shard(tgt, rank, world)
+    step = GraphedStep(model, crit, xs, ts, optimizer=opt)
+    loss = step(xs, ts).detach().float().clone()
+    torch.cuda.synchronize()
+    g_dp = torch.cat([fb["g"].float() for fb in opt._flat]) / world
+    overlapped, buckets = opt.last_overlapped_buckets, opt.last_num_buckets
+    dist.all_reduce(loss, op=dist.ReduceOp.SUM)
+    loss_dp = float(loss) / world
+    lo, hi = g_dp.clone(), g_dp.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    same = bool(torch.equal(lo, hi))
+    res = None
+    if rank == 0:
+        ref = build()
+        ref.load_state_dict(model.state_dict())
+        lf = crit(ref(x), tgt)
+        lf.backward()
+        names = [n for n, p in model.named_parameters() if p.requires_grad]
+        gref = dict(ref.named_parameters())
+        parts = []
+        for fb in opt._flat:
+            buf = torch.zeros(fb["n"], dtype=torch.float32, device=device)
+            byid = {id(p): n for n, p in model.named_parameters()}
+            for (p, off, k) in fb["views"]:
+                gr = gref[byid[id(p)]].grad
+                if gr is not None:
+                    buf[off:off + k] = gr.float().reshape(-1)
+            parts.append(buf)
+        g_full = torch.cat(parts)
+        rel = float((g_dp - g_full).norm() / g_full.norm())
+        res = {"world": world, "global_batch": per * world, "loss_dp_mean": loss_dp, "loss_full_batch": float(lf),
+               "grad_norm_dp": float(g_dp.norm()), "grad_norm_full_batch": float(g_full.norm()), "grad_rel_l2": rel,
+               "buckets_identical_on_all_ranks": same, "allreduce_ranges": buckets, "ranges_overlapped_with_backward": overlapped}
+        ok = (abs(loss_dp - float(lf)) < 2e-3 * max(1.0, abs(float(lf))) and rel < 3e-2 and same
+              and abs(res["grad_norm_dp"] - res["grad_norm_full_batch"]) < 2e-2 * res["grad_norm_full_batch"])
+        res["ok"] = bool(ok)
+    flag = torch.tensor([1.0 if (res is None or res["ok"]) else 0.0], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    opt.close()
+    del step, opt, model
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    if float(flag) == 0.0:
+        if rank == 0:
+            print(json.dumps({"dp_check": res}), flush=True)
+        raise SystemExit("bench.py: data-parallel check FAILED (sharded step != full-batch step)")
+    return res
 
 
 def cpu_reference_forward(c, steps, warmup, batch):
@@ -386,6 +476,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dropout", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--check-dp", dest="check_dp", action="store_true", default=None,
+                    help="N > 1: assert the sharded step equals the full-batch step before timing (default: on when N > 1)")
+    ap.add_argument("--no-check-dp", dest="check_dp", action="store_false")
+    ap.add_argument("--no-exposed", action="store_true", help="N > 1: skip the second (collective-free) capture that measures allreduce_exposed_ms")
     args = ap.parse_args()
     c = dict(CONFIGS[args.config])
     if args.config == "vit_b16_1024":
@@ -412,7 +506,11 @@ def main():
     B = args.batch or c["batch"]
     classes = c["classes"]
 
+    dp_check = None
+    if world > 1 and args.check_dp is not False:
+        dp_check = check_dp(c, device, rank, world, args.curve)
     model = build_b200_model(c, device, args.curve)
+    D.sync_module(model)
     if args.no_dropout:
         for m in model.modules():
             if isinstance(m, torch.nn.Dropout):
@@ -459,27 +557,22 @@ def main():
     gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
     gemm_flops = sum(f for _, _, f in prof)
 
-    # ---------------- the step that is timed: forward + loss + backward replayed from ONE CUDA graph, then the
-    # optimizer (gradient packing, NCCL all-reduce for N > 1, grad-norm, clip + AdamW) launched eagerly
+    # ---------------- the step that is timed: forward + loss + backward + (bucketed NCCL all-reduce on a side stream,
+    # N > 1) + grad-norm + clip + AdamW, ALL replayed from ONE CUDA graph; per step the host only hands lr / bias
+    # corrections to the device (one 1-thread kernel) and replays
     graphed = None
     launches_per_step = None
     if not args.no_graph:
         from src.training.graphs import GraphedStep
         opt.zero_grad(set_to_none=True)
         loss = None                                                   # no live eager autograd graph during capture
-        l0 = ops.LAUNCHES
-        graphed = GraphedStep(model, crit, dev_imgs[0], tgt)
-        fb_launches = (ops.LAUNCHES - l0) // 4                        # 3 warm-up passes + the captured one
-        l0 = ops.LAUNCHES
-        opt.step()
-        launches_per_step = fb_launches + (ops.LAUNCHES - l0)
+        graphed = GraphedStep(model, crit, dev_imgs[0], tgt, optimizer=opt)
+        launches_per_step = graphed.captured_launches + len(opt._flat)   # + the hyper-parameter store per flat buffer
 
     def step(images):
         if graphed is None:
             return eager_step(images)
-        loss = graphed(images)
-        opt.step()
-        return loss
+        return graphed(images)
 
     for i in range(2):
         step(dev_imgs[i % n_bufs])
@@ -512,12 +605,13 @@ def main():
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")          # dram bytes per launch from the ncu --set full capture
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")      # IMPORTED from a committed ncu capture, not measured in this run
     roofline = {
         "bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all fwd/dgrad/wgrad launches)",
         "achieved": gemm_tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
         "frac": gemm_tflops / peaks["tf_sustained"], "peak_source": peaks["source"] + " (sustained; kernels timed inside a long step)",
-        "traffic": traffic, "launches_per_step": len(prof) / roof_steps,
+        "traffic": traffic, "traffic_source": "imported: profiles/gemm_traffic.json (ncu --set full capture of the same kernels, dram read+write per launch)",
+        "launches_per_step": len(prof) / roof_steps,
         "avg_launch_ms": gemm_ms / max(1, len(prof)), "gemm_ms_per_step": gemm_ms / roof_steps,
         "timed_in": "eager replica of the step (same kernels, CUDA events around each launch) run just before the graph-replayed timed region",
         "whole_step_tflops": step_flops / (ms_total / args.steps * 1e-3) / 1e12,
@@ -575,6 +669,27 @@ def main():
     e2e = {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * c["img"] * c["img"] * 4,
            "d2h_bytes_per_step": 4, "steps": e2e_steps, "last_loss": loss_host}
 
+    # ---------------- N > 1: how much of the gradient all-reduce is NOT hidden behind backward: the same graph captured
+    # again with the collectives left out (timing only; replicas diverge afterwards, so this is the last thing measured)
+    allreduce_exposed_ms = None
+    if world > 1 and graphed is not None and not args.no_exposed:
+        from src.training.graphs import GraphedStep
+        opt.skip_comm = True
+        nocomm = GraphedStep(model, crit, dev_imgs[0], tgt, optimizer=opt)
+        for i in range(2):
+            nocomm(dev_imgs[i % n_bufs])
+        sync_all()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record()
+        for i in range(args.steps):
+            nocomm(dev_imgs[i % n_bufs])
+        n1.record()
+        sync_all()
+        tn = torch.tensor([n0.elapsed_time(n1)], dtype=torch.float64, device=device)
+        dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+        allreduce_exposed_ms = ms_total / args.steps - float(tn.item()) / args.steps
+        opt.skip_comm = False
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ips, sec, threads = cpu_reference_throughput(c, 2, 1, args.cpu_batch)
@@ -583,17 +698,18 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric_name(args.config, args.curve), "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{args.config} " + ("generalised-Hilbert (embed-and-prune)" if args.curve == "hilbert" else args.curve) + " tokens, training step fwd+bwd+clip+AdamW",
                        "batch_per_gpu": B, "global_batch": B * world, "tokens": (c["img"] // c["patch"]) ** 2,
                        "dropout": not args.no_dropout, "params_dtype": "bf16", "parallelism": f"dp{world}",
-                       "launch": "eager" if graphed is None else "forward+backward replayed from one CUDA graph; optimizer eager",
+                       "launch": "eager" if graphed is None else "forward+backward+allreduce+clip+AdamW replayed from one CUDA graph",
                        "l2_policy": f"{n_bufs} rotating input batches of {B * 3 * c['img'] ** 2 * 4 / 1e6:.0f} MB (> 126 MB L2); activations per step ~GBs"},
             "roofline": roofline, "patch_embed": patch_embed, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
             "gpu_launches_per_step": launches / args.steps, "clocks": clocks, "loss": float(loss.item()),
-            "allreduce_buckets_per_step": opt.last_num_buckets,
+            "allreduce_buckets_per_step": opt.last_num_buckets, "allreduce_buckets_overlapped": opt.last_overlapped_buckets,
+            "allreduce_exposed_ms": allreduce_exposed_ms, "dp_check": dp_check,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SFCVIT_ABI_VERSION 1
+#define SFCVIT_ABI_VERSION 2
 
 typedef struct CUstream_st* sfc_stream_t; /* == cudaStream_t */
 
@@ -147,13 +147,21 @@ int sfc_attn_bwd(const void* qkv, const void* out, const void* dout, const float
 
 /* ---- K6: fused grad-norm / clip / AdamW over flat buckets
  *      (torch.nn.utils.clip_grad_norm_ + optim.AdamW.step: src/training/train.py:165-166, main.py:288-289) ----
- * sfc_grad_sumsq: accum[0] += sum(g^2) (caller zeroes accum). sfc_adamw_step: decoupled weight decay Adam on
- * n elements; gradient used = g * grad_scale * min(1, max_norm / (sqrt(stats[0]) * grad_scale + 1e-6))
- * (max_norm <= 0 or stats == NULL: no clipping). p/g: bf16 or fp32 (param_fp32); m/v: bf16 or fp32 (state_fp32). */
-int sfc_grad_sumsq(const void* g, int g_fp32, long long n, float* accum, sfc_stream_t stream);
+ * sfc_grad_sumsq: accum[0] += sum(g^2) (caller zeroes accum), reduced in a fixed order (bit-identical on every rank of
+ * a data-parallel job); scratch = sfc_grad_sumsq_scratch_bytes() bytes zeroed once by the caller, private to the stream.
+ * sfc_adamw_step: decoupled weight decay Adam on n elements; gradient used =
+ * g * grad_scale * min(1, max_norm / (sqrt(stats[0]) * grad_scale + 1e-6))
+ * (max_norm <= 0 or stats == NULL: no clipping). p/g: bf16 or fp32 (param_fp32); m/v: bf16 or fp32 (state_fp32).
+ * hyper_dev: optional DEVICE block of 3 floats {lr, 1 - beta1^t, sqrt(1 - beta2^t)} that overrides lr / step at run
+ * time, so a step captured in a CUDA graph follows the host's scheduler (main.py:290-314) without re-capture. */
+size_t sfc_grad_sumsq_scratch_bytes(void);
+int sfc_grad_sumsq(const void* g, int g_fp32, long long n, float* accum, void* scratch, size_t scratch_bytes,
+                   sfc_stream_t stream);
 int sfc_adamw_step(void* p, const void* g, void* m, void* v, long long n, int param_fp32, int state_fp32, float lr,
                    float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, float max_norm,
-                   const float* stats, sfc_stream_t stream);
+                   const float* stats, const float* hyper_dev, sfc_stream_t stream);
+/* dst[0..3] = {a, b, c, d} in stream order (values passed as kernel arguments): feeds hyper_dev between graph replays */
+int sfc_store_f32x4(float* dst, float a, float b, float c, float d, sfc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -6,6 +6,7 @@ Output: space-filling-curves-for-vision-transformers_b200/lib/libsfcvit.so (git-
 """
 import concurrent.futures as cf
 import glob
+import hashlib
 import os
 import subprocess
 import sys
@@ -25,10 +26,26 @@ FLAGS = [
 ] + (["-DSFC_ATTN_TIMELINE"] if os.environ.get("SFC_ATTN_TIMELINE") else [])   # debug stamps for tools/attn_timeline.py
 
 
-def _deps_mtime():
-    hs = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
+def _sha(paths, extra=""):
+    h = hashlib.sha1(extra.encode())
+    for p in sorted(paths):
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _headers():
+    return glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
         glob.glob(os.path.join(ROOT, "include", "*.h"))
-    return max(os.path.getmtime(h) for h in hs)
+
+
+def _stamp(path):
+    try:
+        with open(path) as f:
+            return f.read().strip()
+    except OSError:
+        return None
 
 
 def _compile(src, obj, verbose):
@@ -42,26 +59,38 @@ def _compile(src, obj, verbose):
 def build(force=False, verbose=False):
     os.makedirs(OBJ_DIR, exist_ok=True)
     os.makedirs(LIB_DIR, exist_ok=True)
+    # staleness by CONTENT hash (source + every header + flags), not mtime: the tree is copied to the GPU box with fresh
+    # timestamps, and a spurious rebuild there would burn GPU-box minutes
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
-    hdr_m = _deps_mtime()
+    hdrs = _headers()
+    flags = " ".join(FLAGS)
     jobs, objs = [], []
     for s in srcs:
         o = os.path.join(OBJ_DIR, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
-        if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_m):
-            jobs.append((s, o))
+        want = _sha([s] + hdrs, flags)
+        if force or not os.path.exists(o) or _stamp(o + ".sha") != want:
+            jobs.append((s, o, want))
     if jobs:
         with cf.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
-            futs = {ex.submit(_compile, s, o, verbose): s for s, o in jobs}
+            futs = {ex.submit(_compile, s, o, verbose): (o, want) for s, o, want in jobs}
             for f in cf.as_completed(futs):
                 log = f.result()
+                o, want = futs[f]
+                with open(o + ".sha", "w") as fh:
+                    fh.write(want)
                 if verbose:
                     sys.stderr.write(log)
-    if jobs or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
+    stale = [o for o in glob.glob(os.path.join(OBJ_DIR, "*.o")) if o not in objs]      # objects of deleted sources
+    for o in stale:
+        os.remove(o)
+    if jobs or stale or not os.path.exists(LIB):
+        tmp = f"{LIB}.{os.getpid()}.tmp"                     # link aside, then rename: a concurrent loader never sees a partial file
+        cmd = [NVCC, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        os.replace(tmp, LIB)
     return LIB
 
 

@@ -41,8 +41,12 @@ template <> struct Vec8<float> {
   }
 };
 
+// Deterministic: every block writes its partial, the last block to finish (ticket) adds them up in block order and
+// adds the total to accum[0] — the same bits on every rank of a data-parallel job (an atomicAdd per block would make
+// the clip coefficient, and with it the replicas' parameters, differ in the last place from rank to rank).
 template <typename T>
-__global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ g, long long n, float* __restrict__ accum) {
+__global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ g, long long n, float* __restrict__ accum,
+                                                    unsigned int* __restrict__ ticket, float* __restrict__ partials) {
   float s = 0.f;
   const long long n8 = n / 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
@@ -66,12 +70,34 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ g, lon
     s = red[threadIdx.x];
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffu, s, o);
-    if (threadIdx.x == 0) atomicAdd(accum, s);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+  }
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float t = 0.f;
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) t += __ldcg(partials + i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    accum[0] += t;
+    *ticket = 0u;                              // ready for the next launch on this scratch
   }
 }
 
 struct AdamArgs {
   float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale, max_norm;
+  const float* hyper;   // optional device block {lr, 1 - beta1^t, sqrt(1 - beta2^t)}: overrides lr / bc1 / bc2_sqrt (CUDA-graph replays)
 };
 
 __device__ __forceinline__ void adam_update(float& pi, float gi, float& mi, float& vi, const AdamArgs& a, float coef) {
@@ -87,6 +113,7 @@ __device__ __forceinline__ void adam_update(float& pi, float gi, float& mi, floa
 template <typename T, typename S>
 __global__ void __launch_bounds__(256) adamw_kernel(T* __restrict__ p, const T* __restrict__ g, S* __restrict__ m, S* __restrict__ v,
                                                     long long n, AdamArgs a, const float* __restrict__ stats) {
+  if (a.hyper != nullptr) { a.lr = __ldg(a.hyper); a.bc1 = __ldg(a.hyper + 1); a.bc2_sqrt = __ldg(a.hyper + 2); }
   float coef = a.grad_scale;
   if (a.max_norm > 0.f && stats) {
     const float total = sqrtf(stats[0]) * a.grad_scale;
@@ -116,6 +143,10 @@ __global__ void __launch_bounds__(256) adamw_kernel(T* __restrict__ p, const T* 
   }
 }
 
+__global__ void store_f32x4_kernel(float* dst, float a, float b, float c, float d) {
+  dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d;
+}
+
 int grid_for(long long n) {
   long long b = sfc_ceil_div64(n, 256 * 8);
   const long long cap = 8ll * sfc_num_sms();
@@ -125,34 +156,50 @@ int grid_for(long long n) {
 
 }  // namespace
 
-// accum[0] += sum(g^2); caller zeroes accum before the first bucket
-extern "C" int sfc_grad_sumsq(const void* g, int g_fp32, long long n, float* accum, cudaStream_t stream) {
+extern "C" size_t sfc_grad_sumsq_scratch_bytes(void) { return 16 + sizeof(float) * 8 * (size_t)sfc_num_sms(); }
+
+// accum[0] += sum(g^2); caller zeroes accum before the first bucket. scratch: sfc_grad_sumsq_scratch_bytes() bytes, zeroed
+// ONCE by the caller (the kernel leaves its ticket at zero), private to the stream.
+extern "C" int sfc_grad_sumsq(const void* g, int g_fp32, long long n, float* accum, void* scratch, size_t scratch_bytes,
+                              cudaStream_t stream) {
   SFC_REQUIRE(g && accum && n >= 0, "sfc_grad_sumsq: bad arguments");
   SFC_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "sfc_grad_sumsq: buffer must be 16-byte aligned");
+  SFC_REQUIRE(scratch && scratch_bytes >= sfc_grad_sumsq_scratch_bytes(), "sfc_grad_sumsq: scratch too small");
   if (n == 0) return 0;
-  if (g_fp32) sumsq_kernel<float><<<grid_for(n), 256, 0, stream>>>((const float*)g, n, accum);
-  else sumsq_kernel<__nv_bfloat16><<<grid_for(n), 256, 0, stream>>>((const __nv_bfloat16*)g, n, accum);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch);
+  float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 16);
+  if (g_fp32) sumsq_kernel<float><<<grid_for(n), 256, 0, stream>>>((const float*)g, n, accum, ticket, partials);
+  else sumsq_kernel<__nv_bfloat16><<<grid_for(n), 256, 0, stream>>>((const __nv_bfloat16*)g, n, accum, ticket, partials);
   SFC_LAUNCH_OK();
   return 0;
 }
 
 extern "C" int sfc_adamw_step(void* p, const void* g, void* m, void* v, long long n, int param_fp32, int state_fp32, float lr,
                               float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                              float max_norm, const float* stats, cudaStream_t stream) {
-  SFC_REQUIRE(p && g && m && v && n >= 0 && step >= 1, "sfc_adamw_step: bad arguments");
+                              float max_norm, const float* stats, const float* hyper_dev, cudaStream_t stream) {
+  SFC_REQUIRE(p && g && m && v && n >= 0 && (step >= 1 || hyper_dev), "sfc_adamw_step: bad arguments");
   SFC_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                 reinterpret_cast<uintptr_t>(v)) & 15) == 0, "sfc_adamw_step: buffers must be 16-byte aligned");
   if (n == 0) return 0;
-  const float bc1 = 1.0f - powf(beta1, (float)step);
-  const float bc2s = sqrtf(1.0f - powf(beta2, (float)step));
+  const float bc1 = step >= 1 ? 1.0f - powf(beta1, (float)step) : 1.0f;
+  const float bc2s = step >= 1 ? sqrtf(1.0f - powf(beta2, (float)step)) : 1.0f;
   const int grid = grid_for(n);
-  AdamArgs a{lr, beta1, beta2, eps, weight_decay, bc1, bc2s, grad_scale, max_norm};
+  AdamArgs a{lr, beta1, beta2, eps, weight_decay, bc1, bc2s, grad_scale, max_norm, hyper_dev};
 #define ADAMW(T, S) adamw_kernel<T, S><<<grid, 256, 0, stream>>>((T*)p, (const T*)g, (S*)m, (S*)v, n, a, stats)
   if (param_fp32 && state_fp32) ADAMW(float, float);
   else if (!param_fp32 && state_fp32) ADAMW(__nv_bfloat16, float);
   else if (!param_fp32 && !state_fp32) ADAMW(__nv_bfloat16, __nv_bfloat16);
   else { sfc_set_error("sfc_adamw_step: fp32 parameters with bf16 state is not supported"); return 2; }
 #undef ADAMW
+  SFC_LAUNCH_OK();
+  return 0;
+}
+
+// dst[0..3] = {a, b, c, d}, stream-ordered, values travel as kernel arguments (no host buffer whose lifetime the caller
+// would have to manage while the stream runs ahead): how the host scheduler's lr / bias corrections reach a CUDA graph.
+extern "C" int sfc_store_f32x4(float* dst, float a, float b, float c, float d, cudaStream_t stream) {
+  SFC_REQUIRE(dst != nullptr, "sfc_store_f32x4: null destination");
+  store_f32x4_kernel<<<1, 1, 0, stream>>>(dst, a, b, c, d);
   SFC_LAUNCH_OK();
   return 0;
 }

@@ -48,32 +48,52 @@ SIGNATURES = {
     "sfc_attn_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, ctypes.c_ulonglong, _vp]),
     "sfc_attn_bwd_scratch_bytes": (_sz, [_i, _i, _i]),
     "sfc_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _f, _f, ctypes.c_ulonglong, _vp]),
-    "sfc_grad_sumsq": (_i, [_vp, _i, _ll, _vp, _vp]),
-    "sfc_adamw_step": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _f, _f, _f, _f, _f, _i, _f, _f, _vp, _vp]),
+    "sfc_grad_sumsq_scratch_bytes": (_sz, []),
+    "sfc_grad_sumsq": (_i, [_vp, _i, _ll, _vp, _vp, _sz, _vp]),
+    "sfc_adamw_step": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _f, _f, _f, _f, _f, _i, _f, _f, _vp, _vp, _vp]),
+    "sfc_store_f32x4": (_i, [_vp, _f, _f, _f, _f, _vp]),
     "sfc_gemm_bf16": (_i, [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, ctypes.POINTER(SfcGemmEpilogue), _vp, _sz, _i, _vp]),
 }
 
 
-def load(build_if_missing: bool = True):
-    """Loads libsfcvit.so (building it with nvcc when absent). Raises if it cannot be loaded."""
-    global _lib
-    with _lock:
-        if _lib is not None:
-            return _lib
-        if not os.path.exists(LIB_PATH):
-            if not build_if_missing:
-                raise RuntimeError(f"libsfcvit.so not built: {LIB_PATH}")
-            import importlib.util
+ABI_VERSION = 2
+
+
+def _build_locked():
+    """Runs build.py (a no-op when the library is newer than every source) under an inter-process file lock: under
+    torchrun all ranks import at once, and only one may compile / link; build.py links to a temporary file and renames."""
+    import fcntl
+    import importlib.util
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    with open(LIB_PATH + ".lock", "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
             spec = importlib.util.spec_from_file_location("_sfcvit_build", os.path.join(_PK, "build.py"))
             mod = importlib.util.module_from_spec(spec)
             spec.loader.exec_module(mod)
             mod.build()
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
+
+
+def load(build_if_missing: bool = True):
+    """Loads libsfcvit.so (building it with nvcc when absent or older than its sources and nvcc exists). Raises if it
+    cannot be loaded — there is no CPU fallback behind this library."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        have_nvcc = os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc"))
+        if build_if_missing and have_nvcc and os.path.isdir(os.path.join(_PK, "csrc")):
+            _build_locked()
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"libsfcvit.so not built: {LIB_PATH}")
         lib = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if lib.sfc_abi_version() != 1:
+        if lib.sfc_abi_version() != ABI_VERSION:
             raise RuntimeError("libsfcvit ABI version mismatch")
         _lib = lib
         return _lib

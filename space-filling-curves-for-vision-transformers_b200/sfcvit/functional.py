@@ -15,16 +15,69 @@ ACT_NONE, ACT_RELU, ACT_GELU = ops.ACT_NONE, ops.ACT_RELU, ops.ACT_GELU
 
 _shadow = {}
 
+# Parameters updated through raw pointers (FusedAdamW's kernel, CUDA-graph replays) never bump torch's `_version`, so
+# the weight-conversion caches below are keyed on (tensor version, WEIGHTS_EPOCH); every such update calls
+# bump_weights_epoch().
+WEIGHTS_EPOCH = 0
+
+
+def bump_weights_epoch():
+    global WEIGHTS_EPOCH
+    WEIGHTS_EPOCH += 1
+
+
+def clear_weight_caches():
+    """Drop every cached weight conversion (before / after a CUDA-graph capture: conversions must be re-run INSIDE the
+    graph, and entries created during capture alias graph-private memory)."""
+    _shadow.clear()
+    _wk_cache.clear()
+    _wk_u8_cache.clear()
+
+
+# ---- gradient destinations: slices of a flat gradient bucket (src/training/optim.py) -------------------------------
+# FusedAdamW registers, per parameter, the slice of its flat bucket. A backward function asks grad_out(param) for it and
+# lets its wgrad GEMM / reduction kernel write the gradient THERE; autograd then adopts the returned view as `.grad`
+# (no packing copy before the all-reduce). A slice is handed out at most once between two release_grad_claims() calls
+# and only while `.grad` is None — any other situation (gradient accumulation, a parameter used twice) gets None and
+# the ordinary freshly-allocated gradient, which the optimizer copies into the bucket itself.
+_grad_buf = {}
+_claimed = set()
+
+
+def register_grad_buffer(param, flat, offset):
+    _grad_buf[id(param)] = (weakref.ref(param), flat, int(offset))
+
+
+def unregister_grad_buffers(params):
+    for p in params:
+        _grad_buf.pop(id(p), None)
+        _claimed.discard(id(p))
+
+
+def release_grad_claims():
+    _claimed.clear()
+
+
+def grad_out(param):
+    if param is None:
+        return None
+    ent = _grad_buf.get(id(param))
+    if ent is None or ent[0]() is not param or param.grad is not None or id(param) in _claimed:
+        return None
+    _claimed.add(id(param))
+    n = param.numel()
+    return ent[1][ent[2]:ent[2] + n].view(param.shape)
+
 
 def as_bf16(t):
-    """bf16 view/shadow of a parameter (no copy when it already is bf16). Cached on (storage, version)."""
+    """bf16 view/shadow of a parameter (no copy when it already is bf16). Cached on (tensor, version, weights epoch)."""
     if t is None:
         return None
     if t.dtype == torch.bfloat16:
         return t.detach()
     key = id(t)
     ent = _shadow.get(key)
-    ver = t._version
+    ver = (t._version, WEIGHTS_EPOCH)
     if ent is not None and ent[0]() is t and ent[1] == ver and ent[2].device == t.device:
         return ent[2]
     sh = t.detach().to(torch.bfloat16)
@@ -56,10 +109,15 @@ def _pad_cols(t, mult=8):
     return out
 
 
+def _usable(buf, shape, dtype):
+    return buf if (buf is not None and buf.dtype == dtype and tuple(buf.shape) == tuple(shape)) else None
+
+
 def linear_backward(dy2, x2, wb, w_dtype, need_dx, need_dw, need_db, *, dx_aux=None, dx_aux_mode=ops.AUX_NONE,
-                    dx_alpha=1.0, dx_residual=None):
+                    dx_alpha=1.0, dx_residual=None, w_param=None, b_param=None):
     """Gradients of y = x W^T + b for dy2 [M,N], x2 [M,K], wb bf16 [N,K].
-    dX = epilogue(dY.W) (optionally * relu-mask / gelu' of dx_aux, + dx_residual), dW = dY^T.X, db = colsum(dY)."""
+    dX = epilogue(dY.W) (optionally * relu-mask / gelu' of dx_aux, + dx_residual), dW = dY^T.X, db = colsum(dY).
+    w_param / b_param: the nn.Parameters, so that dW / db can be written straight into their flat-bucket slices."""
     N = wb.shape[0]
     dyp = _pad_cols(dy2)                     # TMA needs 16-byte row strides (e.g. num_classes = 10)
     dx = dw = db = None
@@ -70,10 +128,11 @@ def linear_backward(dy2, x2, wb, w_dtype, need_dx, need_dw, need_db, *, dx_aux=N
             wbp[:N] = wb
         dx = ops.gemm(dyp, wbp, b_mn=True, aux=dx_aux, aux_mode=dx_aux_mode, alpha=dx_alpha, residual=dx_residual)
     if need_dw:
-        dwp = ops.gemm(dyp, x2, a_mn=True, b_mn=True, out_dtype=w_dtype, splits=0)
+        dst = _usable(grad_out(w_param), (dyp.shape[1], x2.shape[1]), w_dtype) if dyp.shape[1] == N else None
+        dwp = ops.gemm(dyp, x2, a_mn=True, b_mn=True, out=dst, out_dtype=w_dtype, splits=0)
         dw = dwp[:N] if dwp.shape[0] != N else dwp
     if need_db:
-        db = ops.colsum(dy2, w_dtype)
+        db = ops.colsum(dy2, w_dtype, out=_usable(grad_out(b_param), (N,), w_dtype))
     return dx, dw, db
 
 
@@ -106,6 +165,7 @@ class LinearFn(Function):
         ctx.has_res = residual is not None
         ctx.has_bias = b is not None
         ctx.w_dtype = w.dtype
+        ctx.w_param, ctx.b_param = (w if w.is_leaf else None), (b if b is not None and b.is_leaf else None)
         # relu: the (post-dropout) output itself is the mask source, but only when no residual was added on top
         aux = pre if act == ACT_GELU else (out if (act == ACT_RELU and residual is None) else None)
         if act == ACT_RELU and residual is not None and need_grad:
@@ -129,7 +189,7 @@ class LinearFn(Function):
         elif ctx.drop_p > 0:
             g = ops.act_bwd(dy2, None, ops.AUX_NONE, drop_p=ctx.drop_p, drop_seed=ctx.seed)
         dx, dw, db = linear_backward(g, x2, wb, ctx.w_dtype, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
-                                     ctx.has_bias and ctx.needs_input_grad[2])
+                                     ctx.has_bias and ctx.needs_input_grad[2], w_param=ctx.w_param, b_param=ctx.b_param)
         if dx is not None:
             dx = dx.reshape(ctx.xs)
         return dx, dw, db, None, d_res, None, None, None
@@ -150,6 +210,7 @@ class LayerNormFn(Function):
         y, mean, rstd = ops.layernorm_fwd(x2, gb, as_bf16(beta), eps)
         ctx.save_for_backward(x2, mean, rstd, gb)
         ctx.xs, ctx.p_dtype = xs, gamma.dtype
+        ctx.params = (gamma if gamma.is_leaf else None, beta if beta.is_leaf else None)
         return y.reshape(xs)
 
     @staticmethod
@@ -158,7 +219,8 @@ class LayerNormFn(Function):
         dy2 = _bf16_act(dy).reshape(x2.shape)
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
-        dx, dg, db, _, _ = ops.layernorm_bwd(dy2, x2, mean, rstd, gb, ctx.p_dtype)
+        dx, dg, db, _, _ = ops.layernorm_bwd(dy2, x2, mean, rstd, gb, ctx.p_dtype, dgamma_out=grad_out(ctx.params[0]),
+                                             dbeta_out=grad_out(ctx.params[1]))
         return dx.reshape(ctx.xs), dg, db, None
 
 
@@ -239,7 +301,7 @@ def kernel_weight(w_ref, C, p, g, k_order):
     The permutation is applied to the WEIGHT once per parameter version, never to the image data."""
     key = id(w_ref)
     ent = _wk_cache.get(key)
-    if ent is not None and ent[0]() is w_ref and ent[1] == w_ref._version and ent[2].device == w_ref.device:
+    if ent is not None and ent[0]() is w_ref and ent[1] == (w_ref._version, WEIGHTS_EPOCH) and ent[2].device == w_ref.device:
         return ent[2]
     D = w_ref.shape[0]
     K = g * p * p * C
@@ -252,7 +314,7 @@ def kernel_weight(w_ref, C, p, g, k_order):
         w = w.reshape(D, K)
     wk = torch.zeros((D, Kpad), dtype=torch.bfloat16, device=w_ref.device)
     wk[:, :K] = w
-    _wk_cache[key] = (weakref.ref(w_ref), w_ref._version, wk)
+    _wk_cache[key] = (weakref.ref(w_ref), (w_ref._version, WEIGHTS_EPOCH), wk)
     return wk
 
 
@@ -264,7 +326,7 @@ def kernel_weight_u8(w_ref, bias, C, p, g, k_order, norm):
     normalisation folded in, the matching bias, and the fp32 per-k scale / shift vectors the backward needs."""
     mean, std = norm if norm is not None else (None, None)
     key = id(w_ref)
-    ver = (w_ref._version, bias._version if bias is not None else -1, id(mean), id(std))
+    ver = (w_ref._version, bias._version if bias is not None else -1, id(mean), id(std), WEIGHTS_EPOCH)
     ent = _wk_u8_cache.get(key)
     if ent is not None and ent[0]() is w_ref and ent[1] == ver and ent[2][0].device == w_ref.device:
         return ent[2]
@@ -321,10 +383,12 @@ class ConcatStreamsFn(Function):
 
 
 def concat_streams(streams, n_tokens):
-    """Kernel path when every stream's feature size is a multiple of 8 (16-byte vectors); None otherwise (the caller
-    then uses torch's upsample + cat on the same device)."""
-    if any(s.shape[2] % 8 for s in streams):
-        return None
+    """Kernel K7. Every stream's feature size must be a multiple of 8 (16-byte vectors; the fusion GEMM that follows
+    needs 16-byte row strides as well) — there is no stock-torch fallback."""
+    bad = [s.shape[2] for s in streams if s.shape[2] % 8]
+    if bad:
+        raise RuntimeError(f"hierarchical tokenizer: per-level embed_dim must be a multiple of 8 (got {bad}); the kernel "
+                           "path has no fallback")
     return ConcatStreamsFn.apply(n_tokens, *streams)
 
 
@@ -353,6 +417,8 @@ class EncoderLayerFn(Function):
         out, mean2, rstd2 = ops.layernorm_fwd(y2, g2b, as_bf16(be2), eps)
         ctx.save_for_backward(x2, qkv, attn, lse, y1, mean1, rstd1, x1, h, y2, mean2, rstd2, wi, wo, wf1, wf2, g1b, g2b)
         ctx.cfg = (B, N, D, heads, drops, seed, in_w.dtype)
+        ctx.params = tuple(t if (t is not None and t.is_leaf) else None
+                           for t in (in_w, in_b, out_w, out_b, w1, b1, w2, b2, g1, be1, g2, be2))
         return out.reshape(B, N, D)
 
     @staticmethod
@@ -365,31 +431,36 @@ class EncoderLayerFn(Function):
         d2 = _bf16_act(dout).reshape(B * N, D)
         if not d2.is_contiguous():
             d2 = d2.contiguous()
+        # gradient destinations: the parameters' slices of the optimizer's flat bucket when registered (else fresh tensors)
+        (o_wi, o_bi, o_wo, o_bo, o_w1, o_b1, o_w2, o_b2, o_g1, o_be1, o_g2, o_be2) = (
+            _usable(grad_out(t), t.shape, pdt) if t is not None else None for t in ctx.params)
         # LN2
         # LN2 backward also emits the dropout2-masked gradient and its column sums (= linear2.bias gradient)
-        dy2, dg2, dbe2, dy2d, db2 = ops.layernorm_bwd(d2, y2, mean2, rstd2, g2b, pdt, drop_p=p_d2, drop_seed=s_d2, want_colsum=True)
+        dy2, dg2, dbe2, dy2d, db2 = ops.layernorm_bwd(d2, y2, mean2, rstd2, g2b, pdt, drop_p=p_d2, drop_seed=s_d2, want_colsum=True,
+                                                      dgamma_out=o_g2, dbeta_out=o_be2, colsum_out=o_b2)
         if dy2d is None:
             dy2d = dy2
         # linear2 (+ReLU/dropout mask fused into the dgrad epilogue)
         dh = ops.gemm(dy2d, wf2, b_mn=True, aux=h, aux_mode=ops.AUX_RELU_MASK, alpha=inv_keep)
-        dw2 = ops.gemm(dy2d, h, a_mn=True, b_mn=True, out_dtype=pdt, splits=0)
+        dw2 = ops.gemm(dy2d, h, a_mn=True, b_mn=True, out=o_w2, out_dtype=pdt, splits=0)
         # linear1 (+ residual gradient of x1 fused)
         dx1 = ops.gemm(dh, wf1, b_mn=True, residual=dy2)
-        dw1 = ops.gemm(dh, x1, a_mn=True, b_mn=True, out_dtype=pdt, splits=0)
-        db1 = ops.colsum(dh, pdt)
+        dw1 = ops.gemm(dh, x1, a_mn=True, b_mn=True, out=o_w1, out_dtype=pdt, splits=0)
+        db1 = ops.colsum(dh, pdt, out=o_b1)
         # LN1
-        dy1, dg1, dbe1, dy1d, dbo = ops.layernorm_bwd(dx1, y1, mean1, rstd1, g1b, pdt, drop_p=p_d1, drop_seed=s_d1, want_colsum=True)
+        dy1, dg1, dbe1, dy1d, dbo = ops.layernorm_bwd(dx1, y1, mean1, rstd1, g1b, pdt, drop_p=p_d1, drop_seed=s_d1, want_colsum=True,
+                                                      dgamma_out=o_g1, dbeta_out=o_be1, colsum_out=o_bo)
         if dy1d is None:
             dy1d = dy1
         # out_proj
         dattn = ops.gemm(dy1d, wo, b_mn=True)
-        dwo = ops.gemm(dy1d, attn, a_mn=True, b_mn=True, out_dtype=pdt, splits=0)
+        dwo = ops.gemm(dy1d, attn, a_mn=True, b_mn=True, out=o_wo, out_dtype=pdt, splits=0)
         # attention
         dqkv = ops.attn_bwd(qkv, attn, dattn, lse, B, heads, N, drop_p=p_attn, drop_seed=s_attn)
         # in_proj (+ residual gradient of x fused)
         dx = ops.gemm(dqkv, wi, b_mn=True, residual=dy1) if ctx.needs_input_grad[0] else None
-        dwi = ops.gemm(dqkv, x2, a_mn=True, b_mn=True, out_dtype=pdt, splits=0)
-        dbi = ops.colsum(dqkv, pdt)
+        dwi = ops.gemm(dqkv, x2, a_mn=True, b_mn=True, out=o_wi, out_dtype=pdt, splits=0)
+        dbi = ops.colsum(dqkv, pdt, out=o_bi)
         if dx is not None:
             dx = dx.reshape(B, N, D)
         return (dx, dwi, dbi, dwo, dbo, dw1, db1, dw2, db2, dg1, dbe1, dg2, dbe2, None, None, None, None)

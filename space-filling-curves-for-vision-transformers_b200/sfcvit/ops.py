@@ -162,9 +162,19 @@ def drop_inv_keep(p):
     return 65536.0 / (65536.0 - thr)
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, param_dtype=torch.bfloat16, *, drop_p=0.0, drop_seed=0, want_colsum=False):
+def _param_out(buf, n, dtype, device):
+    """`buf` when it is a usable destination for an [n] gradient in `dtype` (a slice of a flat gradient bucket), else a
+    fresh tensor."""
+    if buf is not None and buf.dtype == dtype and buf.numel() == n and buf.is_contiguous():
+        return buf
+    return torch.empty(n, dtype=dtype, device=device)
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, param_dtype=torch.bfloat16, *, drop_p=0.0, drop_seed=0, want_colsum=False,
+                  dgamma_out=None, dbeta_out=None, colsum_out=None):
     """Returns (dx, dgamma, dbeta, dx_drop, colsum): dx_drop is the dropout-masked copy of dx (None when drop_p == 0),
-    colsum the column sums of dx_drop (or dx) in param_dtype (None unless want_colsum)."""
+    colsum the column sums of dx_drop (or dx) in param_dtype (None unless want_colsum). *_out: optional destinations
+    (slices of a flat gradient bucket)."""
     lib = _lib.load()
     _require_cuda(dy, x, mean, rstd, gamma)
     assert dy.dtype == torch.bfloat16 and dy.is_contiguous() and x.is_contiguous()
@@ -172,9 +182,9 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, param_dtype=torch.bfloat16, *, drop_
     rows = x.numel() // D
     dx = torch.empty_like(x)
     dxd = torch.empty_like(x) if drop_p > 0 else None
-    dgamma = torch.empty(D, dtype=param_dtype, device=x.device)
-    dbeta = torch.empty(D, dtype=param_dtype, device=x.device)
-    csum = torch.empty(D, dtype=param_dtype, device=x.device) if want_colsum else None
+    dgamma = _param_out(dgamma_out, D, param_dtype, x.device)
+    dbeta = _param_out(dbeta_out, D, param_dtype, x.device)
+    csum = _param_out(colsum_out, D, param_dtype, x.device) if want_colsum else None
     nbytes = lib.sfc_layernorm_bwd_scratch_bytes(rows, D)
     scratch = _workspace(nbytes, x.device)
     with torch.cuda.device(x.device):
@@ -186,13 +196,13 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, param_dtype=torch.bfloat16, *, drop_
     return dx, dgamma, dbeta, dxd, csum
 
 
-def colsum(x, out_dtype=torch.bfloat16):
+def colsum(x, out_dtype=torch.bfloat16, out=None):
     """x: bf16 [rows, N] (row stride arbitrary, inner contiguous) -> [N] column sums (bias gradient)."""
     lib = _lib.load()
     _require_cuda(x)
     assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
     rows, N = x.shape
-    out = torch.empty(N, dtype=out_dtype, device=x.device)
+    out = _param_out(out, N, out_dtype, x.device)
     nbytes = lib.sfc_colsum_scratch_bytes(rows, N)
     scratch = _workspace(nbytes, x.device)
     with torch.cuda.device(x.device):
@@ -356,26 +366,48 @@ def attn_bwd(qkv, out, dout, lse, B, H, N, *, scale=None, drop_p=0.0, drop_seed=
 
 
 # ------------------------------------------------------------------ K6: optimizer
+_sumsq_scratch = {}
+
+
 def grad_sumsq(g, accum):
+    """accum[0] += sum(g^2), reduced in a fixed order (deterministic across ranks)."""
     lib = _lib.load()
     _require_cuda(g, accum)
     assert g.is_contiguous() and accum.dtype == torch.float32
+    key = (g.device.index, torch.cuda.current_stream().cuda_stream)
+    scratch = _sumsq_scratch.get(key)
+    if scratch is None:
+        scratch = torch.zeros(lib.sfc_grad_sumsq_scratch_bytes(), dtype=torch.uint8, device=g.device)   # zeroed ONCE
+        _sumsq_scratch[key] = scratch
     with torch.cuda.device(g.device):
-        _lib.check(lib.sfc_grad_sumsq(_ptr(g), 1 if g.dtype == torch.float32 else 0, g.numel(), _ptr(accum), _stream()),
-                   "sfc_grad_sumsq")
+        _lib.check(lib.sfc_grad_sumsq(_ptr(g), 1 if g.dtype == torch.float32 else 0, g.numel(), _ptr(accum), _ptr(scratch),
+                                      scratch.numel(), _stream()), "sfc_grad_sumsq")
     _count(1)
 
 
-def adamw_step(p, g, m, v, *, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, max_norm=0.0, stats=None):
+def adamw_step(p, g, m, v, *, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, max_norm=0.0, stats=None,
+               hyper=None):
+    """hyper: optional fp32 device tensor {lr, 1 - beta1^t, sqrt(1 - beta2^t)} overriding lr / step at run time."""
     lib = _lib.load()
-    _require_cuda(p, g, m, v, stats)
+    _require_cuda(p, g, m, v, stats, hyper)
     assert p.is_contiguous() and g.is_contiguous() and m.is_contiguous() and v.is_contiguous()
     assert p.dtype == g.dtype and m.dtype == v.dtype
+    assert hyper is None or (hyper.dtype == torch.float32 and hyper.numel() >= 3)
     with torch.cuda.device(p.device):
         _lib.check(lib.sfc_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), 1 if p.dtype == torch.float32 else 0,
                                       1 if m.dtype == torch.float32 else 0, float(lr), float(beta1), float(beta2), float(eps),
                                       float(weight_decay), int(step), float(grad_scale), float(max_norm), _ptr(stats),
-                                      _stream()), "sfc_adamw_step")
+                                      _ptr(hyper), _stream()), "sfc_adamw_step")
+    _count(1)
+
+
+def store_f32x4(dst, a, b=0.0, c=0.0, d=0.0):
+    """dst[0..3] = (a, b, c, d) in stream order (values travel as kernel arguments)."""
+    lib = _lib.load()
+    _require_cuda(dst)
+    assert dst.dtype == torch.float32 and dst.numel() >= 4 and dst.is_contiguous()
+    with torch.cuda.device(dst.device):
+        _lib.check(lib.sfc_store_f32x4(_ptr(dst), float(a), float(b), float(c), float(d), _stream()), "sfc_store_f32x4")
     _count(1)
 
 

@@ -35,11 +35,55 @@ def init_from_env(backend=None):
 
 
 def shard(t, rank, world_size):
-    """This rank's slice of a full batch: every world_size-th sample starting at `rank`."""
+    """This rank's slice of a full TRAINING batch: every world_size-th sample starting at `rank`, equal shard sizes
+    (mean-of-means == global mean; up to world_size - 1 trailing samples of a ragged last batch are dropped, as a
+    DistributedSampler with drop_last would)."""
     if world_size == 1:
         return t
-    n = t.shape[0] - t.shape[0] % world_size          # equal shards (mean-of-means == global mean)
+    n = t.shape[0] - t.shape[0] % world_size
     return t[rank:n:world_size]
+
+
+def shard_all(t, rank, world_size):
+    """This rank's slice of an EVALUATION batch: every sample goes to exactly one rank (the remainder to the low
+    ranks); callers weight their sums by the actual sample count, so metrics cover the full test set."""
+    if world_size == 1:
+        return t
+    return t[rank::world_size]
+
+
+def agree(t, src=0):
+    """Rank `src`'s value of a small device tensor on every rank (the full-batch mixup / cutmix permutation is drawn from
+    the per-rank CUDA generator: equal seeds make it equal, this makes it certain)."""
+    _, ws = world()
+    if ws > 1:
+        dist.broadcast(t, src=src)
+    return t
+
+
+_synced = set()
+
+
+def sync_module(module, src=0, check=True):
+    """Broadcast parameters and buffers from rank `src` (once per module) so the replicas start bit-identical even if
+    their RNG streams diverged during construction; with check=True, also assert afterwards that a checksum agrees."""
+    rank, ws = world()
+    if ws == 1 or id(module) in _synced:
+        return
+    with torch.no_grad():
+        tensors = [p.data for p in module.parameters()] + [b for b in module.buffers()]
+        for t in tensors:
+            if t.numel():
+                dist.broadcast(t, src=src)
+        if check and tensors:
+            dev = tensors[0].device
+            cs = torch.stack([t.double().sum().to(dev) for t in tensors if t.numel() and t.is_floating_point()]).sum().reshape(1)
+            lo, hi = cs.clone(), cs.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            if float(lo) != float(hi):
+                raise RuntimeError("data-parallel replicas differ after the initial broadcast")
+    _synced.add(id(module))
 
 
 def build_buckets(tensors, bucket_bytes=BUCKET_BYTES):

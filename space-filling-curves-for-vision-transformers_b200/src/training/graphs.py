@@ -8,6 +8,16 @@ the ~370 launches of a step once and replay them (no Python / ctypes / tensor-ma
     loss = step(images, targets)        # copies into the static buffers, replays, returns the static loss tensor
     optimizer.step()                    # p.grad tensors are static; do NOT zero them to None between replays
 
+or, with a FusedAdamW (src/training/optim.py), the WHOLE step in one graph — backward's wgrad kernels write into the
+optimizer's flat gradient bucket, the data-parallel all-reduce of each bucket range is captured on a side stream as soon
+as the range is complete, and grad-norm + clip + AdamW follow in the same graph:
+
+    step = GraphedStep(model, criterion, example_images, example_targets, optimizer=fused_adamw)
+    loss = step(images, targets)        # advance() (lr / bias corrections -> device) + one replay; no optimizer.step()
+
+Construct the optimizer BEFORE the GraphedStep: FusedAdamW moves the parameters into its flat buffer at construction, and
+a graph captured earlier would keep reading the old storage — GraphedStep checks the parameter addresses on every call.
+
 Drop every reference to losses / outputs of earlier EAGER passes before constructing it: a live autograd graph keeps
 AccumulateGrad nodes bound to the default stream, which stream capture cannot synchronise with.
 
@@ -37,10 +47,12 @@ def dropout_epoch(device):
 
 
 class GraphedStep:
-    def __init__(self, model, criterion, example_images, example_targets, warmup=3):
+    def __init__(self, model, criterion, example_images, example_targets, warmup=3, optimizer=None):
         if not example_images.is_cuda:
             raise RuntimeError("GraphedStep needs CUDA tensors (no CPU fallback)")
-        self.model, self.criterion = model, criterion
+        if optimizer is not None and not (hasattr(optimizer, "advance") and hasattr(optimizer, "launch")):
+            raise TypeError("GraphedStep(optimizer=...) needs a FusedAdamW (advance() / launch()); step other optimizers eagerly")
+        self.model, self.criterion, self.optimizer = model, criterion, optimizer
         self.images = example_images.clone()
         self.targets = example_targets.clone()
         self.epoch = dropout_epoch(example_images.device)
@@ -52,26 +64,46 @@ class GraphedStep:
             for _ in range(warmup):
                 for p in params:
                     p.grad = None
+                SF.release_grad_claims()
                 self.criterion(self.model(self.images), self.targets).backward()
+                if optimizer is not None:
+                    # a real step with zero learning rate would still decay; the warm-up only has to teach the optimizer
+                    # which parameters receive gradients and grow every workspace, so it launches nothing that updates
+                    optimizer._learn_expected(tuple(p.grad is not None for fb in optimizer._flat for (p, _o, _k) in fb["views"]))
+                    optimizer._pending = None
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         for p in params:
             p.grad = None                         # backward inside the capture allocates the static .grad tensors
-        SF._shadow.clear()                        # cached weight conversions must be RE-RUN inside the graph
-        SF._wk_cache.clear()
+        SF.release_grad_claims()
+        SF.clear_weight_caches()                  # cached weight conversions must be RE-RUN inside the graph
         self.graph = torch.cuda.CUDAGraph()
+        from sfcvit import ops
+        l0 = ops.LAUNCHES
+        if optimizer is not None:
+            optimizer.last_num_buckets = optimizer.last_overlapped_buckets = 0
         with torch.cuda.graph(self.graph):
             self.epoch.add_(1)
             self.logits = self.model(self.images)
             self.loss = self.criterion(self.logits, self.targets)
             self.loss.backward()
-        SF._shadow.clear()                        # entries created during capture alias graph-private memory
-        SF._wk_cache.clear()
+            if optimizer is not None:
+                optimizer.launch()
+        self.captured_launches = ops.LAUNCHES - l0   # libsfcvit kernels per replay
+        SF.clear_weight_caches()                  # entries created during capture alias graph-private memory
+        self._param_ptrs = [p.data_ptr() for p in params]
+        self._params = params
 
     def __call__(self, images, targets=None):
+        if [p.data_ptr() for p in self._params] != self._param_ptrs:
+            raise RuntimeError("GraphedStep: a parameter's storage moved after capture (construct FusedAdamW / load "
+                               "checkpoints BEFORE building the GraphedStep); the graph would read stale weights")
         if images is not self.images:
             self.images.copy_(images, non_blocking=True)
         if targets is not None and targets is not self.targets:
             self.targets.copy_(targets, non_blocking=True)
+        if self.optimizer is not None:
+            self.optimizer.advance()
         self.graph.replay()
+        SF.bump_weights_epoch()                   # replays update / read parameters behind torch's version counters
         return self.loss

@@ -14,7 +14,7 @@ from . import distributed as D
 def mixup_data(x, y, alpha=0.2):
     """Convex mix of the batch with a shuffled copy (reference :7-14). Host RNG: numpy for lambda, torch for the perm."""
     lam = np.random.beta(alpha, alpha) if alpha > 0 else 1.0
-    idx = torch.randperm(x.size(0), device=x.device)
+    idx = D.agree(torch.randperm(x.size(0), device=x.device))
     return lam * x + (1 - lam) * x[idx], y, y[idx], lam
 
 
@@ -31,7 +31,7 @@ def cutmix_data(x, y, alpha=0.2):
     """Paste a box from a shuffled copy, in place (reference :33-47; the x-extent indexes dim 2 as there, :42)."""
     lam = np.random.beta(alpha, alpha) if alpha > 0 else 1.0
     batch_size, _, H, W = x.size()
-    idx = torch.randperm(batch_size, device=x.device)
+    idx = D.agree(torch.randperm(batch_size, device=x.device))
     bbx1, bby1, bbx2, bby2 = rand_bbox(H, W, lam)
     x[:, :, bbx1:bbx2, bby1:bby2] = x[idx, :, bbx1:bbx2, bby1:bby2]
     lam = 1 - ((bbx2 - bbx1) * (bby2 - bby1) / (H * W))
@@ -56,6 +56,7 @@ def train(model, train_loader, criterion, optimizer, device):
     """One epoch, plain cross-entropy (reference :57-77)."""
     model.train()
     rank, ws = D.world()
+    D.sync_module(model)
     total_loss, correct, seen = 0.0, 0.0, 0
     for images, labels in _bar(train_loader, "Training"):
         images, labels = D.shard(images.to(device), rank, ws), D.shard(labels.to(device), rank, ws)
@@ -77,10 +78,13 @@ def evaluate(model, test_loader, criterion, device):
     """Evaluation under bf16 autocast (reference :80-99; device_type is hard-coded to "cuda" there too)."""
     model.eval()
     rank, ws = D.world()
+    D.sync_module(model)
     total_loss, correct, seen = 0.0, 0.0, 0
     with torch.no_grad():
         for images, labels in _bar(test_loader, "Evaluating"):
-            images, labels = D.shard(images.to(device), rank, ws), D.shard(labels.to(device), rank, ws)
+            images, labels = D.shard_all(images.to(device), rank, ws), D.shard_all(labels.to(device), rank, ws)
+            if images.size(0) == 0:
+                continue
             with torch.amp.autocast(device_type="cuda", dtype=torch.bfloat16):
                 outputs = model(images)
                 loss = criterion(outputs, labels)
@@ -96,6 +100,7 @@ def train_with_scheduler(model, train_loader, criterion, optimizer, scheduler, d
     """One epoch with a per-step scheduler whose step() returns the rate (reference :102-130)."""
     model.train()
     rank, ws = D.world()
+    D.sync_module(model)
     total_loss, correct, seen = 0.0, 0.0, 0
     bar = _bar(train_loader, "Training")
     for images, labels in bar:
@@ -124,6 +129,7 @@ def train_with_mixup_or_cutmix(model, train_loader, criterion, optimizer, schedu
     is sharded afterwards, so the union over ranks equals the single-process batch."""
     model.train()
     rank, ws = D.world()
+    D.sync_module(model)
     total_loss, total_correct, total_samples = 0.0, 0.0, 0
     bar = _bar(train_loader, "Training")
     for images, labels in bar:

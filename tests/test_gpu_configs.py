@@ -76,6 +76,33 @@ def test_vit_l16_384_training_step(cuda_device, curve):
         assert cases.rel_l2(ps[n].grad, p.grad) < 1e-1, (n, cases.rel_l2(ps[n].grad, p.grad))
 
 
+def test_vit_b16_224_training_step(cuda_device):
+    """The HEADLINE shape (BASELINE.json metric / configs[2]): ViT-B/16 224 px, D 768, 12 heads, MLP 3072, generalised
+    Hilbert on the 14 x 14 grid, forward + soft-target CE + backward vs the fp32 oracle (reference vit.py:325-385); depth 2
+    and batch 4 so that the CPU oracle finishes in seconds. Standing tolerances; plus the global gradient cosine."""
+    o, s = _pair(224, 16, 768, 2, 12, 3072, 1000, "hilbert")
+    s = s.to(cuda_device)
+    o.train(); s.train()
+    x = cases.make_input((4, 3, 224, 224))
+    tgt = cases.make_soft_targets(4, 1000)
+    lo = o(x)
+    loss_o = om.soft_target_cross_entropy(lo, tgt)
+    loss_o.backward()
+    ls = s(x.to(cuda_device))
+    loss_s = om.soft_target_cross_entropy(ls.float(), tgt.to(cuda_device))
+    loss_s.backward()
+    assert cases.rel_l2(ls, lo) < 2e-2, cases.rel_l2(ls, lo)
+    assert abs(float(loss_s) - float(loss_o)) < 2e-2 * abs(float(loss_o))
+    po, ps = dict(o.named_parameters()), dict(s.named_parameters())
+    assert set(po) == set(ps)
+    for n, p in po.items():
+        assert cases.rel_l2(ps[n].grad, p.grad) < 1e-1, (n, cases.rel_l2(ps[n].grad, p.grad))
+    go = torch.cat([p.grad.reshape(-1) for _, p in sorted(po.items())])
+    gs = torch.cat([ps[n].grad.float().cpu().reshape(-1) for n, _ in sorted(po.items())])
+    cos = float(torch.dot(go, gs) / (go.norm() * gs.norm()))
+    assert cos >= 0.999, cos
+
+
 def test_vit_b16_1024_long_sequence_inference(cuda_device):
     """4096 tokens per image: Hilbert order on the 64 x 64 patch grid, 2 of the 12 layers, head W_seq [1536, 4096, 64]."""
     o, s = _pair(1024, 16, 768, 2, 12, 3072, 1000, "hilbert")

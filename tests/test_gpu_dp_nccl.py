@@ -32,10 +32,17 @@ def _build(device):
 def _step(m, x, t, world_expected):
     from oracle.model import soft_target_cross_entropy
     from src.training.optim import FusedAdamW
-    opt = FusedAdamW(m.parameters(), lr=1e-3, weight_decay=0.0, max_grad_norm=0.0)
-    loss = soft_target_cross_entropy(m(x).float(), t)
-    loss.backward()
-    opt.step()
+    opt = FusedAdamW(m.parameters(), lr=0.0, weight_decay=0.0, max_grad_norm=1.0, comm_buckets=3)
+    # step 1 (lr = 0) teaches the optimizer which parameters receive gradients: its ranges are reduced inside step();
+    # step 2 is the overlapped path — per-parameter hooks all-reduce each range on the side stream during backward
+    for it in range(2):
+        opt.zero_grad()
+        loss = soft_target_cross_entropy(m(x).float(), t)
+        loss.backward()
+        for g in opt.param_groups:
+            g["lr"] = 0.0 if it == 0 else 1e-3
+        opt.step()
+    assert world_expected == 1 or opt.last_overlapped_buckets >= 2, (opt.last_overlapped_buckets, opt.last_num_buckets)
     flat = torch.cat([fb["g"].float() for fb in opt._flat]) / world_expected
     return float(loss.detach()), flat.cpu(), torch.cat([p.detach().float().reshape(-1) for p in m.parameters()]).cpu()
 

@@ -1,0 +1,227 @@
+"""FusedAdamW (src/training/optim.py) and kernel K6 against torch's own AdamW / clip_grad_norm_ (the reference's optimizer
+step: /root/reference/main.py:288-289, src/training/train.py:165-166), including the cases the round-1 review found
+unguarded: bf16 parameters with bf16 moments (what main.py:157 implies), the flat buffers built before a CUDA graph is
+captured, weight-conversion caches after raw-pointer updates, checkpoint round trips, grad-less parameters."""
+import copy
+
+import pytest
+import torch
+
+import cases
+from oracle import model as om
+
+pytestmark = pytest.mark.gpu
+
+
+def _crit(logits, tgt):
+    return om.soft_target_cross_entropy(logits.float(), tgt)
+
+
+def _model(cuda_device, dropout=False, dtype=None):
+    from src.models.vit import VisionTransformer
+    vk, tcase, mkw, batch = cases.MODEL_CASES["vit_sfc_hilbert_14x14"]
+    kind, kw, shape = cases.TOKENIZER_CASES[tcase]
+    torch.manual_seed(cases.INIT_SEED)
+    m = VisionTransformer(patch_embed=cases.build_src_tokenizer(kind, kw), **mkw)
+    if not dropout:
+        m = om.zero_dropout(m)
+    m = m.to(cuda_device).train()
+    if dtype is not None:
+        m = m.to(dtype)
+    x = cases.make_input((batch,) + tuple(shape[1:])).to(cuda_device)
+    tgt = cases.make_soft_targets(batch, mkw["num_classes"]).to(cuda_device)
+    return m, x, tgt
+
+
+@pytest.mark.parametrize("pdt,sdt", [(torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.float32), (torch.float32, torch.float32)])
+def test_adamw_kernel_matches_torch_per_dtype(cuda_device, pdt, sdt):
+    """adamw_kernel<T, S> for every instantiated (parameter, state) dtype pair. Two references on the same bf16-valued
+    gradients: torch.optim.AdamW in fp32 (the exact trajectory; the kernel computes each element in fp32 and rounds the
+    stored values once per step, so it must stay within a few bf16 ulps of it) and torch.optim.AdamW holding parameters
+    and moments in the kernel's PARAMETER dtype (what main.py:157 makes the reference run)."""
+    from sfcvit import ops
+    n, steps, lr = 40003, 4, 1e-2
+    g = torch.Generator(device="cuda").manual_seed(0)
+    p0 = torch.randn(n, generator=g, device="cuda").to(pdt)
+    grads = [(torch.randn(n, generator=g, device="cuda") * 3).to(pdt) for _ in range(steps)]
+    p32 = torch.nn.Parameter(p0.float().clone())
+    o32 = torch.optim.AdamW([p32], lr=lr, weight_decay=0.05, foreach=False)
+    pdt_ref = torch.nn.Parameter(p0.clone())
+    odt = torch.optim.AdamW([pdt_ref], lr=lr, weight_decay=0.05, foreach=False)
+    p, m, v = p0.clone(), torch.zeros(n, device="cuda", dtype=sdt), torch.zeros(n, device="cuda", dtype=sdt)
+    stats = torch.zeros(1, device="cuda")
+    hyper = torch.zeros(4, device="cuda")
+    for step, gr in enumerate(grads, 1):
+        for ref, opt in ((p32, o32), (pdt_ref, odt)):
+            ref.grad = gr.to(ref.dtype).clone()
+            torch.nn.utils.clip_grad_norm_([ref], 1.0, foreach=False)
+            opt.step()
+        stats.zero_()
+        ops.grad_sumsq(gr, stats)
+        if step % 2:                                    # both ways of passing lr / step: host scalars and the device block
+            ops.adamw_step(p, gr, m, v, lr=lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.05, step=step, max_norm=1.0, stats=stats)
+        else:
+            ops.store_f32x4(hyper, lr, 1 - 0.9 ** step, (1 - 0.999 ** step) ** 0.5, step)
+            ops.adamw_step(p, gr, m, v, lr=0.0, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.05, step=0, max_norm=1.0, stats=stats, hyper=hyper)
+    exact = p32.detach()
+    if pdt == torch.float32:
+        assert cases.rel_l2(p, exact) < 1e-5, cases.rel_l2(p, exact)
+        return
+    err = (p.float() - exact).abs()
+    ulp = 2.0 ** -7 * exact.abs().clamp_min(2.0 ** -6)        # bf16 spacing at |x| (8 significant bits), floored near zero
+    assert float((err / ulp).max()) <= steps, float((err / ulp).max())        # at most one rounding per step
+    assert cases.rel_l2(p, exact) < 3e-3, cases.rel_l2(p, exact)
+    moved = (exact - p0.float())
+    assert cases.rel_l2(p.float() - p0.float(), moved) < 0.15                # the update itself is resolved, not rounded away
+    # torch's own bf16 AdamW rounds after every elementary op: the kernel is at least as close to the exact trajectory
+    assert cases.rel_l2(p, exact) <= cases.rel_l2(pdt_ref.detach(), exact) * 1.05 + 1e-6
+    assert cases.rel_l2(p, pdt_ref.detach()) < 6e-3, cases.rel_l2(p, pdt_ref.detach())
+
+
+def test_sumsq_is_deterministic(cuda_device):
+    from sfcvit import ops
+    g = torch.randn(3_000_001, device="cuda").to(torch.bfloat16)
+    outs = []
+    for _ in range(5):
+        s = torch.zeros(1, device="cuda")
+        ops.grad_sumsq(g, s)
+        outs.append(float(s))
+    assert len(set(outs)) == 1, outs
+    assert abs(outs[0] - float(g.float().pow(2).sum())) / outs[0] < 1e-4
+
+
+def test_fused_adamw_tracks_torch_adamw_on_a_model(cuda_device):
+    """Three eager steps of the same model under FusedAdamW (flat buffers, direct gradient slices, fused clip) and under
+    torch AdamW + clip_grad_norm_ (foreach=False, as the reference calls it): parameters stay together (fp32)."""
+    from src.training.optim import FusedAdamW
+    m1, x, tgt = _model(cuda_device)
+    m2 = copy.deepcopy(m1)
+    o1 = FusedAdamW(m1.parameters(), lr=1e-3, weight_decay=0.05, max_grad_norm=1.0)
+    o2 = torch.optim.AdamW(m2.parameters(), lr=1e-3, weight_decay=0.05, foreach=False)
+    for it in range(3):
+        xx = torch.roll(x, it, 0)
+        o1.zero_grad()
+        _crit(m1(xx), tgt).backward()
+        if it == 0:                                     # gradients were written straight into the bucket (no packing copy)
+            direct = sum(p.grad is not None and p.grad.data_ptr() == o1._flat[0]["g"].data_ptr() + off * p.grad.element_size()
+                         for (p, off, _k) in o1._flat[0]["views"])
+            assert direct >= 0.8 * len(o1._flat[0]["views"]), direct
+        o1.step()
+        o2.zero_grad()
+        _crit(m2(xx), tgt).backward()
+        torch.nn.utils.clip_grad_norm_(m2.parameters(), 1.0, foreach=False)
+        o2.step()
+    torch.cuda.synchronize()
+    for (n, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert cases.rel_l2(a, b) < 2e-3, (n, cases.rel_l2(a, b))
+
+
+def test_patch_embed_weight_follows_the_optimizer(cuda_device):
+    """the kernel-layout copy of the projection weight was cached on torch's version counter, which raw-pointer
+    updates never bump — the patch embed must see every FusedAdamW step."""
+    from src.training.optim import FusedAdamW
+    m, x, tgt = _model(cuda_device)
+    opt = FusedAdamW(m.parameters(), lr=1e-2, weight_decay=0.0)
+    with torch.no_grad():
+        t0 = m.patch_embed(x).float().clone()
+    for _ in range(2):
+        opt.zero_grad()
+        _crit(m(x), tgt).backward()
+        opt.step()
+    with torch.no_grad():
+        t1 = m.patch_embed(x).float()
+        # the same numbers as a module that never saw a cache: rebuild the tokens from the current weight by hand
+        w = m.patch_embed.proj.weight.detach().clone()
+    assert cases.rel_l2(t1, t0) > 1e-3                     # the tokens moved with the weight
+    m2, _, _ = _model(cuda_device)
+    m2.load_state_dict(m.state_dict())
+    with torch.no_grad():
+        assert torch.equal(m2.patch_embed(x).float(), t1)
+    assert torch.equal(w, m.patch_embed.proj.weight.detach())
+
+
+def test_graphed_step_with_optimizer_inside_the_graph(cuda_device):
+    """GraphedStep + FusedAdamW. The optimizer owns the flat buffers before capture; the replayed graph
+    (forward + backward + clip + AdamW) must train — losses fall and follow the eager run of the same steps."""
+    from src.training.graphs import GraphedStep
+    from src.training.optim import FusedAdamW
+    m1, x, tgt = _model(cuda_device)
+    m2 = copy.deepcopy(m1)
+    o1 = FusedAdamW(m1.parameters(), lr=2e-3, weight_decay=0.01, max_grad_norm=1.0)
+    o2 = FusedAdamW(m2.parameters(), lr=2e-3, weight_decay=0.01, max_grad_norm=1.0)
+    step = GraphedStep(m1, _crit, x, tgt, optimizer=o1)
+    lg, le = [], []
+    for it in range(6):
+        for g in o1.param_groups + o2.param_groups:       # a host-side schedule must reach the captured kernel
+            g["lr"] = 2e-3 * (1.0 - 0.1 * it)
+        lg.append(float(step(x, tgt)))
+        o2.zero_grad()
+        loss = _crit(m2(x), tgt)
+        loss.backward()
+        o2.step()
+        le.append(float(loss))
+    torch.cuda.synchronize()
+    assert lg[-1] < lg[0] - 0.05, lg                        # it trains
+    for a, b in zip(lg, le):
+        assert abs(a - b) < 2e-2 * max(1.0, abs(b)), (lg, le)
+    for (n, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert cases.rel_l2(a, b) < 2e-2, (n, cases.rel_l2(a, b))
+    # eval() through the eager path sees the replay-updated weights (cache keyed on the weights epoch)
+    m1.eval(); m2.eval()
+    with torch.no_grad():
+        assert cases.rel_l2(m1(x), m2(x)) < 2e-2
+
+
+def test_graphed_step_detects_moved_parameters(cuda_device):
+    from src.training.graphs import GraphedStep
+    from src.training.optim import FusedAdamW
+    m, x, tgt = _model(cuda_device)
+    step = GraphedStep(m, _crit, x, tgt)
+    FusedAdamW(m.parameters(), lr=1e-3)                     # moves every parameter into the flat buffer AFTER capture
+    with pytest.raises(RuntimeError, match="storage moved"):
+        step(x, tgt)
+
+
+def test_optimizer_checkpoint_roundtrip(cuda_device):
+    """reference main.py:317-330 checkpoints optimizer.state_dict(): a resumed FusedAdamW continues bit-identically."""
+    from src.training.optim import FusedAdamW
+    m1, x, tgt = _model(cuda_device)
+    o1 = FusedAdamW(m1.parameters(), lr=1e-3, weight_decay=0.05, max_grad_norm=1.0)
+    for _ in range(2):
+        o1.zero_grad(); _crit(m1(x), tgt).backward(); o1.step()
+    sd_m, sd_o = copy.deepcopy(m1.state_dict()), copy.deepcopy(o1.state_dict())
+    m2, _, _ = _model(cuda_device)
+    m2.load_state_dict(sd_m)
+    o2 = FusedAdamW(m2.parameters(), lr=1e-3, weight_decay=0.05, max_grad_norm=1.0)
+    o2.load_state_dict(sd_o)
+    assert o2._step_count == 2
+    for m, o in ((m1, o1), (m2, o2)):
+        o.zero_grad(); _crit(m(x), tgt).backward(); o.step()
+    torch.cuda.synchronize()
+    for (n, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert torch.equal(a, b), n
+    for fa, fb in zip(o1._flat, o2._flat):
+        assert torch.equal(fa["m"], fb["m"]) and torch.equal(fa["v"], fb["v"])
+
+
+def test_gradless_parameters_are_left_alone(cuda_device):
+    """MixerBlock.token_mix* never receive gradients (reference vit.py:269-271): like torch's AdamW, no update and no
+    weight decay for them, and they do not disturb the norm."""
+    from src.models.vit import VisionTransformer1D
+    from src.training.optim import FusedAdamW
+    vk, tcase, mkw, batch = cases.MODEL_CASES["vit1d_hier_morton"]
+    kind, kw, shape = cases.TOKENIZER_CASES[tcase]
+    torch.manual_seed(cases.INIT_SEED)
+    m = om.zero_dropout(VisionTransformer1D(patch_embed=cases.build_src_tokenizer(kind, kw), **mkw)).to(cuda_device).train()
+    before = {n: p.detach().clone() for n, p in m.named_parameters()}
+    opt = FusedAdamW(m.parameters(), lr=1e-2, weight_decay=0.5, max_grad_norm=1.0)
+    x = cases.make_input((batch,) + tuple(shape[1:])).to(cuda_device)
+    tgt = cases.make_soft_targets(batch, mkw["num_classes"]).to(cuda_device)
+    for _ in range(2):
+        opt.zero_grad(); _crit(m(x), tgt).backward(); opt.step()
+    torch.cuda.synchronize()
+    for n, p in m.named_parameters():
+        if "token_mix" in n:
+            assert p.grad is None and torch.equal(p.detach(), before[n]), n
+        else:
+            assert not torch.equal(p.detach(), before[n]), n

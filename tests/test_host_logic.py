@@ -59,7 +59,7 @@ def test_abi_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in sfcvit.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.sfc_abi_version() == 1
+    assert lib.sfc_abi_version() == 2
     assert lib.sfc_patch_embed_kpad(3, 16, 1) == 768 and lib.sfc_patch_embed_kpad(3, 1, 16) == 64
 
 

@@ -2,9 +2,15 @@
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "space-filling-curves-for-vision-transformers_b200"))
+import subprocess
 import torch
-from sfcvit import _lib
-lib = _lib.load()
+# built on demand into tools/ (NOT part of the product library libsfcvit.so)
+PK = os.path.join(ROOT, "space-filling-curves-for-vision-transformers_b200")
+so = os.path.join(ROOT, "tools", "libsfcdebug.so")
+subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-shared",
+                       "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(PK, "csrc"),
+                       os.path.join(ROOT, "tools", "debug_bench.cu"), os.path.join(PK, "csrc", "host.cu"), "-lcuda", "-o", so])
+lib = ctypes.CDLL(so)
 f = lib.sfc_debug_bench
 f.restype = ctypes.c_int
 cyc = torch.zeros(148, dtype=torch.int64, device="cuda")
