@@ -70,10 +70,16 @@ typedef struct SfcGemmEpilogue {
   int accumulate;        /* split-K only: out += result */
   float drop_p;          /* dropout probability applied after act (0 = off) */
   unsigned long long drop_seed;
+  void* colsum_out;      /* optional [M]: colsum_out[m] = sum_k A[m, k] — for a weight gradient dW = dY^T . X this is the bias
+                            gradient sum_tokens dY (reference: autograd of every nn.Linear bias), computed as one more
+                            accumulator column of the kernel that already streams dY. Needs the split count of
+                            sfc_gemm_colsum_splits (> 0) and a workspace of sfc_gemm_workspace_bytes. */
+  int colsum_fp32;       /* 0: colsum_out is bf16, 1: fp32 */
 } SfcGemmEpilogue;
 
 size_t sfc_gemm_workspace_bytes(int M, int N, int K, int splits);
 int sfc_gemm_suggest_splits(int M, int N, int K);
+int sfc_gemm_colsum_splits(int M, int N, int K, int a_mn_major, int b_mn_major);   /* 0 = not covered: use sfc_colsum */
 int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major, long long ldb, int M,
                   int N, int K, const SfcGemmEpilogue* ep, void* workspace, size_t workspace_bytes, int splits,
                   sfc_stream_t stream);

@@ -30,15 +30,22 @@ constexpr int kNumThreads = 128 + kEpiThreads;
 struct GemmParams {
   int M, N, K;
   int num_m_tiles, num_n_tiles, splits, kblocks_per_split, num_k_blocks;
+  float* cs_ws;             // CS variant: fp32 [splits][M] partial row sums of A over K (wgrad: the bias gradient)
   EpiParams epi;
 };
 
-template <int BN, int kStages, int CL, int EPI>
+// CS ("column sums", wgrad only): db = dY^T . 1 is one more accumulator column of the GEMM that already streams dY —
+// the units of n-tile 0 issue, per k-block, four extra M x 16 MMAs of their A tile against a constant all-ones B tile
+// (1 KB of shared memory) into 16 TMEM columns behind the accumulator, and their epilogue writes that column per split.
+// The accumulator is single-buffered in this variant (256 + 16 columns do not leave room for a second 256-column
+// buffer); split-K weight gradients run one unit per CTA pair, so there is no next main loop to overlap with anyway.
+template <int BN, int kStages, int CL, int EPI, bool CS = false>
 struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (BN / CL) * BK * 2;                 // CL == 2: this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiOffset = kStages * kStageBytes;          // per-epilogue-warp stage (transpose / TMA boxes)
+  static constexpr int kOnesOffset = kStages * kStageBytes;         // CS: 8 rows x 128 B of bf16 1.0 (1024-byte aligned)
+  static constexpr int kEpiOffset = kOnesOffset + (CS ? 1024 : 0);  // per-epilogue-warp stage (transpose / TMA boxes)
   static constexpr int kEpiWarpBytes = EPI >= 3 ? 2 * kEpiStageBytes : kEpiStageBytes;   // + operand boxes
   static constexpr int kBarOffset = kEpiOffset + kEpiWarps * kEpiWarpBytes;
   static constexpr int kNumBars = 2 * kStages + 4 + 2 * kEpiWarps;  // full, empty, tmem_full[2], tmem_empty[2], operand[warp][2]
@@ -54,11 +61,14 @@ struct SmemLayout {
 //          B tile — the tensor cores of the pair exchange the B halves, so shared-memory operand reads and L2 -> SM
 //          traffic per FLOP drop by a third against CL = 1. The leader (rank 0) issues all MMAs; both CTAs' TMA loads
 //          count their bytes on the leader's full barrier; tcgen05.commit multicasts to both CTAs' barriers.
-template <int BN, int kStages, bool A_MN, bool B_MN, int EPI, int CL>
+template <int BN, int kStages, bool A_MN, bool B_MN, int EPI, int CL, bool CS = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_opnd, const GemmParams p) {
-  using L = SmemLayout<BN, kStages, CL, EPI>;
+  using L = SmemLayout<BN, kStages, CL, EPI, CS>;
+  constexpr int kAccBufs = CS ? 1 : 2;
+  constexpr uint32_t kTmemCols = CS ? (BN == 256 ? 512u : 256u) : (uint32_t)(2 * BN);
+  constexpr uint32_t kCsCol = BN;                                     // CS: 16 columns behind the (single) accumulator
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
@@ -94,8 +104,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    if constexpr (CL == 2) ptx::tmem_alloc_2cta<2 * BN>(tmem_ptr);
-    else ptx::tmem_alloc<2 * BN>(tmem_ptr);
+    if constexpr (CL == 2) ptx::tmem_alloc_2cta<kTmemCols>(tmem_ptr);
+    else ptx::tmem_alloc<kTmemCols>(tmem_ptr);
+  }
+  if constexpr (CS) {
+    if (warp == 3) {                                 // the all-ones B tile: every byte pattern of a swizzle is ones
+      reinterpret_cast<uint4*>(smem + L::kOnesOffset)[threadIdx.x & 31] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+      reinterpret_cast<uint4*>(smem + L::kOnesOffset)[32 + (threadIdx.x & 31)] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+      ptx::fence_proxy_async_smem();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -166,6 +183,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     } else if (ptx::elect_one()) {
       // ===================== MMA issuer =====================
       const uint32_t idesc = umma_idesc_bf16(BM * CL, BN, A_MN, B_MN);
+      const uint32_t idesc_cs = umma_idesc_bf16(BM * CL, 16, A_MN, false);
+      const uint64_t d_ones = umma_smem_desc_sw128(ptx::smem_u32(smem + L::kOnesOffset), 0, 1024);
       constexpr uint32_t kLboA = A_MN ? BK * 128 : 0, kLboB = B_MN ? BK * 128 : 0;
       constexpr uint32_t kAdvA = A_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;   // per UMMA_K = 16, in 16-byte units
       constexpr uint32_t kAdvB = B_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;
@@ -176,8 +195,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int split = t % p.splits;
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(kb0 + p.kblocks_per_split, p.num_k_blocks);
-        const int acc = iter & 1;
-        const uint32_t acc_phase = (iter >> 1) & 1;
+        const int acc = iter % kAccBufs;
+        const uint32_t acc_phase = (iter / kAccBufs) & 1;
+        const bool cs_unit = CS && ((t / p.splits) % p.num_n_tiles) == 0;
         if constexpr (CL == 2) ptx::mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
         else ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
@@ -195,6 +215,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint32_t accf = (kb > kb0 || k > 0) ? 1u : 0u;
             if constexpr (CL == 2) ptx::umma_f16_2cta(tmem_d, da + (uint64_t)(k * kAdvA), db + (uint64_t)(k * kAdvB), idesc, accf);
             else ptx::umma_f16(tmem_d, da + (uint64_t)(k * kAdvA), db + (uint64_t)(k * kAdvB), idesc, accf);
+          }
+          if constexpr (CS) {
+            if (cs_unit) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint32_t accf = (kb > kb0 || k > 0) ? 1u : 0u;
+                if constexpr (CL == 2) ptx::umma_f16_2cta(tmem_base + kCsCol, da + (uint64_t)(k * kAdvA), d_ones, idesc_cs, accf);
+                else ptx::umma_f16(tmem_base + kCsCol, da + (uint64_t)(k * kAdvA), d_ones, idesc_cs, accf);
+              }
+            }
           }
           // frees the smem slot (in both CTAs of a pair) when these MMAs retire
           if constexpr (CL == 2) ptx::umma_commit_2cta(&empty_bar[stage], kMask);
@@ -224,8 +254,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int tile = t / p.splits;
       const int n_tile = tile % p.num_n_tiles;
       const int m_tile = (tile / p.num_n_tiles) * CL + crank;
-      const int acc = iter & 1;
-      const uint32_t acc_phase = (iter >> 1) & 1;
+      const int acc = iter % kAccBufs;
+      const uint32_t acc_phase = (iter / kAccBufs) & 1;
       ptx::mbar_wait_sleep(&tmem_full[acc], acc_phase, 64);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + half * (BN / 2) + ((uint32_t)(quarter * 32) << 16);
@@ -234,6 +264,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if constexpr (EPI >= 2) epi_tile_tma<EPI - 2>(p.epi, &tmap_out, &tmap_opnd, taddr, n0, BN / 2, m0, stage, box_counter, opnd_bar + 2 * (warp - 4));
       else if constexpr (EPI == 1) epi_tile_fast(p.epi, taddr, n0, BN / 2, m0, (long long)p.M, EpiRowIdentity{}, split, stage);
       else epi_tile(p.epi, taddr, n0, BN / 2, m0, (long long)p.M, EpiRowIdentity{}, split, stage);
+      if constexpr (CS) {
+        if (n_tile == 0 && half == 0) {              // the row sums of this unit's A rows over its k range (lane = row)
+          uint32_t r16[16];
+          ptx::tmem_ld_x16(tmem_base + kCsCol + ((uint32_t)(quarter * 32) << 16), r16);
+          ptx::tmem_ld_wait();
+          const long long m = m0 + (threadIdx.x & 31);
+          if (m < p.M) p.cs_ws[(long long)split * p.M + m] = __uint_as_float(r16[0]);
+        }
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if ((threadIdx.x & 31) == 0) {               // the accumulator buffer is drained: tell the (leader's) MMA issuer
@@ -249,18 +288,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if constexpr (CL > 1) ptx::cluster_sync();       // no CTA exits (or frees TMEM) while its peer may still touch it
   if (warp == 2) {
     ptx::tc_fence_after();
-    if constexpr (CL == 2) ptx::tmem_dealloc_2cta<2 * BN>(tmem_base);
-    else ptx::tmem_dealloc<2 * BN>(tmem_base);
+    if constexpr (CL == 2) ptx::tmem_dealloc_2cta<kTmemCols>(tmem_base);
+    else ptx::tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
 // out[m,n] (bf16 or fp32) = (accumulate ? out : 0) + act(alpha * sum_s ws[s,m,n] + bias[n])
+// column-sum partials of the CS variant: cs_out[m] = sum_s cs_ws[s, m] (threads past the main range)
+__device__ __forceinline__ void reduce_colsum(long long i, const float* __restrict__ cs_ws, int splits, int M, void* __restrict__ cs_out,
+                                              int cs_fp32) {
+  if (cs_ws == nullptr || i >= M) return;
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += cs_ws[(long long)k * M + i];
+  if (cs_fp32) reinterpret_cast<float*>(cs_out)[i] = s;
+  else reinterpret_cast<__nv_bfloat16*>(cs_out)[i] = __float2bfloat16(s);
+}
+
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, long long split_stride, int splits, void* __restrict__ out,
                                      long long ld_out, int M, int N, int out_fp32, int accumulate, float alpha,
-                                     const __nv_bfloat16* __restrict__ bias, int act) {
+                                     const __nv_bfloat16* __restrict__ bias, int act, const float* __restrict__ cs_ws,
+                                     void* __restrict__ cs_out, int cs_fp32) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)M * N;
-  if (idx >= total) return;
+  if (idx >= total) { reduce_colsum(idx - total, cs_ws, splits, M, cs_out, cs_fp32); return; }
   const long long m = idx / N, n = idx % N;
   float s = 0.f;
   for (int k = 0; k < splits; ++k) s += ws[k * split_stride + idx];
@@ -281,9 +331,10 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, long long spl
 // loads, four independent partial sums so that the loads of a thread are all in flight together
 __global__ void __launch_bounds__(256) splitk_reduce_vec4_kernel(const float4* __restrict__ ws, long long split_stride4, int splits,
                                                                  void* __restrict__ out, long long ld_out, int M, int N4, int out_fp32,
-                                                                 int accumulate) {
+                                                                 int accumulate, const float* __restrict__ cs_ws,
+                                                                 void* __restrict__ cs_out, int cs_fp32) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)M * N4) return;
+  if (idx >= (long long)M * N4) { reduce_colsum(idx - (long long)M * N4, cs_ws, splits, M, cs_out, cs_fp32); return; }
   const long long m = idx / N4, n = (idx % N4) * 4;
   float4 a[4];
 #pragma unroll
@@ -325,11 +376,11 @@ constexpr int gemm_stages(int bn, int cl, int epi) {
   return s > 8 ? 8 : s;
 }
 
-template <int BN, int kStages, bool A_MN, bool B_MN, int EPI, int CL>
+template <int BN, int kStages, bool A_MN, bool B_MN, int EPI, int CL, bool CS = false>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& topnd, const GemmParams& p,
                 cudaStream_t stream) {
-  using L = SmemLayout<BN, kStages, CL, EPI>;
-  auto kern = gemm_bf16_kernel<BN, kStages, A_MN, B_MN, EPI, CL>;
+  using L = SmemLayout<BN, kStages, CL, EPI, CS>;
+  auto kern = gemm_bf16_kernel<BN, kStages, A_MN, B_MN, EPI, CL, CS>;
   static bool configured = false;
   if (!configured) {
     SFC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -354,9 +405,11 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
 
 }  // namespace
 
+extern "C" int sfc_gemm_suggest_splits(int M, int N, int K);
+
 extern "C" size_t sfc_gemm_workspace_bytes(int M, int N, int K, int splits) {
   if (splits <= 1) return 0;
-  return (size_t)splits * (size_t)M * (size_t)N * sizeof(float);
+  return (size_t)splits * (size_t)M * ((size_t)N + 1) * sizeof(float);      // partial tiles + partial column sums
 }
 
 // Split-K factor for reductions over the token dimension (wgrad): the output has few tiles, so K is cut into `s`
@@ -371,6 +424,18 @@ static int gemm_pick_bn(int N, int K) {
   static const bool off = getenv("SFC_GEMM_BN256") != nullptr;
   const long long pad256 = (long long)sfc_ceil_div(N, 256) * 256, pad128 = (long long)sfc_ceil_div(N, 128) * 128;
   return (!off && pad128 < pad256 && pad256 * 100 > (long long)N * 115) ? 128 : 256;
+}
+
+// Split count for a GEMM that also returns the row sums of A over K (ep->colsum_out; wgrad: the bias gradient) inside
+// the same kernel, or 0 when no fused variant covers the shape (the caller then uses sfc_colsum). The fused variant is
+// the split-K CTA-pair kernel with MN-major operands: M >= 2 row tiles, K >= 2 k-blocks, N % 32 == 0.
+extern "C" int sfc_gemm_colsum_splits(int M, int N, int K, int a_mn_major, int b_mn_major) {
+  if (!a_mn_major || !b_mn_major) return 0;
+  if (sfc_ceil_div(M, BM) < 2 || sfc_ceil_div(K, BK) < 2 || N % 32 != 0 || N < 32) return 0;
+  static const bool off = getenv("SFC_GEMM_NOCOLSUM") != nullptr;
+  if (off) return 0;
+  const int s = sfc_gemm_suggest_splits(M, N, K);
+  return s < 2 ? 2 : s;
 }
 
 extern "C" int sfc_gemm_suggest_splits(int M, int N, int K) {
@@ -425,6 +490,11 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
   SFC_REQUIRE(e.aux_mode == SFC_AUX_NONE || e.aux != nullptr, "sfc_gemm_bf16: aux_mode set but aux is null");
   SFC_REQUIRE(e.drop_p >= 0.f && e.drop_p < 1.f, "sfc_gemm_bf16: dropout p out of range");
 
+  p.cs_ws = nullptr;
+  const bool want_cs = ep->colsum_out != nullptr;
+  if (want_cs)
+    SFC_REQUIRE(splits > 1 && a_mn_major && b_mn_major && p.num_m_tiles >= 2 && N % 32 == 0,
+                "sfc_gemm_bf16: colsum_out needs the split-K MN-major (wgrad) path: ask sfc_gemm_colsum_splits first");
   GemmParams pk = p;
   if (splits > 1) {
     // bias and activation are applied by the reduce kernel (skinny weight-streaming GEMMs: the factorised head at small
@@ -435,6 +505,10 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
     const size_t need = (size_t)splits * (size_t)M * (size_t)N * sizeof(float);
     SFC_REQUIRE(workspace && workspace_bytes >= need, "sfc_gemm_bf16: split-K workspace too small (%zu < %zu)", workspace_bytes, need);
     pk.epi.out = workspace; pk.epi.out_fp32 = 1; pk.epi.ld_out = N; pk.epi.split_stride = (long long)M * N;
+    if (want_cs) {
+      SFC_REQUIRE(workspace_bytes >= need + (size_t)splits * (size_t)M * sizeof(float), "sfc_gemm_bf16: workspace too small for the column sums");
+      pk.cs_ws = reinterpret_cast<float*>(workspace) + (size_t)splits * (size_t)M * (size_t)N;
+    }
   } else {
     SFC_REQUIRE(!ep->accumulate, "sfc_gemm_bf16: accumulate requires split-K (splits > 1)");
   }
@@ -442,6 +516,7 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
   const bool fast = epi_fast_ok(pk.epi);
   static const bool cl_off = getenv("SFC_GEMM_NOCLUSTER") != nullptr;
   const bool cl2 = fast && !cl_off && p.num_m_tiles >= 2;      // CTA pairs, tcgen05.mma.cta_group::2
+  if (want_cs) SFC_REQUIRE(fast && cl2, "sfc_gemm_bf16: colsum_out: operands must be 16-byte aligned (fast epilogue) and CTA pairs enabled");
   static const bool tma_off = getenv("SFC_GEMM_NOTMASTORE") != nullptr;
   // bf16 output: staged in swizzled smem boxes and stored by TMA (EPI 2); one [M, N] operand (residual or ReLU-mask
   // source) is fetched by TMA the same way (EPI 3 / 4). fp32 output (split-K partials) and residual + aux together keep
@@ -485,7 +560,10 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
     else if (fast) SFC_DISPATCH2(BN_, 1, 1);                                           \
     else SFC_DISPATCH2(BN_, 0, 1);                                                     \
   } while (0)
-  if (BN == 256) SFC_DISPATCH(256); else SFC_DISPATCH(128);
+  if (want_cs) {
+    if (BN == 256) rc = launch_gemm<256, gemm_stages(256, 2, 1), true, true, 1, 2, true>(ta, tb, tout, topnd, pk, stream);
+    else rc = launch_gemm<128, gemm_stages(128, 2, 1), true, true, 1, 2, true>(ta, tb, tout, topnd, pk, stream);
+  } else if (BN == 256) SFC_DISPATCH(256); else SFC_DISPATCH(128);
 #undef SFC_DISPATCH2
 #undef SFC_DISPATCH
   if (rc) return rc;
@@ -495,13 +573,15 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
     const int threads = 256;
     const bool vec4 = N % 4 == 0 && ep->ld_out % 4 == 0 && !ep->bias && ep->act == SFC_ACT_NONE && ep->alpha == 1.0f &&
                       (reinterpret_cast<uintptr_t>(ep->out) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0;
+    const long long extra = want_cs ? M : 0;                  // threads past the main range reduce the column sums
     if (vec4)
-      splitk_reduce_vec4_kernel<<<(unsigned)((total / 4 + threads - 1) / threads), threads, 0, stream>>>(
-          (const float4*)workspace, (long long)M * N / 4, splits, ep->out, ep->ld_out, M, N / 4, ep->out_fp32, ep->accumulate);
+      splitk_reduce_vec4_kernel<<<(unsigned)((total / 4 + extra + threads - 1) / threads), threads, 0, stream>>>(
+          (const float4*)workspace, (long long)M * N / 4, splits, ep->out, ep->ld_out, M, N / 4, ep->out_fp32, ep->accumulate,
+          pk.cs_ws, ep->colsum_out, ep->colsum_fp32);
     else
-      splitk_reduce_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(
+      splitk_reduce_kernel<<<(unsigned)((total + extra + threads - 1) / threads), threads, 0, stream>>>(
         (const float*)workspace, (long long)M * N, splits, ep->out, ep->ld_out, M, N, ep->out_fp32, ep->accumulate, ep->alpha,
-        (const __nv_bfloat16*)ep->bias, ep->act);
+        (const __nv_bfloat16*)ep->bias, ep->act, pk.cs_ws, ep->colsum_out, ep->colsum_fp32);
     SFC_LAUNCH_OK();
   }
   return 0;

@@ -18,7 +18,7 @@ class SfcGemmEpilogue(ctypes.Structure):
         ("ld_out", ctypes.c_longlong), ("ld_res", ctypes.c_longlong), ("ld_aux", ctypes.c_longlong),
         ("alpha", ctypes.c_float), ("act", ctypes.c_int), ("aux_mode", ctypes.c_int),
         ("out_fp32", ctypes.c_int), ("accumulate", ctypes.c_int), ("drop_p", ctypes.c_float),
-        ("drop_seed", ctypes.c_ulonglong),
+        ("drop_seed", ctypes.c_ulonglong), ("colsum_out", ctypes.c_void_p), ("colsum_fp32", ctypes.c_int),
     ]
 
 
@@ -34,6 +34,7 @@ SIGNATURES = {
     "sfc_curve_perm": (_i, [_i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "sfc_gemm_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "sfc_gemm_suggest_splits": (_i, [_i, _i, _i]),
+    "sfc_gemm_colsum_splits": (_i, [_i, _i, _i, _i, _i]),
     "sfc_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _vp]),
     "sfc_layernorm_bwd_scratch_bytes": (_sz, [_ll, _i]),
     "sfc_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, ctypes.c_ulonglong, _vp, _vp, _vp, _i, _i, _vp, _sz, _ll, _i, _vp]),

@@ -128,10 +128,13 @@ def linear_backward(dy2, x2, wb, w_dtype, need_dx, need_dw, need_db, *, dx_aux=N
             wbp[:N] = wb
         dx = ops.gemm(dyp, wbp, b_mn=True, aux=dx_aux, aux_mode=dx_aux_mode, alpha=dx_alpha, residual=dx_residual)
     if need_dw:
-        dst = _usable(grad_out(w_param), (dyp.shape[1], x2.shape[1]), w_dtype) if dyp.shape[1] == N else None
-        dwp = ops.gemm(dyp, x2, a_mn=True, b_mn=True, out=dst, out_dtype=w_dtype, splits=0)
-        dw = dwp[:N] if dwp.shape[0] != N else dwp
-    if need_db:
+        padded = dyp.shape[1] != N
+        dst = _usable(grad_out(w_param), (N, x2.shape[1]), w_dtype) if not padded else None
+        fuse_db = need_db and not padded
+        dwp, db = ops.wgrad(dyp, x2, w_dtype, dw_out=dst, want_db=fuse_db,
+                            db_out=_usable(grad_out(b_param), (N,), w_dtype) if fuse_db else None)
+        dw = dwp[:N] if padded else dwp
+    if need_db and db is None:
         db = ops.colsum(dy2, w_dtype, out=_usable(grad_out(b_param), (N,), w_dtype))
     return dx, dw, db
 
@@ -445,8 +448,7 @@ class EncoderLayerFn(Function):
         dw2 = ops.gemm(dy2d, h, a_mn=True, b_mn=True, out=o_w2, out_dtype=pdt, splits=0)
         # linear1 (+ residual gradient of x1 fused)
         dx1 = ops.gemm(dh, wf1, b_mn=True, residual=dy2)
-        dw1 = ops.gemm(dh, x1, a_mn=True, b_mn=True, out=o_w1, out_dtype=pdt, splits=0)
-        db1 = ops.colsum(dh, pdt, out=o_b1)
+        dw1, db1 = ops.wgrad(dh, x1, pdt, dw_out=o_w1, db_out=o_b1, want_db=True)       # db1 = one more accumulator column
         # LN1
         dy1, dg1, dbe1, dy1d, dbo = ops.layernorm_bwd(dx1, y1, mean1, rstd1, g1b, pdt, drop_p=p_d1, drop_seed=s_d1, want_colsum=True,
                                                       dgamma_out=o_g1, dbeta_out=o_be1, colsum_out=o_bo)
@@ -459,8 +461,7 @@ class EncoderLayerFn(Function):
         dqkv = ops.attn_bwd(qkv, attn, dattn, lse, B, heads, N, drop_p=p_attn, drop_seed=s_attn)
         # in_proj (+ residual gradient of x fused)
         dx = ops.gemm(dqkv, wi, b_mn=True, residual=dy1) if ctx.needs_input_grad[0] else None
-        dwi = ops.gemm(dqkv, x2, a_mn=True, b_mn=True, out=o_wi, out_dtype=pdt, splits=0)
-        dbi = ops.colsum(dqkv, pdt, out=o_bi)
+        dwi, dbi = ops.wgrad(dqkv, x2, pdt, dw_out=o_wi, db_out=o_bi, want_db=True)
         if dx is not None:
             dx = dx.reshape(B, N, D)
         return (dx, dwi, dbi, dwo, dbo, dw1, db1, dw2, db2, dg1, dbe1, dg2, dbe2, None, None, None, None)

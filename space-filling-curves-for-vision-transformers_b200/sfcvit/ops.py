@@ -75,9 +75,11 @@ def curve_perm(curve, w: int, h: int, device="cuda"):
 
 def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=None, aux_mode=AUX_NONE, act=ACT_NONE,
          alpha=1.0, out=None, out_dtype=torch.bfloat16, want_pre=False, splits=1, accumulate=False, drop_p=0.0,
-         drop_seed=0):
+         drop_seed=0, colsum_out=None):
     """D[M,N] = epilogue(alpha * A.B^T).  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn); bf16, 2-D,
-    inner dimension contiguous. Returns out (and out_pre when want_pre)."""
+    inner dimension contiguous. Returns out (and out_pre when want_pre).
+    colsum_out: optional [M] tensor receiving sum_k A[m, k] from the same kernel (wgrad: the bias gradient); only when
+    gemm_colsum_splits(...) > 0 — pass that value as `splits`."""
     lib = _lib.load()
     _require_cuda(a, b, bias, residual, aux, out)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.dim() == 2 and b.dim() == 2
@@ -114,6 +116,13 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=None, au
     ep.accumulate = 1 if accumulate else 0
     ep.drop_p = float(drop_p)
     ep.drop_seed = int(drop_seed) & 0xFFFFFFFFFFFFFFFF
+    if colsum_out is not None:
+        assert colsum_out.numel() == M and colsum_out.is_contiguous() and colsum_out.dtype in (torch.bfloat16, torch.float32)
+        ep.colsum_out = colsum_out.data_ptr()
+        ep.colsum_fp32 = 1 if colsum_out.dtype == torch.float32 else 0
+    else:
+        ep.colsum_out = None
+        ep.colsum_fp32 = 0
     if splits is None or splits == 0:
         splits = lib.sfc_gemm_suggest_splits(M, N, K)
     ws, ws_bytes = None, 0
@@ -133,6 +142,24 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=None, au
     _lib.check(rc, "sfc_gemm_bf16")
     _count(2 if splits > 1 else 1)
     return (out, pre) if want_pre else out
+
+
+def wgrad(dy, x, w_dtype, *, dw_out=None, db_out=None, want_db=False):
+    """dW[N, K] = dY[M, N]^T . X[M, K] (split-K over the M tokens) and, when want_db, db[N] = sum_m dY[m, :] — as one more
+    accumulator column of the SAME kernel when the shape is covered (no second pass over dY), else by sfc_colsum."""
+    lib = _lib.load()
+    Mtok, N = dy.shape
+    K = x.shape[1]
+    db = None
+    if want_db:
+        s = lib.sfc_gemm_colsum_splits(N, K, Mtok, 1, 1)
+        if s > 0 and dy.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0:
+            db = _param_out(db_out, N, w_dtype, dy.device)
+            dw = gemm(dy, x, a_mn=True, b_mn=True, out=dw_out, out_dtype=w_dtype, splits=s, colsum_out=db)
+            return dw, db
+        db = colsum(dy, w_dtype, out=db_out)
+    dw = gemm(dy, x, a_mn=True, b_mn=True, out=dw_out, out_dtype=w_dtype, splits=0)
+    return dw, db
 
 
 # ------------------------------------------------------------------ K5: LayerNorm / column sums

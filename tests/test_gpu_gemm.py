@@ -79,3 +79,36 @@ def test_gemm_splitk_accumulate(cuda_device, out_dtype):
     ops.gemm(a, b, a_mn=True, b_mn=True, out=out, splits=4, accumulate=True)
     ref = base.float() + a.float().t() @ b.float()
     assert float((out.float() - ref).norm() / ref.norm()) < (1e-4 if out_dtype == "fp32" else 6e-3)
+
+
+@pytest.mark.parametrize("shape", [(3072, 768, 50176 // 8), (2304, 768, 3920), (1024, 384, 1568), (256, 768, 136), (384, 96, 1000),
+                                   (200, 64, 392), (128, 768, 4096), (1000, 1536, 784)])
+@pytest.mark.parametrize("wdt", ["bf16", "fp32"])
+def test_wgrad_with_fused_bias_gradient(cuda_device, shape, wdt):
+    """ops.wgrad: dW = dY^T X and db = sum_tokens dY. Covered shapes get db as one more accumulator column of the wgrad
+    kernel (all-ones B tile; reference: autograd of nn.Linear's bias); the others use the separate column-sum kernel —
+    either way the numbers must equal torch fp32 sums of the same bf16 inputs (db: fp32 accumulation, one rounding)."""
+    import torch
+    from sfcvit import _lib, ops
+    N, K, Mtok = shape
+    dt = torch.bfloat16 if wdt == "bf16" else torch.float32
+    g = torch.Generator(device="cuda").manual_seed(N + K)
+    dy = (torch.randn(Mtok, N, generator=g, device="cuda") * 0.5 + 0.05).to(torch.bfloat16)
+    x = torch.randn(Mtok, K, generator=g, device="cuda").to(torch.bfloat16)
+    fused = _lib.load().sfc_gemm_colsum_splits(N, K, Mtok, 1, 1) > 0
+    assert fused == (N > 128 and K % 32 == 0 and Mtok > 64)
+    l0 = ops.LAUNCHES
+    dw, db = ops.wgrad(dy, x, dt, want_db=True)
+    launches = ops.LAUNCHES - l0
+    assert launches == (2 if fused else 2 + (2 if _lib.load().sfc_gemm_suggest_splits(N, K, Mtok) > 1 else 1)), launches
+    ref_w = dy.float().t() @ x.float()
+    ref_b = dy.float().sum(0)
+    assert dw.dtype == dt and db.dtype == dt and tuple(dw.shape) == (N, K) and tuple(db.shape) == (N,)
+    tol = 6e-3 if wdt == "bf16" else 2e-5
+    assert float((dw.float() - ref_w).norm() / ref_w.norm()) < tol
+    assert float((db.float() - ref_b).norm() / ref_b.norm()) < (4e-3 if wdt == "bf16" else 1e-5)
+    # destinations supplied by the caller (slices of a flat gradient bucket)
+    flat = torch.zeros(N * K + N + 64, dtype=dt, device="cuda")
+    dw2, db2 = ops.wgrad(dy, x, dt, want_db=True, dw_out=flat[:N * K].view(N, K), db_out=flat[N * K:N * K + N])
+    assert dw2.data_ptr() == flat.data_ptr() and torch.equal(dw2, dw) and torch.equal(db2, db)
+    assert float(flat[N * K + N:].abs().sum()) == 0.0

@@ -70,12 +70,12 @@ def test_adamw_kernel_matches_torch_per_dtype(cuda_device, pdt, sdt):
     err = (p.float() - exact).abs()
     ulp = 2.0 ** -7 * exact.abs().clamp_min(2.0 ** -6)        # bf16 spacing at |x| (8 significant bits), floored near zero
     assert float((err / ulp).max()) <= steps, float((err / ulp).max())        # at most one rounding per step
-    assert cases.rel_l2(p, exact) < 3e-3, cases.rel_l2(p, exact)
+    assert cases.rel_l2(p, exact) < 6e-3, cases.rel_l2(p, exact)   # 4 roundings of ~0.29 ulp rms, ulp/|x| in [2^-8, 2^-7]
     moved = (exact - p0.float())
     assert cases.rel_l2(p.float() - p0.float(), moved) < 0.15                # the update itself is resolved, not rounded away
     # torch's own bf16 AdamW rounds after every elementary op: the kernel is at least as close to the exact trajectory
     assert cases.rel_l2(p, exact) <= cases.rel_l2(pdt_ref.detach(), exact) * 1.05 + 1e-6
-    assert cases.rel_l2(p, pdt_ref.detach()) < 6e-3, cases.rel_l2(p, pdt_ref.detach())
+    assert cases.rel_l2(p, pdt_ref.detach()) < 1.5e-2, cases.rel_l2(p, pdt_ref.detach())
 
 
 def test_sumsq_is_deterministic(cuda_device):
