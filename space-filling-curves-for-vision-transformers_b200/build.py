@@ -14,9 +14,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OBJ_DIR = os.path.join(HERE, "build")
+_TL = bool(os.environ.get("SFC_ATTN_TIMELINE"))               # debug build with clock64 stamps (tools/attn_timeline*.py)
+OBJ_DIR = os.path.join(HERE, "build_tl" if _TL else "build")
 LIB_DIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIB_DIR, "libsfcvit.so")
+LIB = os.path.join(LIB_DIR, "libsfcvit_tl.so" if _TL else "libsfcvit.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

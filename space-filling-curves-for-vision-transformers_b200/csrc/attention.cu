@@ -85,6 +85,12 @@ __device__ __forceinline__ void store_p_half(uint32_t buf, int r, int c16, const
   }
 }
 
+#ifdef SFC_ATTN_TIMELINE
+#define SFC_TL(...) __VA_ARGS__
+#else
+#define SFC_TL(...)
+#endif
+
 // ================================================= forward =================================================
 // Persistent, warp-specialised. Work item = (image b, head h, query pair qp): 256 query rows = two 128-row tiles A
 // and B, each owned by one softmax warpgroup (thread <-> query row <-> TMEM lane), so the tensor core, the TMA engine
@@ -132,10 +138,104 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// ---- the exp pass as an explicitly interleaved instruction stream -------------------------------------------------
+// Measured (profiles/r2_attn_fwd_timeline.txt, tools/pipe_bench.cu): MUFU.EX2 occupies its pipe for 8 cycles per warp
+// instruction but does NOT block the scheduler — other pipes keep issuing — provided the instruction stream offers them
+// work BETWEEN the MUFUs. Left to ptxas, a 32-column chunk became 32 x (FFMA, MUFU, FADD) followed by ~140 integer / select
+// / convert instructions of the dropout mask and the bf16 pack: two phases bound by different pipes that a warp executes
+// one after the other (18 cycles per element instead of 8). Here the stream is written out by hand in units of 16 key
+// columns (= one dropout group): `volatile` keeps the order, so while unit u's exponentials go down the MUFU pipe the
+// row sum, mask, pack and shared-memory store of unit u-1 fill the issue slots in between (~6.5 instructions per MUFU).
+template <int I>
+__device__ __forceinline__ void exp_post_elem(float& pv, float& psum, uint32_t seed, uint32_t thr_hi, bool drop) {
+  asm volatile("add.f32 %0, %0, %1;" : "+f"(psum) : "f"(pv));                 // the denominator sums the UNMASKED probabilities
+  if (drop) {
+    constexpr uint32_t A = lcg_mul(I + 1), C = lcg_add(I + 1);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .u32 t;\n\t"
+        "mad.lo.u32 t, %1, %2, %3;\n\t"
+        "setp.ge.u32 p, t, %4;\n\t"
+        "selp.f32 %0, %0, 0f00000000, p;\n\t"
+        "}"
+        : "+f"(pv)
+        : "r"(seed), "n"(A), "n"(C), "r"(thr_hi));
+  }
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// shared-memory address (32-bit window) of the 16-byte slot j8 (8 keys) of row r in the K-major SW128 P operand
+__device__ __forceinline__ uint32_t p_slot_addr(uint32_t rowbase, int rx, int j8) {
+  return rowbase + (uint32_t)((j8 >> 3) * kTile + (((j8 & 7) ^ rx) << 4));
+}
+
+// One pipeline step: exponentials of 16 raw scores s[0..15] into pn[] (stage A of the current unit) interleaved with the
+// row sum / dropout mask / pack / store of the previous unit's probabilities pp[] (stage B). kDrop: pp's mask comes from
+// `seed_prev` (one hash per aligned group of 16 keys, csrc/gemm_epilogue.cuh). st0 / st1: the previous unit's two slots.
+template <bool kDrop, int I>
+__device__ __forceinline__ void exp_step_elem(const uint32_t* s, float sl2, float nmb, float* pn, float* pp, float& psum,
+                                              uint32_t seed_prev, uint32_t thr_hi, uint32_t* pk) {
+  float x;
+  asm volatile("fma.rn.f32 %0, %1, %2, %3;" : "=f"(x) : "f"(__uint_as_float(s[I])), "f"(sl2), "f"(nmb));
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(pn[I]) : "f"(x));
+  exp_post_elem<I>(pp[I], psum, seed_prev, thr_hi, kDrop);
+  if constexpr ((I & 1) == 1) pk[I >> 1] = cvt_bf16x2(pp[I - 1], pp[I]);
+}
+template <bool kDrop>
+__device__ __forceinline__ void exp_step(const uint32_t* s, float sl2, float nmb, float (&pn)[16], float (&pp)[16], float& psum,
+                                         uint32_t seed_prev, uint32_t thr_hi, uint32_t st0, uint32_t st1) {
+  uint32_t pk[8];
+  exp_step_elem<kDrop, 0>(s, sl2, nmb, pn, pp, psum, seed_prev, thr_hi, pk);
+  exp_step_elem<kDrop, 1>(s, sl2, nmb, pn, pp, psum, seed_prev, thr_hi, pk);
+  exp_step_elem<kDrop, 2>(s, sl2, nmb, pn, pp, psum, seed_prev, thr_hi, pk);
+  exp_step_elem<kDrop, 3>(s, sl2, nmb, pn, pp, psum, seed_prev, thr_hi, pk);
+  exp_step_elem<kDrop, 4>(s, sl2, nmb, pn, pp, psum, seed_prev, thr_hi, pk);
+  exp_step_elem<kDrop, 5>(s, sl2, nmb, pn, pp, psum, seed_prev, thr_hi, pk);
+  exp_step_elem<kDrop, 6>(s, sl2, nmb, pn, pp, psum, seed_prev, thr_hi, pk);
+  exp_step_elem<kDrop, 7>(s, sl2, nmb, pn, pp, psum, seed_prev, thr_hi, pk);
+  sts_v4(st0, pk[0], pk[1], pk[2], pk[3]);
+  exp_step_elem<kDrop, 8>(s, sl2, nmb, pn, pp, psum, seed_prev, thr_hi, pk);
+  exp_step_elem<kDrop, 9>(s, sl2, nmb, pn, pp, psum, seed_prev, thr_hi, pk);
+  exp_step_elem<kDrop, 10>(s, sl2, nmb, pn, pp, psum, seed_prev, thr_hi, pk);
+  exp_step_elem<kDrop, 11>(s, sl2, nmb, pn, pp, psum, seed_prev, thr_hi, pk);
+  exp_step_elem<kDrop, 12>(s, sl2, nmb, pn, pp, psum, seed_prev, thr_hi, pk);
+  exp_step_elem<kDrop, 13>(s, sl2, nmb, pn, pp, psum, seed_prev, thr_hi, pk);
+  exp_step_elem<kDrop, 14>(s, sl2, nmb, pn, pp, psum, seed_prev, thr_hi, pk);
+  exp_step_elem<kDrop, 15>(s, sl2, nmb, pn, pp, psum, seed_prev, thr_hi, pk);
+  sts_v4(st1, pk[4], pk[5], pk[6], pk[7]);
+}
+// drains the pipeline: stage B of the last unit
+template <bool kDrop, int I>
+__device__ __forceinline__ void exp_flush_elem(float* pp, float& psum, uint32_t seed_prev, uint32_t thr_hi, uint32_t* pk) {
+  exp_post_elem<I>(pp[I], psum, seed_prev, thr_hi, kDrop);
+  if constexpr ((I & 1) == 1) pk[I >> 1] = cvt_bf16x2(pp[I - 1], pp[I]);
+}
+template <bool kDrop>
+__device__ __forceinline__ void exp_flush(float (&pp)[16], float& psum, uint32_t seed_prev, uint32_t thr_hi, uint32_t st0, uint32_t st1) {
+  uint32_t pk[8];
+  exp_flush_elem<kDrop, 0>(pp, psum, seed_prev, thr_hi, pk);   exp_flush_elem<kDrop, 1>(pp, psum, seed_prev, thr_hi, pk);
+  exp_flush_elem<kDrop, 2>(pp, psum, seed_prev, thr_hi, pk);   exp_flush_elem<kDrop, 3>(pp, psum, seed_prev, thr_hi, pk);
+  exp_flush_elem<kDrop, 4>(pp, psum, seed_prev, thr_hi, pk);   exp_flush_elem<kDrop, 5>(pp, psum, seed_prev, thr_hi, pk);
+  exp_flush_elem<kDrop, 6>(pp, psum, seed_prev, thr_hi, pk);   exp_flush_elem<kDrop, 7>(pp, psum, seed_prev, thr_hi, pk);
+  sts_v4(st0, pk[0], pk[1], pk[2], pk[3]);
+  exp_flush_elem<kDrop, 8>(pp, psum, seed_prev, thr_hi, pk);   exp_flush_elem<kDrop, 9>(pp, psum, seed_prev, thr_hi, pk);
+  exp_flush_elem<kDrop, 10>(pp, psum, seed_prev, thr_hi, pk);  exp_flush_elem<kDrop, 11>(pp, psum, seed_prev, thr_hi, pk);
+  exp_flush_elem<kDrop, 12>(pp, psum, seed_prev, thr_hi, pk);  exp_flush_elem<kDrop, 13>(pp, psum, seed_prev, thr_hi, pk);
+  exp_flush_elem<kDrop, 14>(pp, psum, seed_prev, thr_hi, pk);  exp_flush_elem<kDrop, 15>(pp, psum, seed_prev, thr_hi, pk);
+  sts_v4(st1, pk[4], pk[5], pk[6], pk[7]);
+}
+
 template <bool kSingle, bool kDrop>
 __global__ void __launch_bounds__(kFwdThreads, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, const AttnParams p,
-                const FwdLayout L) {
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                const __grid_constant__ CUtensorMap tmap_o, const AttnParams p, const FwdLayout L) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
@@ -150,6 +250,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (tid == 0) {
     ptx::prefetch_tmap(&tmap_q);
     ptx::prefetch_tmap(&tmap_kv);
+    ptx::prefetch_tmap(&tmap_o);
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bars[FwdBars::q_full + i], 1);
       ptx::mbar_init(&bars[FwdBars::q_empty + i], 1);
@@ -181,7 +282,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int qp = item % nqp, h = (item / nqp) % p.H, b = item / (nqp * p.H);
         const int row0 = b * p.N;
         for (int w = 0; w < 2; ++w) {
-          ptx::mbar_wait(&bars[FwdBars::q_empty + w], (ii & 1) ^ 1);
+          ptx::mbar_wait_relaxed(&bars[FwdBars::q_empty + w], (ii & 1) ^ 1);
           ptx::mbar_expect_tx(&bars[FwdBars::q_full + w], kTile);
           ptx::tma_load_2d(&tmap_q, &bars[FwdBars::q_full + w], smem + w * kTile, h * DH, row0 + qp * 2 * BQ + w * BQ);
         }
@@ -189,10 +290,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const int g = ii * nkv + j;
           const int st = g % stages;
           const uint32_t ph = (uint32_t)((g / stages) & 1);
-          ptx::mbar_wait(&bars[FwdBars::k_empty + st], ph ^ 1);
+          ptx::mbar_wait_relaxed(&bars[FwdBars::k_empty + st], ph ^ 1);
           ptx::mbar_expect_tx(&bars[FwdBars::k_full + st], (uint32_t)(bkv * 128));
           ptx::tma_load_2d(&tmap_kv, &bars[FwdBars::k_full + st], smem + L.off_k + st * kv_bytes, p.D + h * DH, row0 + j * bkv);
-          ptx::mbar_wait(&bars[FwdBars::v_empty + st], ph ^ 1);
+          ptx::mbar_wait_relaxed(&bars[FwdBars::v_empty + st], ph ^ 1);
           ptx::mbar_expect_tx(&bars[FwdBars::v_full + st], (uint32_t)(bkv * 128));
           ptx::tma_load_2d(&tmap_kv, &bars[FwdBars::v_full + st], smem + L.off_v + st * kv_bytes, 2 * p.D + h * DH, row0 + j * bkv);
         }
@@ -208,11 +309,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const int total = my_items * nkv;
       auto issue_s = [&](int w, int g) {
         const int j = g % nkv, ii = g / nkv, st = g % stages;
-        if (j == 0) ptx::mbar_wait(&bars[FwdBars::q_full + w], ii & 1);
-        ptx::mbar_wait(&bars[FwdBars::k_full + st], (g / stages) & 1);
+        if (j == 0) ptx::mbar_wait_relaxed(&bars[FwdBars::q_full + w], ii & 1);
+        ptx::mbar_wait_relaxed(&bars[FwdBars::k_full + st], (g / stages) & 1);
         // single pass: S overwrites the columns O(g-1) was read from. Multi-tile: S has its own columns, which are free
         // once P(g-1) is complete — issue_pv(w, g-1) waited for that just before this call.
-        if constexpr (kSingle) ptx::mbar_wait(&bars[FwdBars::o_empty + w], (g & 1) ^ 1);
+        if constexpr (kSingle) ptx::mbar_wait_relaxed(&bars[FwdBars::o_empty + w], (g & 1) ^ 1);
         ptx::tc_fence_after();
         const uint64_t dq = umma_smem_desc_sw128(ptx::smem_u32(smem + w * kTile), 0, 1024);
         const uint64_t dk = umma_smem_desc_sw128(ptx::smem_u32(smem + L.off_k + st * kv_bytes), 0, 1024);
@@ -226,10 +327,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       auto issue_pv = [&](int w, int g) {
         const int st = g % stages;
         const int j = g % nkv, ii = g / nkv;
-        if constexpr (kSingle) ptx::mbar_wait(&bars[FwdBars::p_full + w], g & 1);   // multi-tile: the caller waited (once)
-        ptx::mbar_wait(&bars[FwdBars::v_full + st], (g / stages) & 1);
+        if constexpr (kSingle) ptx::mbar_wait_relaxed(&bars[FwdBars::p_full + w], g & 1);   // multi-tile: the caller waited (once)
+        ptx::mbar_wait_relaxed(&bars[FwdBars::v_full + st], (g / stages) & 1);
         if constexpr (!kSingle) {
-          if (j == 0) ptx::mbar_wait(&bars[FwdBars::o_empty + w], (ii & 1) ^ 1);   // previous item's O has been read out
+          if (j == 0) ptx::mbar_wait_relaxed(&bars[FwdBars::o_empty + w], (ii & 1) ^ 1);   // previous item's O has been read out
         }
         ptx::tc_fence_after();
         const uint32_t acc0 = (!kSingle && j > 0) ? 1u : 0u;          // multi-tile: O accumulates in TMEM across key tiles
@@ -252,15 +353,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         issue_s(1, 0);
         for (int g = 0; g < total; ++g) {
           if constexpr (kSingle) {
+            SFC_TL(long long* dbg = (blockIdx.x == 0 && g < 32) ? p.dbg : nullptr;)
             issue_pv(0, g);
+            SFC_TL(if (dbg) dbg[g * 32 + 16] = clock64();)
             if (g + 1 < total) issue_s(0, g + 1);
+            SFC_TL(if (dbg) dbg[g * 32 + 17] = clock64();)
             issue_pv(1, g);
+            SFC_TL(if (dbg) dbg[g * 32 + 18] = clock64();)
             if (g + 1 < total) issue_s(1, g + 1);
+            SFC_TL(if (dbg) dbg[g * 32 + 19] = clock64();)
           } else {
             // P(g) complete = the S columns are free: the next S goes FIRST (the softmax warps wait for nothing else),
             // the PV product follows; O lives in its own columns
             for (int w = 0; w < 2; ++w) {
-              ptx::mbar_wait(&bars[FwdBars::p_full + w], g & 1);
+              ptx::mbar_wait_relaxed(&bars[FwdBars::p_full + w], g & 1);
               if (g + 1 < total) issue_s(w, g + 1);
               issue_pv(w, g);
             }
@@ -276,10 +382,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int lane = tid & 31;
     const int r = quarter * 32 + lane;             // row in tile == TMEM lane
     const uint32_t t_s = tmem_base + w * 256 + ((uint32_t)(quarter * 32) << 16);
-    uint8_t* p_smem = smem + L.off_p + w * L.p_atoms * kTile;
+    uint8_t* p_smem = smem + L.off_p + w * L.p_atoms * kTile;      // P operand; its first 16 KB double as the O staging tile
     const float sl2 = p.scale * kLog2e;
     const DropKey dkey = drop_key(p.drop_seed, p.drop_p, p.drop_epoch);
+    const uint32_t thr_hi = dkey.thr16 << 16;
     const uint32_t p_s32 = ptx::smem_u32(p_smem);                  // 32-bit shared address: st.shared, no 64-bit address math
+    const uint32_t p_row = p_s32 + (uint32_t)(r * 128);
+    const int rx = r & 7;
+    const bool store_owner = quarter == 0 && lane == 0;            // issues (and waits for) this tile's TMA stores
     int g = 0, ii = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ii) {
       const int qp = item % nqp, h = (item / nqp) % p.H, b = item / (nqp * p.H);
@@ -290,15 +400,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       // the true maximum exceeds it by more than 2^8 — P stays <= 256, the final O / l is unchanged.
       float m_run = -INFINITY, l_run = 0.f;
       for (int j = 0; j < nkv; ++j, ++g) {
-        ptx::mbar_wait(&bars[FwdBars::s_full + w], g & 1);
+        SFC_TL(long long* dbg = (blockIdx.x == 0 && g < 32 && (tid == 128 || tid == 256)) ? p.dbg + g * 32 + w * 8 : nullptr;)
+        SFC_TL(if (dbg) dbg[0] = clock64();)
+        ptx::mbar_wait_relaxed(&bars[FwdBars::s_full + w], g & 1);
         ptx::tc_fence_after();
+        SFC_TL(if (dbg) dbg[1] = clock64();)
+        uint32_t ra[32], rb[32];
         if (warp_active) {
           const int kv_valid = min(bkv, p.N - j * bkv);
           const int nch = (kv_valid + 31) / 32;
           // Both passes keep the TMEM load of the next 32-column chunk in flight while the current one is processed
           // (two register buffers, loop unrolled by two so that they stay in registers).
           float mx = -INFINITY, mx1 = -INFINITY;   // two chains of 3-input maxima: issue-bound, not latency-bound
-          uint32_t ra[32], rb[32];
           auto max_chunk = [&](const uint32_t (&rr)[32], int c) {
             if (c * 32 + 32 <= kv_valid) {
 #pragma unroll
@@ -334,7 +447,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               m_run = mx;
             } else {
               // PV(g-1) was issued right after S(g): every o_full phase is consumed exactly once, here or at the item's end
-              ptx::mbar_wait(&bars[FwdBars::o_full + w], (g - 1) & 1);
+              ptx::mbar_wait_relaxed(&bars[FwdBars::o_full + w], (g - 1) & 1);
               ptx::tc_fence_after();
               const bool need = (mx - m_run) * sl2 > 8.0f;
               if (__any_sync(0xffffffffu, need)) {
@@ -354,83 +467,110 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             }
           }
           ptx::tmem_ld_x32(t_s, ra);                    // first chunk of pass 2, in flight during the scalar work below
-          const float mb = m_run * sl2;
+        }
+        // The previous item's TMA store reads the staging tile that aliases this P operand: its owner waits for that read,
+        // the tile-wide barrier hands the news to the other 127 threads before anybody writes P again.
+        if (store_owner) ptx::tma_store_wait_read<0>();
+        ptx::named_bar_sync(1 + w, 128);
+        SFC_TL(if (dbg) dbg[2] = clock64();)
+        if (warp_active) {
+          const int kv_valid = min(bkv, p.N - j * bkv);
+          const int nch = (kv_valid + 31) / 32;
+          const float nmb = -m_run * sl2;
           float psum = 0.f;
           // dropout index space: (probability row) x (key index, row pitch padded to 16 so that 16-key groups are aligned)
-          unsigned long long drop_row = 0;
+          unsigned long long drop_grp = 0;
           if constexpr (kDrop)
-            drop_row = (((unsigned long long)(b * p.H + h) * p.N + (unsigned long long)qi) * (unsigned long long)((p.N + 15) & ~15)) + (unsigned long long)(j * bkv);
-          const int nch_all = (bkv + 31) / 32;         // P columns read by the PV MMA: [0, bkv)
-          auto exp_chunk = [&](const uint32_t (&rr)[32], int c) {
-            float pv[32];
-            if (c * 32 + 32 <= kv_valid) {
+            drop_grp = ((((unsigned long long)(b * p.H + h) * p.N + (unsigned long long)qi) * (unsigned long long)((p.N + 15) & ~15)) + (unsigned long long)(j * bkv)) >> 4;
+          // software pipeline over 16-column units (see exp_step): pp = probabilities of the previous unit, still to be
+          // summed / masked / packed / stored. It starts with an all-zero dummy unit aimed at unit 0's slots (which the
+          // real unit 0 rewrites afterwards, same thread, program order).
+          float pp[16], pq[16];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) { pv[i] = ex2_approx(fmaf(__uint_as_float(rr[i]), sl2, -mb)); psum += pv[i]; }
-            } else {
+          for (int i = 0; i < 16; ++i) pp[i] = 0.f;
+          uint32_t seed_prev = 0, st0 = p_slot_addr(p_row, rx, 0), st1 = p_slot_addr(p_row, rx, 1);
+          // one 32-column chunk = two units; the probability buffers swap roles (pp -> pq -> pp): no register copies
+          auto chunk = [&](uint32_t* s32, int c) {
+            const int nv = kv_valid - c * 32;
+            if (nv < 32) {                              // keys past the sequence end: exp2(-inf) = 0
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                pv[i] = (c * 32 + i < kv_valid) ? ex2_approx(fmaf(__uint_as_float(rr[i]), sl2, -mb)) : 0.f;
-                psum += pv[i];
-              }
+              for (int i = 0; i < 32; ++i)
+                if (i >= nv) s32[i] = 0xff800000u;
             }
-            if constexpr (kDrop) drop_zero<32, 16>(pv, dkey, drop_row + (unsigned long long)(c * 32));   // 1 / keep: in inv_l below
-            store_p_chunk_s32(p_s32, r, c, pv);
+            exp_step<kDrop>(s32, sl2, nmb, pq, pp, psum, seed_prev, thr_hi, st0, st1);
+            if constexpr (kDrop) seed_prev = drop_hash2(dkey, drop_grp + (unsigned long long)(2 * c));
+            st0 = p_slot_addr(p_row, rx, 4 * c);
+            st1 = p_slot_addr(p_row, rx, 4 * c + 1);
+            exp_step<kDrop>(s32 + 16, sl2, nmb, pp, pq, psum, seed_prev, thr_hi, st0, st1);
+            if constexpr (kDrop) seed_prev = drop_hash2(dkey, drop_grp + (unsigned long long)(2 * c + 1));
+            st0 = p_slot_addr(p_row, rx, 4 * c + 2);
+            st1 = p_slot_addr(p_row, rx, 4 * c + 3);
           };
 #pragma unroll 1
           for (int c = 0; c < nch; c += 2) {
             ptx::tmem_ld_wait();
             if (c + 1 < nch) ptx::tmem_ld_x32(t_s + (c + 1) * 32, rb);
-            exp_chunk(ra, c);
+            chunk(ra, c);
             if (c + 1 < nch) {
               ptx::tmem_ld_wait();
               if (c + 2 < nch) ptx::tmem_ld_x32(t_s + (c + 2) * 32, ra);
-              exp_chunk(rb, c + 1);
+              chunk(rb, c + 1);
             }
           }
-          for (int c = nch; c < nch_all; ++c) {        // key columns past the sequence end inside [0, bkv)
-            float pv[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) pv[i] = 0.f;
-            store_p_chunk_s32(p_s32, r, c, pv);
+          exp_flush<kDrop>(pp, psum, seed_prev, thr_hi, st0, st1);
+          for (int u = 2 * nch; u < (bkv >> 4); ++u) {  // whole chunks past the sequence end inside [0, bkv): P = 0
+            ptx::sts_zero16(p_slot_addr(p_row, rx, 2 * u));
+            ptx::sts_zero16(p_slot_addr(p_row, rx, 2 * u + 1));
           }
           l_run += psum;
         }
+        SFC_TL(if (dbg) dbg[3] = clock64();)
         ptx::tc_fence_before();
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&bars[FwdBars::p_full + w]);
+        SFC_TL(if (dbg) dbg[4] = clock64();)
         // The softmax warps do not stall on a PV product between key tiles: S(g+1) goes to its own columns and O stays in
         // TMEM; the finished O is normalised and stored from TMEM after the item's last PV.
         if constexpr (!kSingle) {
           if (j < nkv - 1) continue;
         }
-        ptx::mbar_wait(&bars[FwdBars::o_full + w], g & 1);
+        ptx::mbar_wait_relaxed(&bars[FwdBars::o_full + w], g & 1);
         ptx::tc_fence_after();
+        SFC_TL(if (dbg) dbg[5] = clock64();)
         if (warp_active) {
-          const float inv_l = (kDrop ? dkey.inv_keep : 1.0f) / l_run;   // O = (keep . P / keep_prob) V / l: the mask zeroes, this scales
-#pragma unroll
-          for (int c = 0; c < DH / 32; ++c) {
-            uint32_t rr[32];
-            ptx::tmem_ld_x32(t_s + kOCol + c * 32, rr);
-            ptx::tmem_ld_wait();
-            if (qi < p.N) {
-              __nv_bfloat16* op = p.out + (long long)(b * p.N + qi) * p.D + h * DH + c * 32;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint4 o;
-                o.x = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 0]) * inv_l, __uint_as_float(rr[q * 8 + 1]) * inv_l);
-                o.y = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 2]) * inv_l, __uint_as_float(rr[q * 8 + 3]) * inv_l);
-                o.z = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 4]) * inv_l, __uint_as_float(rr[q * 8 + 5]) * inv_l);
-                o.w = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 6]) * inv_l, __uint_as_float(rr[q * 8 + 7]) * inv_l);
-                reinterpret_cast<uint4*>(op)[q] = o;
-              }
-            }
-          }
+          ptx::tmem_ld_x32(t_s + kOCol, ra);
+          ptx::tmem_ld_x32(t_s + kOCol + 32, rb);
+          ptx::tmem_ld_wait();
         }
+        // O sits in registers: the accumulator columns are released BEFORE the rows are normalised and stored, so the next
+        // item's S product (single pass: it overwrites these columns) starts ~1.5 k cycles earlier
         ptx::tc_fence_before();
         ptx::mbar_arrive(&bars[FwdBars::o_empty + w]);
+        if (warp_active) {
+          const float inv_l = (kDrop ? dkey.inv_keep : 1.0f) / l_run;   // O = (keep . P / keep_prob) V / l: the mask zeroes, this scales
+          // one 128-byte row per thread into the SW128 staging tile (16-byte slot ^= row & 7: conflict-free), then ONE TMA
+          // store per tile — row-per-lane st.global touched 32 different lines per instruction (~1.7 k cycles per tile)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t* src = q < 4 ? ra + q * 8 : rb + (q - 4) * 8;
+            sts_v4(p_row + (uint32_t)((q ^ rx) << 4),
+                   ptx::pack_bf16(__uint_as_float(src[0]) * inv_l, __uint_as_float(src[1]) * inv_l),
+                   ptx::pack_bf16(__uint_as_float(src[2]) * inv_l, __uint_as_float(src[3]) * inv_l),
+                   ptx::pack_bf16(__uint_as_float(src[4]) * inv_l, __uint_as_float(src[5]) * inv_l),
+                   ptx::pack_bf16(__uint_as_float(src[6]) * inv_l, __uint_as_float(src[7]) * inv_l));
+          }
+          if (qi < p.N && p.lse) p.lse[((long long)b * p.H + h) * p.N + qi] = m_run * p.scale + logf(l_run);
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::named_bar_sync(3 + w, 128);                            // the staging tile is complete
+        if (store_owner && q_tile0 < p.N) {
+          ptx::tma_store_3d(&tmap_o, p_smem, h * DH, q_tile0, b);   // rows past the image end are clipped by the tensor map
+          ptx::tma_store_commit();
+        }
+        SFC_TL(if (dbg) dbg[6] = clock64();)
       }
-      if (qi < p.N && p.lse) p.lse[((long long)b * p.H + h) * p.N + qi] = m_run * p.scale + logf(l_run);
     }
+    if (store_owner) ptx::tma_store_wait_all<0>();
   }
 
   ptx::tc_fence_before();
@@ -456,11 +596,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 // and the warpgroups run  P = exp2(S - lse) (kept in registers)  ->  read dQ(s-1) out  ->  dS = P (dP - delta) scale.
 // Per-step clock64 stamps of CTA 0 (tools/attn_timeline.py): compiled in only with -DSFC_ATTN_TIMELINE, they cost
 // registers in a kernel that is 2 registers away from spilling.
-#ifdef SFC_ATTN_TIMELINE
-#define SFC_TL(...) __VA_ARGS__
-#else
-#define SFC_TL(...)
-#endif
 constexpr int kBwdEwWarps = 16;                 // element-wise warps: 4 per TMEM lane quarter, one 32-column chunk each
 constexpr int kBwdThreads = 64 + kBwdEwWarps * 32;   // warp 0: TMEM alloc + TMA, warp 1: MMA issuer; 18 warps leave 112 registers per thread
 constexpr int kQdoStages = 3;
@@ -615,13 +750,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int row0 = c.b * p.N;
         if (c.qt == 0) {
           const int kvst = c.ii & 1;
-          ptx::mbar_wait(&bars[BwdBars::kv_empty + kvst], ((c.ii >> 1) & 1) ^ 1);
+          ptx::mbar_wait_relaxed(&bars[BwdBars::kv_empty + kvst], ((c.ii >> 1) & 1) ^ 1);
           ptx::mbar_expect_tx(&bars[BwdBars::kv_full + kvst], (uint32_t)(2 * bkv * 128));
           ptx::tma_load_2d(&tmap_kv, &bars[BwdBars::kv_full + kvst], smem + BwdSmem::kK + kvst * kTile, p.D + c.h * DH, row0 + c.jt * bkv);
           ptx::tma_load_2d(&tmap_kv, &bars[BwdBars::kv_full + kvst], smem + BwdSmem::kV + kvst * kTile, 2 * p.D + c.h * DH, row0 + c.jt * bkv);
         }
         const int st = c.st3;
-        ptx::mbar_wait(&bars[BwdBars::qdo_empty + st], (uint32_t)(c.ph3 ^ 1));
+        ptx::mbar_wait_relaxed(&bars[BwdBars::qdo_empty + st], (uint32_t)(c.ph3 ^ 1));
         ptx::mbar_expect_tx(&bars[BwdBars::qdo_full + st], 2 * kTile);
         ptx::tma_load_2d(&tmap_q, &bars[BwdBars::qdo_full + st], smem + BwdSmem::kQ + st * kTile, c.h * DH, row0 + c.qt * BQ);
         ptx::tma_load_2d(&tmap_do, &bars[BwdBars::qdo_full + st], smem + BwdSmem::kDO + st * kTile, c.h * DH, row0 + c.qt * BQ);
@@ -636,9 +771,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const uint32_t idesc_q = umma_idesc_bf16(BQ, DH, false, true);       // dQ    : K-major A (dS), MN-major B (K)
       auto s_issue = [&](const BwdCursor& c) {
         const int s = c.s, st = c.st3, kvst = c.ii & 1;
-        ptx::mbar_wait(&bars[BwdBars::qdo_full + st], (uint32_t)c.ph3);
-        if (c.qt == 0) ptx::mbar_wait(&bars[BwdBars::kv_full + kvst], (c.ii >> 1) & 1);
-        if (s >= 2) ptx::mbar_wait(&bars[BwdBars::dq_empty], s & 1);       // dQ(s-2) read out of S[s&1]
+        ptx::mbar_wait_relaxed(&bars[BwdBars::qdo_full + st], (uint32_t)c.ph3);
+        if (c.qt == 0) ptx::mbar_wait_relaxed(&bars[BwdBars::kv_full + kvst], (c.ii >> 1) & 1);
+        if (s >= 2) ptx::mbar_wait_relaxed(&bars[BwdBars::dq_empty], s & 1);       // dQ(s-2) read out of S[s&1]
         ptx::tc_fence_after();
         const uint64_t dq = umma_smem_desc_sw128(ptx::smem_u32(smem + BwdSmem::kQ + st * kTile), 0, 1024);
         const uint64_t dk = umma_smem_desc_sw128(ptx::smem_u32(smem + BwdSmem::kK + kvst * kTile), 0, 1024);
@@ -706,7 +841,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           SFC_TL(if (dbg && s < 64) dbg[s * 16 + 8] = clock64();)
           if (s + 1 < T) s_issue(c1);
           SFC_TL(if (dbg && s < 64) dbg[s * 16 + 9] = clock64();)
-          ptx::mbar_wait(&bars[BwdBars::pds_full], s & 1);       // P / dS of step s are in smem, dP(s) has been consumed
+          ptx::mbar_wait_relaxed(&bars[BwdBars::pds_full], s & 1);       // P / dS of step s are in smem, dP(s) has been consumed
           SFC_TL(if (dbg && s < 64) dbg[s * 16 + 12] = clock64();)
           ptx::tc_fence_after();
           if (s + 1 < T) dp_issue(c1);                           // first: it is the input the warpgroups wait for next
@@ -736,7 +871,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     auto readout = [&](const EwPos& cp) {
       const int sp = cp.s, qt = cp.qt, jt = cp.jt, h = cp.h;
       const int row0 = cp.b * p.N;
-      ptx::mbar_wait(&bars[BwdBars::dq_full], sp & 1);
+      ptx::mbar_wait_relaxed(&bars[BwdBars::dq_full], sp & 1);
       ptx::tc_fence_after();
       {
         uint32_t rr[16];
@@ -843,7 +978,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         float pr[32];
         SFC_TL(long long* dbg = (blockIdx.x == 0 && tid == 64 && s < 64) ? p.dbg : nullptr;)
         SFC_TL(if (dbg) dbg[s * 16 + 0] = clock64();)
-        ptx::mbar_wait(&bars[BwdBars::s_full + (s & 1)], (s >> 1) & 1);
+        ptx::mbar_wait_relaxed(&bars[BwdBars::s_full + (s & 1)], (s >> 1) & 1);
         SFC_TL(if (dbg) dbg[s * 16 + 1] = clock64();)
         ptx::tc_fence_after();
         const int c = ch;
@@ -888,7 +1023,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
         SFC_TL(if (dbg) dbg[s * 16 + 3] = clock64();)
         // ---- phase B: dS = P * (dP - delta) * scale; P (dropped) and dS -> shared memory
-        ptx::mbar_wait(&bars[BwdBars::dp_full], s & 1);
+        ptx::mbar_wait_relaxed(&bars[BwdBars::dp_full], s & 1);
         SFC_TL(if (dbg) dbg[s * 16 + 4] = clock64();)
         ptx::tc_fence_after();
         if (chunk_active) {
@@ -986,9 +1121,11 @@ extern "C" int sfc_attn_fwd(const void* qkv, void* out, float* lse, int B, int H
   CUtensorMap tq, tkv;
   if (int e = sfc_make_tmap_2d(&tq, qkv, 2, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D * 2, DH, BQ, true)) return e;
   if (int e = sfc_make_tmap_2d(&tkv, qkv, 2, (uint64_t)3 * D, (uint64_t)B * N, (uint64_t)3 * D * 2, DH, (uint32_t)L.bkv, true)) return e;
+  CUtensorMap to;      // O [B][N][D]: a 128-row x 64-column box of one image; rows past N are clipped by the TMA unit
+  if (int e = sfc_make_tmap_3d(&to, out, (uint64_t)D, (uint64_t)N, (uint64_t)B, (uint64_t)D * 2, (uint64_t)N * D * 2, DH, BQ)) return e;
   AttnParams p{};
   p.B = B; p.H = H; p.N = N; p.D = D; p.scale = scale; p.drop_p = drop_p; p.drop_seed = drop_seed; p.drop_epoch = sfc_dropout_epoch_ptr();
-  p.out = (__nv_bfloat16*)out; p.lse = lse;
+  p.out = (__nv_bfloat16*)out; p.lse = lse; p.dbg = g_attn_dbg;
   static bool configured = false;
   if (!configured) {
     SFC_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -1000,10 +1137,10 @@ extern "C" int sfc_attn_fwd(const void* qkv, void* out, float* lse, int B, int H
   const long long items = (long long)B * H * ((N + 2 * BQ - 1) / (2 * BQ));
   const int grid = (int)(items < sfc_num_sms() ? items : sfc_num_sms());
   const bool drop = drop_p > 0.f;
-  if (L.nkv == 1 && drop) attn_fwd_kernel<true, true><<<grid, kFwdThreads, L.total, stream>>>(tq, tkv, p, L);
-  else if (L.nkv == 1) attn_fwd_kernel<true, false><<<grid, kFwdThreads, L.total, stream>>>(tq, tkv, p, L);
-  else if (drop) attn_fwd_kernel<false, true><<<grid, kFwdThreads, L.total, stream>>>(tq, tkv, p, L);
-  else attn_fwd_kernel<false, false><<<grid, kFwdThreads, L.total, stream>>>(tq, tkv, p, L);
+  if (L.nkv == 1 && drop) attn_fwd_kernel<true, true><<<grid, kFwdThreads, L.total, stream>>>(tq, tkv, to, p, L);
+  else if (L.nkv == 1) attn_fwd_kernel<true, false><<<grid, kFwdThreads, L.total, stream>>>(tq, tkv, to, p, L);
+  else if (drop) attn_fwd_kernel<false, true><<<grid, kFwdThreads, L.total, stream>>>(tq, tkv, to, p, L);
+  else attn_fwd_kernel<false, false><<<grid, kFwdThreads, L.total, stream>>>(tq, tkv, to, p, L);
   SFC_LAUNCH_OK();
   return 0;
 }

@@ -49,6 +49,9 @@ int sfc_make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_
 int sfc_make_tmap_2d_sw(CUtensorMap* out, const void* base, int elem_bytes, uint64_t cols, uint64_t rows,
                         uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows, int swizzle_bytes);
 
+int sfc_make_tmap_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t slabs, uint64_t row_stride_bytes,
+                     uint64_t slab_stride_bytes, uint32_t box_cols, uint32_t box_rows);
+
 int sfc_num_sms();
 const unsigned long long* sfc_dropout_epoch_ptr();   // device pointer or null (sfc_set_dropout_epoch_ptr)
 
@@ -234,6 +237,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// 3-D tiled store shared -> global: coordinates {col, row, slab}; rows / columns outside the tensor are not written
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
@@ -394,6 +403,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+__device__ __forceinline__ void sts_zero16(uint32_t addr) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

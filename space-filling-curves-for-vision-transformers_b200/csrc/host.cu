@@ -66,6 +66,27 @@ int sfc_make_tmap_2d_sw(CUtensorMap* out, const void* base, int elem_bytes, uint
   return 0;
 }
 
+// 3-D bf16 tensor map {cols, rows, slabs} with a {box_cols, box_rows, 1} box, 128-byte swizzle: rows past `rows` of a slab are
+// clipped by the TMA unit (stores) / zero-filled (loads), so a tile never spills into the next image.
+int sfc_make_tmap_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t slabs, uint64_t row_stride_bytes,
+                     uint64_t slab_stride_bytes, uint32_t box_cols, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  SFC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+  SFC_REQUIRE(((uintptr_t)base & 15) == 0 && (row_stride_bytes & 15) == 0 && (slab_stride_bytes & 15) == 0,
+              "TMA base / strides must be 16-byte aligned");
+  SFC_REQUIRE(box_cols * 2 == 128 && box_rows >= 1 && box_rows <= 256, "3-D TMA box: 64 bf16 columns, <= 256 rows");
+  cuuint64_t gdim[3] = {cols, rows, slabs};
+  cuuint64_t gstride[2] = {row_stride_bytes, slab_stride_bytes};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SFC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed (%d) cols=%llu rows=%llu slabs=%llu", (int)r,
+              (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)slabs);
+  return 0;
+}
+
 int sfc_num_sms() {
   static int n = 0;
   if (!n) {

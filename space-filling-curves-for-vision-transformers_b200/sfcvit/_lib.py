@@ -5,7 +5,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PK = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_PK, "lib", "libsfcvit.so")
+LIB_PATH = os.path.join(_PK, "lib", "libsfcvit_tl.so" if os.environ.get("SFC_ATTN_TIMELINE") else "libsfcvit.so")
 
 _lock = threading.Lock()
 _lib = None
