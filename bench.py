@@ -672,6 +672,7 @@ def main():
     # ---------------- N > 1: how much of the gradient all-reduce is NOT hidden behind backward: the same graph captured
     # again with the collectives left out (timing only; replicas diverge afterwards, so this is the last thing measured)
     allreduce_exposed_ms = None
+    nocomm = None
     if world > 1 and graphed is not None and not args.no_exposed:
         from src.training.graphs import GraphedStep
         opt.skip_comm = True
@@ -713,8 +714,16 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # captured graphs hold NCCL kernels: release them before the communicator goes away (destroying the process
+        # group underneath live graphs hangs), then leave without the collective teardown
+        graphed = nocomm = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -197,7 +197,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int kb1 = min(kb0 + p.kblocks_per_split, p.num_k_blocks);
         const int acc = iter % kAccBufs;
         const uint32_t acc_phase = (iter / kAccBufs) & 1;
-        const bool cs_unit = CS && ((t / p.splits) % p.num_n_tiles) == 0;
+        const int cs_tile = CS ? (t / p.splits) % p.num_n_tiles : 0;   // CS: this unit takes the k-blocks kb % num_n_tiles == its n-tile
+        bool cs_started = false;
         if constexpr (CL == 2) ptx::mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
         else ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
@@ -217,13 +218,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             else ptx::umma_f16(tmem_d, da + (uint64_t)(k * kAdvA), db + (uint64_t)(k * kAdvB), idesc, accf);
           }
           if constexpr (CS) {
-            if (cs_unit) {
+            // the extra MMAs re-read the A tile from shared memory (+50 % operand traffic for the k-block), so the n-tiles
+            // of an m-tile share them round-robin: every unit pays a third, none of them becomes the kernel's critical path
+            if (kb % p.num_n_tiles == cs_tile) {
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
-                const uint32_t accf = (kb > kb0 || k > 0) ? 1u : 0u;
+                const uint32_t accf = (cs_started || k > 0) ? 1u : 0u;
                 if constexpr (CL == 2) ptx::umma_f16_2cta(tmem_base + kCsCol, da + (uint64_t)(k * kAdvA), d_ones, idesc_cs, accf);
                 else ptx::umma_f16(tmem_base + kCsCol, da + (uint64_t)(k * kAdvA), d_ones, idesc_cs, accf);
               }
+              cs_started = true;
             }
           }
           // frees the smem slot (in both CTAs of a pair) when these MMAs retire
@@ -265,12 +269,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       else if constexpr (EPI == 1) epi_tile_fast(p.epi, taddr, n0, BN / 2, m0, (long long)p.M, EpiRowIdentity{}, split, stage);
       else epi_tile(p.epi, taddr, n0, BN / 2, m0, (long long)p.M, EpiRowIdentity{}, split, stage);
       if constexpr (CS) {
-        if (n_tile == 0 && half == 0) {              // the row sums of this unit's A rows over its k range (lane = row)
+        if (half == 0) {                             // the row sums of this unit's A rows over ITS k-blocks (lane = row)
           uint32_t r16[16];
           ptx::tmem_ld_x16(tmem_base + kCsCol + ((uint32_t)(quarter * 32) << 16), r16);
           ptx::tmem_ld_wait();
+          const int kb0 = split * p.kblocks_per_split, kb1 = min(kb0 + p.kblocks_per_split, p.num_k_blocks);
+          const int first = kb0 + ((n_tile - kb0 % p.num_n_tiles) + p.num_n_tiles) % p.num_n_tiles;   // first k-block it owns
           const long long m = m0 + (threadIdx.x & 31);
-          if (m < p.M) p.cs_ws[(long long)split * p.M + m] = __uint_as_float(r16[0]);
+          if (m < p.M) p.cs_ws[((long long)split * p.num_n_tiles + n_tile) * p.M + m] = first < kb1 ? __uint_as_float(r16[0]) : 0.f;
         }
       }
       ptx::tc_fence_before();
@@ -296,10 +302,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // out[m,n] (bf16 or fp32) = (accumulate ? out : 0) + act(alpha * sum_s ws[s,m,n] + bias[n])
 // column-sum partials of the CS variant: cs_out[m] = sum_s cs_ws[s, m] (threads past the main range)
 __device__ __forceinline__ void reduce_colsum(long long i, const float* __restrict__ cs_ws, int splits, int M, void* __restrict__ cs_out,
-                                              int cs_fp32) {
+                                              int cs_fp32) {   // splits = number of partial rows (split count x n-tiles)
   if (cs_ws == nullptr || i >= M) return;
   float s = 0.f;
-  for (int k = 0; k < splits; ++k) s += cs_ws[(long long)k * M + i];
+  for (int k = 0; k < splits; ++k) s += cs_ws[(long long)k * M + i];            // `splits` here = split count x n-tiles
   if (cs_fp32) reinterpret_cast<float*>(cs_out)[i] = s;
   else reinterpret_cast<__nv_bfloat16*>(cs_out)[i] = __float2bfloat16(s);
 }
@@ -307,10 +313,10 @@ __device__ __forceinline__ void reduce_colsum(long long i, const float* __restri
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, long long split_stride, int splits, void* __restrict__ out,
                                      long long ld_out, int M, int N, int out_fp32, int accumulate, float alpha,
                                      const __nv_bfloat16* __restrict__ bias, int act, const float* __restrict__ cs_ws,
-                                     void* __restrict__ cs_out, int cs_fp32) {
+                                     void* __restrict__ cs_out, int cs_fp32, int cs_parts) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)M * N;
-  if (idx >= total) { reduce_colsum(idx - total, cs_ws, splits, M, cs_out, cs_fp32); return; }
+  if (idx >= total) { reduce_colsum(idx - total, cs_ws, cs_parts, M, cs_out, cs_fp32); return; }
   const long long m = idx / N, n = idx % N;
   float s = 0.f;
   for (int k = 0; k < splits; ++k) s += ws[k * split_stride + idx];
@@ -332,9 +338,9 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, long long spl
 __global__ void __launch_bounds__(256) splitk_reduce_vec4_kernel(const float4* __restrict__ ws, long long split_stride4, int splits,
                                                                  void* __restrict__ out, long long ld_out, int M, int N4, int out_fp32,
                                                                  int accumulate, const float* __restrict__ cs_ws,
-                                                                 void* __restrict__ cs_out, int cs_fp32) {
+                                                                 void* __restrict__ cs_out, int cs_fp32, int cs_parts) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)M * N4) { reduce_colsum(idx - (long long)M * N4, cs_ws, splits, M, cs_out, cs_fp32); return; }
+  if (idx >= (long long)M * N4) { reduce_colsum(idx - (long long)M * N4, cs_ws, cs_parts, M, cs_out, cs_fp32); return; }
   const long long m = idx / N4, n = (idx % N4) * 4;
   float4 a[4];
 #pragma unroll
@@ -409,7 +415,7 @@ extern "C" int sfc_gemm_suggest_splits(int M, int N, int K);
 
 extern "C" size_t sfc_gemm_workspace_bytes(int M, int N, int K, int splits) {
   if (splits <= 1) return 0;
-  return (size_t)splits * (size_t)M * ((size_t)N + 1) * sizeof(float);      // partial tiles + partial column sums
+  return (size_t)splits * (size_t)M * ((size_t)N + (size_t)sfc_ceil_div(N, 128)) * sizeof(float);   // partial tiles + partial column sums per n-tile
 }
 
 // Split-K factor for reductions over the token dimension (wgrad): the output has few tiles, so K is cut into `s`
@@ -506,7 +512,7 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
     SFC_REQUIRE(workspace && workspace_bytes >= need, "sfc_gemm_bf16: split-K workspace too small (%zu < %zu)", workspace_bytes, need);
     pk.epi.out = workspace; pk.epi.out_fp32 = 1; pk.epi.ld_out = N; pk.epi.split_stride = (long long)M * N;
     if (want_cs) {
-      SFC_REQUIRE(workspace_bytes >= need + (size_t)splits * (size_t)M * sizeof(float), "sfc_gemm_bf16: workspace too small for the column sums");
+      SFC_REQUIRE(workspace_bytes >= need + (size_t)splits * (size_t)p.num_n_tiles * (size_t)M * sizeof(float), "sfc_gemm_bf16: workspace too small for the column sums");
       pk.cs_ws = reinterpret_cast<float*>(workspace) + (size_t)splits * (size_t)M * (size_t)N;
     }
   } else {
@@ -577,11 +583,11 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
     if (vec4)
       splitk_reduce_vec4_kernel<<<(unsigned)((total / 4 + extra + threads - 1) / threads), threads, 0, stream>>>(
           (const float4*)workspace, (long long)M * N / 4, splits, ep->out, ep->ld_out, M, N / 4, ep->out_fp32, ep->accumulate,
-          pk.cs_ws, ep->colsum_out, ep->colsum_fp32);
+          pk.cs_ws, ep->colsum_out, ep->colsum_fp32, splits * p.num_n_tiles);
     else
       splitk_reduce_kernel<<<(unsigned)((total + extra + threads - 1) / threads), threads, 0, stream>>>(
         (const float*)workspace, (long long)M * N, splits, ep->out, ep->ld_out, M, N, ep->out_fp32, ep->accumulate, ep->alpha,
-        (const __nv_bfloat16*)ep->bias, ep->act, pk.cs_ws, ep->colsum_out, ep->colsum_fp32);
+        (const __nv_bfloat16*)ep->bias, ep->act, pk.cs_ws, ep->colsum_out, ep->colsum_fp32, splits * p.num_n_tiles);
     SFC_LAUNCH_OK();
   }
   return 0;

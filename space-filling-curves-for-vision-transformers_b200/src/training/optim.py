@@ -150,6 +150,8 @@ class FusedAdamW(torch.optim.Optimizer):
     def _begin_backward(self):
         self._pending = dict(self._expected_counts)
         self._launched = set()
+        self.last_num_buckets = 0                 # counters describe the step that is starting
+        self.last_overlapped_buckets = 0
 
     def _launch_range(self, fi, ri, overlapped):
         fb = self._flat[fi]
@@ -275,8 +277,9 @@ class FusedAdamW(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        self.last_num_buckets = 0
-        self.last_overlapped_buckets = 0
+        if self._pending is None:                 # no hook ran during this backward: nothing was reduced yet
+            self.last_num_buckets = 0
+            self.last_overlapped_buckets = 0
         self.advance()
         self.launch()
         return loss

@@ -87,6 +87,8 @@ def bench_gemm(M, D=768, F=3072):
         for sp in (0, 1):
             report(f"wgrad_{name}_splits{sp}", timeit(lambda i: ops.gemm(dys[i], xs[i], a_mn=True, b_mn=True, splits=sp), nrot), fl,
                    splits=ops._lib.load().sfc_gemm_suggest_splits(N, K, M) if sp == 0 else 1)
+        report(f"wgrad_{name}_with_db_fused", timeit(lambda i: ops.wgrad(dys[i], xs[i], torch.bfloat16, want_db=True), nrot), fl)
+        report(f"colsum_{name}_separate", timeit(lambda i: ops.colsum(dys[i]), nrot), None, M * N * 2)
         del xs, dys, res
 
 
