@@ -151,6 +151,19 @@ int sfc_attn_bwd(const void* qkv, const void* out, const void* dout, const float
                  size_t scratch_bytes, int B, int H, int N, int D, float scale, float drop_p,
                  unsigned long long drop_seed, sfc_stream_t stream);
 
+/* ---- soft-target cross entropy (SoftTargetCrossEntropy: main.py:45-51,
+ *      loss = -(targets * log_softmax(inputs.float(), -1)).sum(-1).mean(), called from src/training/train.py:158-160) ----
+ * logits: bf16 or fp32 [B, ld_logits]; targets: fp32 [B, ld_targets] (soft labels, rows need not sum to 1);
+ * loss: fp32 [1] = batch mean, reduced in a fixed order; row_lse / row_tsum: fp32 [B], saved for backward.
+ * scratch: sfc_softce_scratch_bytes() bytes, zeroed once by the caller, private to the stream.
+ * backward: dlogits[b, c] = dloss[0] / B * (softmax(logits)[b, c] * row_tsum[b] - targets[b, c]), in the logits' dtype. */
+size_t sfc_softce_scratch_bytes(void);
+int sfc_softce_fwd(const void* logits, int logits_fp32, long long ld_logits, const float* targets, long long ld_targets, int B,
+                   int C, float* loss, float* row_lse, float* row_tsum, void* scratch, size_t scratch_bytes, sfc_stream_t stream);
+int sfc_softce_bwd(const void* logits, int logits_fp32, long long ld_logits, const float* targets, long long ld_targets,
+                   const float* row_lse, const float* row_tsum, const float* dloss, int B, int C, void* dlogits,
+                   long long ld_dlogits, sfc_stream_t stream);
+
 /* ---- K6: fused grad-norm / clip / AdamW over flat buckets
  *      (torch.nn.utils.clip_grad_norm_ + optim.AdamW.step: src/training/train.py:165-166, main.py:288-289) ----
  * sfc_grad_sumsq: accum[0] += sum(g^2) (caller zeroes accum), reduced in a fixed order (bit-identical on every rank of

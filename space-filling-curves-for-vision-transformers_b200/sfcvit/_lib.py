@@ -53,6 +53,9 @@ SIGNATURES = {
     "sfc_grad_sumsq": (_i, [_vp, _i, _ll, _vp, _vp, _sz, _vp]),
     "sfc_adamw_step": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _f, _f, _f, _f, _f, _i, _f, _f, _vp, _vp, _vp]),
     "sfc_store_f32x4": (_i, [_vp, _f, _f, _f, _f, _vp]),
+    "sfc_softce_scratch_bytes": (_sz, []),
+    "sfc_softce_fwd": (_i, [_vp, _i, _ll, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "sfc_softce_bwd": (_i, [_vp, _i, _ll, _vp, _ll, _vp, _vp, _vp, _i, _i, _vp, _ll, _vp]),
     "sfc_gemm_bf16": (_i, [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _i, ctypes.POINTER(SfcGemmEpilogue), _vp, _sz, _i, _vp]),
 }
 

@@ -532,3 +532,33 @@ class PatchRowsFn(Function):
 
 def patch_rows(img, perm32, p, g=1):
     return PatchRowsFn.apply(img, perm32, int(p), int(g))
+
+
+class SoftTargetCEFn(Function):
+    """-(targets * log_softmax(logits.float(), -1)).sum(-1).mean() (reference main.py:45-51) as one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, logits, targets):
+        if not logits.is_cuda:
+            raise RuntimeError("sfcvit: CUDA tensors only (the B200 path has no CPU fallback)")
+        x = logits if logits.dtype in (torch.bfloat16, torch.float32) else logits.float()
+        x = x.reshape(-1, x.shape[-1])
+        if x.stride(-1) != 1:
+            x = x.contiguous()
+        t = targets.reshape(-1, targets.shape[-1]).to(torch.float32)
+        if t.stride(-1) != 1:
+            t = t.contiguous()
+        loss, lse, tsum = ops.softce_fwd(x, t)
+        ctx.save_for_backward(x, t, lse, tsum)
+        ctx.shape, ctx.dtype = logits.shape, logits.dtype
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        x, t, lse, tsum = ctx.saved_tensors
+        dx = ops.softce_bwd(x, t, lse, tsum, dloss.reshape(1).to(torch.float32).contiguous())
+        return dx.reshape(ctx.shape).to(ctx.dtype), None
+
+
+def soft_target_cross_entropy(logits, targets):
+    return SoftTargetCEFn.apply(logits, targets)

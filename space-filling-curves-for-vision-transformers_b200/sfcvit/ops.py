@@ -450,3 +450,44 @@ def act_bwd(dy, aux, mode, alpha=1.0, drop_p=0.0, drop_seed=0):
                                    int(drop_seed) & 0xFFFFFFFFFFFFFFFF, _stream()), "sfc_act_bwd")
     _count(1)
     return out
+
+
+# ------------------------------------------------------------------ soft-target cross entropy (main.py:45-51)
+_softce_scratch = {}
+
+
+def softce_fwd(logits, targets):
+    """logits bf16 / fp32 [B, C], targets fp32 [B, C] -> (loss fp32 [1] = batch mean, row_lse [B], row_tsum [B])."""
+    lib = _lib.load()
+    _require_cuda(logits, targets)
+    assert logits.dim() == 2 and targets.shape == logits.shape and logits.stride(1) == 1 and targets.stride(1) == 1
+    assert logits.dtype in (torch.bfloat16, torch.float32) and targets.dtype == torch.float32
+    B, C = logits.shape
+    key = (logits.device.index, torch.cuda.current_stream().cuda_stream)
+    scratch = _softce_scratch.get(key)
+    if scratch is None:
+        scratch = torch.zeros(lib.sfc_softce_scratch_bytes(), dtype=torch.uint8, device=logits.device)   # zeroed ONCE
+        _softce_scratch[key] = scratch
+    loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+    lse = torch.empty(B, dtype=torch.float32, device=logits.device)
+    tsum = torch.empty(B, dtype=torch.float32, device=logits.device)
+    with torch.cuda.device(logits.device):
+        _lib.check(lib.sfc_softce_fwd(_ptr(logits), 1 if logits.dtype == torch.float32 else 0, logits.stride(0), _ptr(targets),
+                                      targets.stride(0), B, C, _ptr(loss), _ptr(lse), _ptr(tsum), _ptr(scratch), scratch.numel(),
+                                      _stream()), "sfc_softce_fwd")
+    _count(1)
+    return loss, lse, tsum
+
+
+def softce_bwd(logits, targets, lse, tsum, dloss):
+    lib = _lib.load()
+    _require_cuda(logits, targets, lse, tsum, dloss)
+    assert dloss.dtype == torch.float32 and dloss.numel() == 1
+    B, C = logits.shape
+    dx = torch.empty_like(logits)
+    with torch.cuda.device(logits.device):
+        _lib.check(lib.sfc_softce_bwd(_ptr(logits), 1 if logits.dtype == torch.float32 else 0, logits.stride(0), _ptr(targets),
+                                      targets.stride(0), _ptr(lse), _ptr(tsum), _ptr(dloss), B, C, _ptr(dx), dx.stride(0), _stream()),
+                   "sfc_softce_bwd")
+    _count(1)
+    return dx

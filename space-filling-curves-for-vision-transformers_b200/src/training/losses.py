@@ -1,10 +1,12 @@
 """SoftTargetCrossEntropy — the criterion the reference defines in main.py:45-51 (not importable from there without
 running the script), provided for callers of train_with_mixup_or_cutmix: -(targets * log_softmax(logits)).sum(-1).mean().
-Logits are [B, num_classes] (tiny): plain torch ops on the kernel path's output tensor."""
+One libsfcvit kernel forward (row log-sum-exp, target-weighted sum and a fixed-order batch mean) and one backward
+(csrc/softce.cu) instead of six ATen launches each way; CUDA tensors only."""
 import torch.nn as nn
-import torch.nn.functional as F
+
+from sfcvit import functional as SF
 
 
 class SoftTargetCrossEntropy(nn.Module):
     def forward(self, inputs, targets):
-        return -(targets * F.log_softmax(inputs.float(), dim=-1)).sum(dim=-1).mean()
+        return SF.soft_target_cross_entropy(inputs, targets)

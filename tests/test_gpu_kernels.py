@@ -148,3 +148,31 @@ def test_interp_concat_rejects_bad_layout(cuda_device):
     with pytest.raises(RuntimeError):
         ops.interp_concat_fwd(torch.zeros(1, 4, 12, dtype=torch.bfloat16, device="cuda"),
                               torch.zeros(1, 8, 12, dtype=torch.bfloat16, device="cuda"), 0)
+
+
+@pytest.mark.parametrize("B,C,dt", [(512, 10, "bf16"), (256, 1000, "bf16"), (37, 1000, "fp32"), (1, 3, "fp32"), (4096, 100, "bf16")])
+def test_soft_target_cross_entropy_matches_reference_formula(cuda_device, B, C, dt):
+    """csrc/softce.cu vs the reference criterion (/root/reference/main.py:45-51) evaluated by torch on the same inputs:
+    loss (fp32), gradient w.r.t. the logits (in the logits' dtype), deterministic from run to run; mixup-style targets
+    (two-hot rows) and rows that do not sum to one."""
+    import torch
+    import torch.nn.functional as F
+    from src.training.losses import SoftTargetCrossEntropy
+    g = torch.Generator(device="cuda").manual_seed(B * 31 + C)
+    dtype = torch.bfloat16 if dt == "bf16" else torch.float32
+    x = (torch.randn(B, C, generator=g, device="cuda") * 3).to(dtype).requires_grad_(True)
+    ya, yb = torch.randint(0, C, (B,), generator=g, device="cuda"), torch.randint(0, C, (B,), generator=g, device="cuda")
+    t = 0.3 * F.one_hot(ya, C).float() + 0.7 * F.one_hot(yb, C).float()
+    t[0] *= 0.5                                                     # a row that does not sum to one
+    loss = SoftTargetCrossEntropy()(x, t)
+    (loss * 2.0).backward()
+    xr = x.detach().clone().requires_grad_(True)
+    ref = -(t * F.log_softmax(xr.float(), dim=-1)).sum(dim=-1).mean()
+    (ref * 2.0).backward()
+    assert loss.dtype == torch.float32 and loss.dim() == 0
+    assert abs(float(loss) - float(ref)) < 2e-5 * max(1.0, abs(float(ref)))
+    assert x.grad.dtype == dtype
+    tol = 1e-5 if dt == "fp32" else 4e-3
+    assert float((x.grad.float() - xr.grad.float()).norm() / xr.grad.float().norm()) < tol
+    again = SoftTargetCrossEntropy()(x.detach(), t)
+    assert float(again) == float(loss.detach())
