@@ -170,6 +170,72 @@ def cpu_reference_throughput(c, steps, warmup, batch):
     return batch / sec, sec, torch.get_num_threads()
 
 
+def torch_gpu_throughput(c, device, batch, steps, warmup, compiled=False, infer=False):
+    """INFORMATIONAL comparator: the reference's own modules (oracle port = stock torch nn.TransformerEncoder,
+    SDPA, nn.Linear -> cuBLAS / cuDNN / flash kernels) on the SAME B200, bf16 autocast as the reference trains
+    (train.py:155), eager or torch.compile(mode="reduce-overhead") as main.py:284. Same step as the b200 arm:
+    forward + soft-target CE + backward + clip + AdamW. Library kernels: not the product, the kernel to beat."""
+    from oracle.model import soft_target_cross_entropy
+    model = build_oracle_model(c).to(device)
+    fwd = torch.compile(model, mode="reduce-overhead") if compiled else model
+    opt = torch.optim.AdamW(model.parameters(), lr=3e-4, weight_decay=5e-5, fused=True)
+    g = torch.Generator(device=device).manual_seed(0)
+    xs = [torch.randn(batch, 3, c["img"], c["img"], generator=g, device=device) for _ in range(4)]
+    la = torch.randint(0, c["classes"], (batch,), generator=g, device=device)
+    tgt = soft_targets(la, la.roll(1), 0.3, c["classes"])
+
+    def step(x):
+        if infer:
+            with torch.no_grad(), torch.amp.autocast(device_type="cuda", dtype=torch.bfloat16):
+                return fwd(x)
+        opt.zero_grad(set_to_none=True)
+        with torch.amp.autocast(device_type="cuda", dtype=torch.bfloat16):
+            loss = soft_target_cross_entropy(fwd(x), tgt)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        return loss
+    if infer:
+        model.eval()
+    for i in range(warmup):
+        step(xs[i % 4])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(xs[i % 4])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del model, opt, xs
+    torch.cuda.empty_cache()
+    return batch / (ms * 1e-3), ms
+
+
+def run_torch_gpu_arm(args, c):
+    """`--impl torch-gpu`: stock PyTorch on this GPU, eager and compiled, one JSON line (informational)."""
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl torch-gpu needs a CUDA device")
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(device)
+    B = args.batch or c["batch"]
+    infer = args.mode == "infer"
+    res = {}
+    for name, comp in (("eager", False), ("compiled_reduce_overhead", True)):
+        try:
+            ips, ms = torch_gpu_throughput(c, device, B, max(3, args.steps), max(3, args.warmup), compiled=comp, infer=infer)
+            res[name] = {"value": ips, "ms_per_step": ms}
+        except Exception as e:                                        # e.g. no host compiler for inductor on the box
+            res[name] = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+    best = max((v["value"] for v in res.values() if "value" in v), default=None)
+    print(json.dumps({"metric": metric_name(args.config, args.curve, infer), "impl": "torch-gpu", "value": best, "unit": "images/s",
+                      "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "dtype": "bf16 autocast (fp32 parameters)",
+                      "data": "synthetic", "config": {"workload": f"{args.config} stock torch modules (oracle port of the reference) on the GPU", "batch_per_gpu": B},
+                      "variants": res, "note": "library kernels (cuBLAS, flash SDPA, ATen); informational comparator, not the product"}), flush=True)
+
+
 def run_reference_arm(args, c):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -465,7 +531,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch-gpu"])
     ap.add_argument("--config", default="vit_b16_224", choices=sorted(CONFIGS))
     ap.add_argument("--mode", default="train", choices=["train", "infer"],
                     help="train = the headline metric (fwd+bwd+optimizer); infer = forward only (BASELINE.json configs[1], [4])")
@@ -479,6 +545,7 @@ def main():
     ap.add_argument("--check-dp", dest="check_dp", action="store_true", default=None,
                     help="N > 1: assert the sharded step equals the full-batch step before timing (default: on when N > 1)")
     ap.add_argument("--no-check-dp", dest="check_dp", action="store_false")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: one all-reduce after backward instead of bucket ranges on a side stream during backward")
     ap.add_argument("--no-exposed", action="store_true", help="N > 1: skip the second (collective-free) capture that measures allreduce_exposed_ms")
     args = ap.parse_args()
     c = dict(CONFIGS[args.config])
@@ -486,6 +553,8 @@ def main():
         args.mode = "infer"                                           # 4096-token config is an inference sweep
     if args.impl == "reference":
         return run_reference_arm(args, c)
+    if args.impl == "torch-gpu":
+        return run_torch_gpu_arm(args, c)
     if args.warmup < 3:
         args.warmup = 3
     if args.mode == "infer":
@@ -517,7 +586,8 @@ def main():
                 m.p = 0.0
             if isinstance(m, torch.nn.MultiheadAttention):
                 m.dropout = 0.0
-    opt = FusedAdamW(model.parameters(), lr=3e-4, weight_decay=5e-5, max_grad_norm=1.0)   # main.py:288-289 + train.py:165
+    opt = FusedAdamW(model.parameters(), lr=3e-4, weight_decay=5e-5, max_grad_norm=1.0,   # main.py:288-289 + train.py:165
+                     overlap=not args.no_overlap, comm_buckets=1 if args.no_overlap else 4)
     crit = SoftTargetCrossEntropy()
 
     g = torch.Generator(device=device).manual_seed(1234 + rank)
@@ -697,6 +767,20 @@ def main():
         cpu_baseline = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
                         "sample": f"2 timed steps (+1 warm-up) of batch {args.cpu_batch}, fp32, {threads} threads, same model/step as the GPU arm"}
 
+    final_loss = float(loss.item())
+    torch_gpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            graphed = None                                            # free the captured activations first
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            ips, ms = torch_gpu_throughput(c, device, B, 3, 3, compiled=False)
+            torch_gpu_baseline = {"value": ips, "unit": "images/s", "ms_per_step": ms, "variant": "eager, bf16 autocast, fused AdamW",
+                                  "note": "stock torch modules on the same GPU (library kernels); `bench.py --impl torch-gpu` adds torch.compile"}
+        except Exception as e:
+            torch_gpu_baseline = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+
     if rank == 0:
         line = {
             "metric": metric_name(args.config, args.curve), "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -708,9 +792,9 @@ def main():
                        "launch": "eager" if graphed is None else "forward+backward+allreduce+clip+AdamW replayed from one CUDA graph",
                        "l2_policy": f"{n_bufs} rotating input batches of {B * 3 * c['img'] ** 2 * 4 / 1e6:.0f} MB (> 126 MB L2); activations per step ~GBs"},
             "roofline": roofline, "patch_embed": patch_embed, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
-            "gpu_launches_per_step": launches / args.steps, "clocks": clocks, "loss": float(loss.item()),
+            "gpu_launches_per_step": launches / args.steps, "clocks": clocks, "loss": final_loss,
             "allreduce_buckets_per_step": opt.last_num_buckets, "allreduce_buckets_overlapped": opt.last_overlapped_buckets,
-            "allreduce_exposed_ms": allreduce_exposed_ms, "dp_check": dp_check,
+            "allreduce_exposed_ms": allreduce_exposed_ms, "dp_check": dp_check, "torch_gpu_baseline": torch_gpu_baseline,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -47,12 +47,13 @@ def dropout_epoch(device):
 
 
 class GraphedStep:
-    def __init__(self, model, criterion, example_images, example_targets, warmup=3, optimizer=None):
+    def __init__(self, model, criterion, example_images, example_targets, warmup=3, optimizer=None, autocast_dtype=None):
         if not example_images.is_cuda:
             raise RuntimeError("GraphedStep needs CUDA tensors (no CPU fallback)")
         if optimizer is not None and not (hasattr(optimizer, "advance") and hasattr(optimizer, "launch")):
             raise TypeError("GraphedStep(optimizer=...) needs a FusedAdamW (advance() / launch()); step other optimizers eagerly")
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
+        self.autocast_dtype = autocast_dtype      # run forward + loss under torch.amp.autocast (the reference loops do, train.py:155)
         self.images = example_images.clone()
         self.targets = example_targets.clone()
         self.epoch = dropout_epoch(example_images.device)
@@ -65,7 +66,7 @@ class GraphedStep:
                 for p in params:
                     p.grad = None
                 SF.release_grad_claims()
-                self.criterion(self.model(self.images), self.targets).backward()
+                self._forward_loss()[1].backward()
                 if optimizer is not None:
                     # a real step with zero learning rate would still decay; the warm-up only has to teach the optimizer
                     # which parameters receive gradients and grow every workspace, so it launches nothing that updates
@@ -84,8 +85,7 @@ class GraphedStep:
             optimizer.last_num_buckets = optimizer.last_overlapped_buckets = 0
         with torch.cuda.graph(self.graph):
             self.epoch.add_(1)
-            self.logits = self.model(self.images)
-            self.loss = self.criterion(self.logits, self.targets)
+            self.logits, self.loss = self._forward_loss()
             self.loss.backward()
             if optimizer is not None:
                 optimizer.launch()
@@ -93,6 +93,14 @@ class GraphedStep:
         SF.clear_weight_caches()                  # entries created during capture alias graph-private memory
         self._param_ptrs = [p.data_ptr() for p in params]
         self._params = params
+
+    def _forward_loss(self):
+        if self.autocast_dtype is None:
+            logits = self.model(self.images)
+            return logits, self.criterion(logits, self.targets)
+        with torch.amp.autocast(device_type="cuda", dtype=self.autocast_dtype):
+            logits = self.model(self.images)
+            return logits, self.criterion(logits, self.targets)
 
     def __call__(self, images, targets=None):
         if [p.data_ptr() for p in self._params] != self._param_ptrs:

@@ -43,6 +43,84 @@ def mixup_criterion(criterion, pred, y_a, y_b, lam):
     return lam * criterion(pred, y_a) + (1 - lam) * criterion(pred, y_b)
 
 
+# ---- lazily graphed steps ------------------------------------------------------------------------------------------
+# The reference wraps its model in torch.compile(mode="reduce-overhead") (main.py:284), i.e. CUDA-graphed code. The
+# libsfcvit kernels are launched through a C ABI that no tracing compiler sees, so the loops below get the same effect
+# themselves: the first full-size batch of an epoch function captures forward + loss + backward ONCE per (model,
+# criterion, batch shape) and every later step replays it (no Python / ctypes / tensor-map encoding per kernel). The
+# caller's optimizer, scheduler and gradient clipping stay what main.py passes in. SFC_TRAIN_GRAPH=0 turns it off; a
+# ragged last batch, CPU tensors or a failed capture fall back to launching the same kernels eagerly.
+_GRAPHS = {}
+
+
+def _graphed_step(model, criterion, images, targets, autocast_dtype):
+    import os
+    if os.environ.get("SFC_TRAIN_GRAPH", "1") == "0" or not images.is_cuda:
+        return None
+    key = (id(model), id(criterion), tuple(images.shape), images.dtype, tuple(targets.shape), targets.dtype, autocast_dtype)
+    ent = _GRAPHS.get(key)
+    if ent is None:
+        if sum(1 for k in _GRAPHS if k[0] == id(model)) >= 2:      # at most two captured shapes per model (activations are pinned)
+            return None
+        from .graphs import GraphedStep
+        try:
+            ent = GraphedStep(model, criterion, images, targets, autocast_dtype=autocast_dtype)
+        except Exception as e:                                     # e.g. a criterion with a host sync: stay eager, say so once
+            import warnings
+            warnings.warn(f"sfcvit: step not capturable in a CUDA graph ({type(e).__name__}: {e}); launching eagerly")
+            ent = False
+        _GRAPHS[key] = ent
+    return ent or None
+
+
+def _has_graphs(model):
+    return any(k[0] == id(model) and v for k, v in _GRAPHS.items())
+
+
+def _step(model, criterion, optimizer, images, targets, full_batch, autocast_dtype):
+    """forward + loss + backward of one batch: a replay of the captured step when the batch has the captured shape, the
+    same kernels launched eagerly otherwise. Returns (outputs, loss); gradients are in .grad either way."""
+    step = _graphed_step(model, criterion, images, targets, autocast_dtype) if images.size(0) == full_batch else None
+    if step is not None:
+        loss = step(images, targets)                               # gradients are (re)written into the static .grad tensors
+        return step.logits, loss
+    optimizer.zero_grad(set_to_none=not _has_graphs(model))       # keep captured .grad tensors alive: zero them in place
+    if autocast_dtype is None:
+        outputs = model(images)
+        loss = criterion(outputs, targets)
+    else:
+        with torch.amp.autocast(device_type="cuda", dtype=autocast_dtype):
+            outputs = model(images)
+            loss = criterion(outputs, targets)
+    loss.backward()
+    return outputs, loss
+
+
+_NUM_CLASSES = {}
+
+
+def _num_classes(model, images):
+    n = _NUM_CLASSES.get(id(model))
+    if n is None:
+        was = model.training
+        model.eval()
+        with torch.no_grad(), torch.amp.autocast(device_type="cuda", dtype=torch.bfloat16):
+            n = int(model(images[:1]).size(1))
+        model.train(was)
+        _NUM_CLASSES[id(model)] = n
+    return n
+
+
+def _clip_grad_norm(params, max_norm):
+    """torch.nn.utils.clip_grad_norm_ (reference :165). The reference asks for foreach=False (one norm kernel per
+    parameter, ~3 launches x 150 tensors); the multi-tensor form computes the same norm in a handful of launches."""
+    params = [p for p in params if p.grad is not None]
+    try:
+        return torch.nn.utils.clip_grad_norm_(params, max_norm, foreach=True)
+    except RuntimeError:
+        return torch.nn.utils.clip_grad_norm_(params, max_norm, foreach=False)
+
+
 def _bar(loader, desc):
     rank, _ = D.world()
     return tqdm(loader, desc=desc, leave=False, disable=rank != 0)
@@ -58,12 +136,12 @@ def train(model, train_loader, criterion, optimizer, device):
     rank, ws = D.world()
     D.sync_module(model)
     total_loss, correct, seen = 0.0, 0.0, 0
+    full_batch = None
     for images, labels in _bar(train_loader, "Training"):
         images, labels = D.shard(images.to(device), rank, ws), D.shard(labels.to(device), rank, ws)
-        optimizer.zero_grad()
-        outputs = model(images)
-        loss = criterion(outputs, labels)
-        loss.backward()
+        if full_batch is None:
+            full_batch = images.size(0)
+        outputs, loss = _step(model, criterion, optimizer, images, labels, full_batch, None)
         D.allreduce_gradients(model.parameters(), ws)
         optimizer.step()
         total_loss += loss.item() * images.size(0)
@@ -102,14 +180,13 @@ def train_with_scheduler(model, train_loader, criterion, optimizer, scheduler, d
     rank, ws = D.world()
     D.sync_module(model)
     total_loss, correct, seen = 0.0, 0.0, 0
+    full_batch = None
     bar = _bar(train_loader, "Training")
     for images, labels in bar:
         images, labels = D.shard(images.to(device), rank, ws), D.shard(labels.to(device), rank, ws)
-        optimizer.zero_grad()
-        with torch.amp.autocast(device_type="cuda", dtype=torch.bfloat16):
-            outputs = model(images)
-            loss = criterion(outputs, labels)
-        loss.backward()
+        if full_batch is None:
+            full_batch = images.size(0)
+        outputs, loss = _step(model, criterion, optimizer, images, labels, full_batch, torch.bfloat16)
         D.allreduce_gradients(model.parameters(), ws)
         optimizer.step()
         current_lr = scheduler.step()
@@ -131,23 +208,22 @@ def train_with_mixup_or_cutmix(model, train_loader, criterion, optimizer, schedu
     rank, ws = D.world()
     D.sync_module(model)
     total_loss, total_correct, total_samples = 0.0, 0.0, 0
+    full_batch = None
     bar = _bar(train_loader, "Training")
     for images, labels in bar:
         images, labels = images.to(device), labels.to(device)
+        if full_batch is None:
+            full_batch = D.shard(images, rank, ws).size(0)          # the loader's batch size (per rank): the shape that is captured
         if np.random.rand() < mix_prob:
             images, y_a, y_b, lam = mixup_data(images, labels, alpha=mixup_alpha)
         else:
             images, y_a, y_b, lam = cutmix_data(images, labels, alpha=cutmix_alpha)
         images, y_a, y_b = D.shard(images, rank, ws), D.shard(y_a, rank, ws), D.shard(y_b, rank, ws)
-        optimizer.zero_grad()
-        with torch.amp.autocast(device_type="cuda", dtype=torch.bfloat16):
-            outputs = model(images)
-            num_classes = outputs.size(1)
-            soft_targets = lam * F.one_hot(y_a, num_classes).float() + (1 - lam) * F.one_hot(y_b, num_classes).float()
-            loss = criterion(outputs, soft_targets)
-        loss.backward()
+        num_classes = _num_classes(model, images)
+        soft_targets = lam * F.one_hot(y_a, num_classes).float() + (1 - lam) * F.one_hot(y_b, num_classes).float()
+        outputs, loss = _step(model, criterion, optimizer, images, soft_targets, full_batch, torch.bfloat16)
         D.allreduce_gradients(model.parameters(), ws)
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0, foreach=False)
+        _clip_grad_norm(model.parameters(), 1.0)
         optimizer.step()
         scheduler.step()
         preds = outputs.argmax(dim=1)
