@@ -170,6 +170,32 @@ def cpu_reference_throughput(c, steps, warmup, batch):
     return batch / sec, sec, torch.get_num_threads()
 
 
+def curve_generation_table(device):
+    """K1 (csrc/curves.cu, one launch pair: count + emit) next to the CPU oracle port of the reference's
+    embed_and_prune_sfc (C restatement of its float pipeline, 1 core) for the grids BASELINE.md §4 names. The reference's
+    own Python recursion took 2.2 ms (n = 14) ... 9.0 s (n = 1024) at survey time (this container)."""
+    from oracle import curves as oc
+    from sfcvit import ops
+    rows = []
+    for curve, n in (("hilbert", 14), ("hilbert", 24), ("peano", 24), ("hilbert", 64), ("z", 224), ("hilbert", 224), ("hilbert", 1024)):
+        ops.curve_perm(curve, n, n, device)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            perm, _inv = ops.curve_perm(curve, n, n, device)
+        e1.record()
+        torch.cuda.synchronize()
+        gpu_us = e0.elapsed_time(e1) * 100.0                          # per call, microseconds
+        t0 = time.perf_counter()
+        ref = oc.flat_perm(curve, n, n)
+        cpu_us = (time.perf_counter() - t0) * 1e6
+        same = bool((perm.cpu().numpy().astype("int64") == ref).all())
+        rows.append({"curve": curve, "n": n, "k1_us": round(gpu_us, 1), "cpu_oracle_us": round(cpu_us, 1), "bit_exact": same,
+                     "cells_per_us_k1": round(n * n / gpu_us, 1)})
+    return rows
+
+
 def torch_gpu_throughput(c, device, batch, steps, warmup, compiled=False, infer=False):
     """INFORMATIONAL comparator: the reference's own modules (oracle port = stock torch nn.TransformerEncoder,
     SDPA, nn.Linear -> cuBLAS / cuDNN / flash kernels) on the SAME B200, bf16 autocast as the reference trains
@@ -768,6 +794,7 @@ def main():
                         "sample": f"2 timed steps (+1 warm-up) of batch {args.cpu_batch}, fp32, {threads} threads, same model/step as the GPU arm"}
 
     final_loss = float(loss.item())
+    curve_gen = curve_generation_table(device) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
     torch_gpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -795,6 +822,7 @@ def main():
             "gpu_launches_per_step": launches / args.steps, "clocks": clocks, "loss": final_loss,
             "allreduce_buckets_per_step": opt.last_num_buckets, "allreduce_buckets_overlapped": opt.last_overlapped_buckets,
             "allreduce_exposed_ms": allreduce_exposed_ms, "dp_check": dp_check, "torch_gpu_baseline": torch_gpu_baseline,
+            "curve_generation": curve_gen,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

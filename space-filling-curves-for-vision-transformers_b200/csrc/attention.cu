@@ -871,13 +871,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     auto readout = [&](const EwPos& cp) {
       const int sp = cp.s, qt = cp.qt, jt = cp.jt, h = cp.h;
       const int row0 = cp.b * p.N;
+      const int qi = qt * BQ + r;
       ptx::mbar_wait_relaxed(&bars[BwdBars::dq_full], sp & 1);
       ptx::tc_fence_after();
       {
         uint32_t rr[16];
         ptx::tmem_ld_x16(tmem_base + (sp & 1) * 128 + lane_off + ch * 16, rr);
         ptx::tmem_ld_wait();
-        const int qi = qt * BQ + r;
         if (qi < p.N) {
           if (p.dq_mode == 0) {
             float* dst = p.dq_acc + (long long)(row0 + qi) * p.D + h * DH + ch * 16;
@@ -889,9 +889,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             // (head-major item order), the first tile's dQ goes to scratch as bf16 and the second tile's read-out — the
             // same thread, two steps later — adds it back and writes the final value
             const bool first_of_two = p.dq_mode == 2 && jt == 0;
+            const bool second = p.dq_mode == 2 && jt != 0;
             __nv_bfloat16* part = p.dq_part + (long long)(row0 + qi) * p.D + h * DH + ch * 16;
             __nv_bfloat16* dst = first_of_two ? part : p.dqkv + (long long)(row0 + qi) * (3 * p.D) + h * DH + ch * 16;
-            const bool second = p.dq_mode == 2 && jt != 0;
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               float v[8];
