@@ -46,6 +46,18 @@ size_t sfc_curve_perm_scratch_bytes(int curve_id, int w, int h);
 int sfc_curve_perm(int curve_id, int w, int h, int32_t* perm_dev, int32_t* inv_dev, void* scratch_dev,
                    size_t scratch_bytes, sfc_stream_t stream);
 
+/* ---- host-side curve utilities (C++, no device work; init-time):
+ *      block_stitch_sfc (src/curves/space_filling_curves.py:513-591) and find_hamiltonian_path /
+ *      refine_curve_to_hamiltonian (:273-455) ----
+ * sfc_block_stitch: greedy power-of-base block decomposition of the width x height grid, per block the best of the 8
+ * symmetries; writes (i, j) pairs in stitched order and the points per block; returns the point count.
+ * sfc_hamiltonian_path: DFS with forced-move and flood-fill pruning; priority[i * height + j] = visiting priority
+ * (lower first; width * height for cells the guiding curve does not contain) or NULL; returns width * height on success,
+ * 0 if no path exists / the budget of max_steps expansions (0 = unlimited) ran out. */
+int sfc_block_stitch(int curve_id, int width, int height, int32_t* out_ij, int cap_pairs, int32_t* block_len, int block_cap,
+                     int* n_blocks);
+int sfc_hamiltonian_path(int width, int height, const int32_t* priority, int diag, long long max_steps, int32_t* out_ij);
+
 /* ---- K3: bf16 GEMM family with fused epilogue (nn.Linear / MHA projections / einsum:
  *      src/models/vit.py:197-206, 262-266, 289-292; tokenizer proj multi_hilbert.py:66,84) ----
  * D[M,N] = epilogue( alpha * A . B^T )

@@ -32,6 +32,8 @@ SIGNATURES = {
     "sfc_set_dropout_epoch_ptr": (None, [_vp]),
     "sfc_curve_perm_scratch_bytes": (_sz, [_i, _i, _i]),
     "sfc_curve_perm": (_i, [_i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "sfc_block_stitch": (_i, [_i, _i, _i, _vp, _i, _vp, _i, _vp]),
+    "sfc_hamiltonian_path": (_i, [_i, _i, _vp, _i, _ll, _vp]),
     "sfc_gemm_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "sfc_gemm_suggest_splits": (_i, [_i, _i, _i]),
     "sfc_gemm_colsum_splits": (_i, [_i, _i, _i, _i, _i]),

@@ -133,7 +133,32 @@ def get_symmetries(B: int) -> List[Callable[[float, float], Tuple[float, float]]
 
 def block_stitch_sfc(sfc, width: int, height: int):
     """Greedy power-of-base block decomposition with the best of 8 orientations per block (:513-591).
-    Returns (curve, blocked_curve). Host-side, init-time utility (not used by any tokenizer)."""
+    Returns (curve, blocked_curve). Init-time host utility (not used by any tokenizer): the four library curves run
+    in the C++ routine sfc_block_stitch (csrc/host_curves.cu) on the same integer per-index curve code as kernel K1."""
+    name = getattr(sfc, "__name__", None)
+    if name in _KERNEL_CURVES and getattr(sys.modules[__name__], name, None) is sfc:
+        import ctypes
+        from sfcvit import _lib, ops
+        lib = _lib.load()
+        n = width * height
+        out = np.empty((n, 2), dtype=np.int32)
+        blen = np.empty(n, dtype=np.int32)
+        nb = ctypes.c_int(0)
+        got = lib.sfc_block_stitch(ops.curve_id(sfc), width, height, out.ctypes.data, n, blen.ctypes.data, n, ctypes.byref(nb))
+        if got != n:
+            msg = lib.sfc_last_error()
+            raise RuntimeError(f"sfc_block_stitch failed: {msg.decode() if msg else got}")
+        curve = [(int(i), int(j)) for i, j in out]
+        blocked, off = [], 0
+        for k in blen[:nb.value]:
+            blocked.append(curve[off:off + int(k)])
+            off += int(k)
+        return curve, blocked
+    return _block_stitch_generic(sfc, width, height)
+
+
+def _block_stitch_generic(sfc, width: int, height: int):
+    """The same recipe for a user-supplied curve callable (host Python, as in the reference)."""
     base = 3 if sfc.__name__ == "peano_curve" else 2
     blocks = []
 
@@ -174,67 +199,25 @@ def block_stitch_sfc(sfc, width: int, height: int):
     return curve, blocked
 
 
-def find_hamiltonian_path(width, height, adjacency_order=None, diag=False):
-    """Depth-first Hamiltonian path search on the grid with flood-fill and dead-end pruning (:273-443)."""
-    sys.setrecursionlimit(10_000_000)
+def find_hamiltonian_path(width, height, adjacency_order=None, diag=False, max_steps=200_000_000):
+    """Depth-first Hamiltonian path search on the grid with forced-move and flood-fill pruning (:273-443), as the C++
+    routine sfc_hamiltonian_path (csrc/host_curves.cu; same neighbour order and tie-breaking, so the same path).
+    `max_steps` bounds the exponential worst case (the reference has no bound); None when no path was found."""
+    from sfcvit import _lib
+    lib = _lib.load()
     total = width * height
-    visited = [[False] * height for _ in range(width)]
-    path = []
-    dirs = [(1, 0), (-1, 0), (0, 1), (0, -1)] + ([(1, 1), (1, -1), (-1, 1), (-1, -1)] if diag else [])
-    nbrs_of = {(x, y): [(x + dx, y + dy) for dx, dy in dirs if 0 <= x + dx < width and 0 <= y + dy < height]
-               for x in range(width) for y in range(height)}
-
-    def ordered(x, y):
-        def key(v):
-            is_diag = 1 if abs(v[0] - x) == 1 and abs(v[1] - y) == 1 else 0
-            return (is_diag, adjacency_order.get(v, total) if adjacency_order else 0)
-        return sorted(nbrs_of[(x, y)], key=key)
-
-    def reachable(sx, sy, remaining):
-        stack, seen, cnt = [(sx, sy)], {(sx, sy)}, 0
-        while stack:
-            x, y = stack.pop()
-            cnt += 1
-            if cnt >= remaining:
-                return True
-            for n in nbrs_of[(x, y)]:
-                if not visited[n[0]][n[1]] and n not in seen:
-                    seen.add(n)
-                    stack.append(n)
-        return cnt >= remaining
-
-    def dfs(x, y):
-        if len(path) == total:
-            return True
-        cand = [n for n in ordered(x, y) if not visited[n[0]][n[1]]]
-        forced, kept = [], []
-        for n in cand:
-            exits = sum(1 for u in nbrs_of[n] if not visited[u[0]][u[1]] and u != (x, y))
-            if exits == 0 and len(path) + 1 < total:
-                continue
-            if exits == 1:
-                forced.append(n)
-            kept.append(n)
-        for nx, ny in (forced or kept):
-            visited[nx][ny] = True
-            path.append((nx, ny))
-            rem = total - len(path)
-            if rem == 0 or reachable(nx, ny, rem):
-                if dfs(nx, ny):
-                    return True
-            visited[nx][ny] = False
-            path.pop()
-        return False
-
-    starts = [min(adjacency_order, key=adjacency_order.get)] if adjacency_order else \
-        [(0, 0), (width - 1, 0), (0, height - 1), (width - 1, height - 1)]
-    for sx, sy in starts:
-        visited[sx][sy] = True
-        path[:] = [(sx, sy)]
-        if dfs(sx, sy):
-            return path
-        visited[sx][sy] = False
-    return None
+    pr = None
+    if adjacency_order:
+        pr = np.full(total, total, dtype=np.int32)
+        for (x, y), v in adjacency_order.items():
+            if 0 <= x < width and 0 <= y < height:
+                pr[x * height + y] = v
+    out = np.empty((total, 2), dtype=np.int32)
+    got = lib.sfc_hamiltonian_path(width, height, pr.ctypes.data if pr is not None else None, 1 if diag else 0, int(max_steps),
+                                   out.ctypes.data)
+    if got != total:
+        return None
+    return [(int(i), int(j)) for i, j in out]
 
 
 def refine_curve_to_hamiltonian(curve, width, height):

@@ -123,3 +123,55 @@ def test_uint8_normalisation_folding(k_order):
     got = patch.reshape(5, K) @ wk[:, :K].float().t() + bias_k.float()
     assert float((got - ref).norm() / ref.norm()) < 1e-2                         # bf16 rounding of the folded weight
     assert torch.allclose(scale_k.reshape(-1, C)[0], 1.0 / (255.0 * std)) and torch.allclose(shift_k.reshape(-1, C)[0], mean / std)
+
+
+def _h16(curve, height):
+    import hashlib
+    import numpy as np
+    return hashlib.sha256(np.array([int(i) * height + int(j) for i, j in curve], "<i8").tobytes()).hexdigest()[:16]
+
+
+def test_block_stitch_cpp_matches_live_reference_goldens():
+    """sfc_block_stitch (C++ host routine, csrc/host_curves.cu) vs hashes of the LIVE reference's block_stitch_sfc
+    (/root/reference/src/curves/space_filling_curves.py:513-591; tests/golden/make_host_curve_golden.py): 4 curves x
+    {7, 12, 14, 24, 27, 32}^2 and two rectangles — the stitched order AND the block partition."""
+    import json
+    from src.curves import space_filling_curves as sc
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "host_curves.json")))["block_stitch"]
+    fn = {"hilbert": sc.hilbert_curve, "z": sc.z_curve, "peano": sc.peano_curve, "moore": sc.moore_curve}
+    assert len(gold) == 32
+    for key, g in gold.items():
+        name, dims = key.split("_")
+        w, h = map(int, dims.split("x"))
+        curve, blocked = sc.block_stitch_sfc(fn[name], w, h)
+        assert sorted(curve) == [(i, j) for i in range(w) for j in range(h)], key
+        assert _h16(curve, h) == g["hash"], key
+        assert [len(b) for b in blocked] == g["blocks"], key
+
+
+def test_hamiltonian_refinement_cpp_matches_live_reference_goldens():
+    """sfc_hamiltonian_path vs the live reference's find_hamiltonian_path / refine_curve_to_hamiltonian (:273-455): the
+    guiding curves come from the oracle (no GPU here); every grid the reference solved within 20 s is pinned."""
+    import json
+    from oracle import curves as oc
+    from src.curves import space_filling_curves as sc
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "host_curves.json")))
+    n = 0
+    for key, g in gold["refine"].items():
+        if "hash" not in g:
+            continue                                    # the reference itself timed out on this grid
+        name, dims = key.split("_")
+        w, h = map(int, dims.split("x"))
+        guide = [tuple(x) for x in oc.embed_and_prune(name, w, h).tolist()]
+        ham = sc.refine_curve_to_hamiltonian(guide, w, h)
+        assert ham is not None and _h16(ham, h) == g["hash"], key
+        assert all(abs(a[0] - b[0]) + abs(a[1] - b[1]) == 1 for a, b in zip(ham, ham[1:])), key
+        n += 1
+    assert n >= 16
+    for key, g in gold["hamiltonian"].items():
+        dims, dg = key.split("_diag")
+        w, h = map(int, dims.split("x"))
+        p = sc.find_hamiltonian_path(w, h, diag=bool(int(dg)))
+        assert _h16(p, h) == g["hash"], key
+    # 3 x 3 grid from an edge-middle cell: 4 cells of that colour against 5 of the other — no Hamiltonian path exists
+    assert sc.find_hamiltonian_path(3, 3, adjacency_order={(0, 1): 0}, max_steps=100000) is None
