@@ -175,3 +175,35 @@ def test_hamiltonian_refinement_cpp_matches_live_reference_goldens():
         assert _h16(p, h) == g["hash"], key
     # 3 x 3 grid from an edge-middle cell: 4 cells of that colour against 5 of the other — no Hamiltonian path exists
     assert sc.find_hamiltonian_path(3, 3, adjacency_order={(0, 1): 0}, max_steps=100000) is None
+
+
+def test_curve_properties_hypothesis(host_curve_lib):
+    """Property tests (hypothesis) of the kernel's integer curve routines on arbitrary rectangles: the emitted order is a
+    permutation of the grid, equals the oracle's float pipeline, restricting a larger grid's curve to a sub-rectangle
+    that shares its padded order gives the sub-rectangle's curve (pruning commutes), and Hilbert / Moore / Peano on
+    their full power-of-base squares move one cell at a time."""
+    from hypothesis import given, settings, strategies as st
+
+    def perm(cid, w, h):
+        out = np.empty(w * h, dtype=np.int64)
+        assert host_curve_lib.sfc_host_perm(cid, w, h, out.ctypes.data) == w * h
+        return out
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(0, 3), st.integers(1, 48), st.integers(1, 48))
+    def prop(cid, w, h):
+        curve = ["hilbert", "z", "peano", "moore"][cid]
+        p = perm(cid, w, h)
+        assert np.array_equal(np.sort(p), np.arange(w * h))
+        assert np.array_equal(p, oc.flat_perm(curve, w, h))
+        base = 3 if cid == 2 else 2
+        P = 1
+        while P < max(w, h):
+            P *= base
+        full = perm(cid, P, P)                               # the un-pruned curve on the padded square
+        i, j = full // P, full % P
+        keep = (i < w) & (j < h)
+        assert np.array_equal(i[keep] * h + j[keep], p)
+        if cid != 1 and P > 1:                               # continuity (the Z curve jumps by construction)
+            assert int((np.abs(np.diff(i)) + np.abs(np.diff(j))).max()) == 1
+    prop()
