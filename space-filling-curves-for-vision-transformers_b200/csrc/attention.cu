@@ -144,14 +144,15 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // work BETWEEN the MUFUs. Left to ptxas, a 32-column chunk became 32 x (FFMA, MUFU, FADD) followed by ~140 integer / select
 // / convert instructions of the dropout mask and the bf16 pack: two phases bound by different pipes that a warp executes
 // one after the other (18 cycles per element instead of 8). Here the stream is written out by hand in units of 16 key
-// columns (= one dropout group): `volatile` keeps the order, so while unit u's exponentials go down the MUFU pipe the
-// row sum, mask, pack and shared-memory store of unit u-1 fill the issue slots in between (~6.5 instructions per MUFU).
+// columns (= one dropout group) as a software pipeline: while unit u's exponentials go down the MUFU pipe, the row sum,
+// mask, pack and shared-memory store of unit u-1 are independent work for the issue slots in between (~6.5 instructions
+// per MUFU); ptxas schedules the merged stream (measured: 7.8 SASS instructions per element, 0.169 -> 0.134 ms).
 template <int I>
 __device__ __forceinline__ void exp_post_elem(float& pv, float& psum, uint32_t seed, uint32_t thr_hi, bool drop) {
-  asm volatile("add.f32 %0, %0, %1;" : "+f"(psum) : "f"(pv));                 // the denominator sums the UNMASKED probabilities
+  asm("add.f32 %0, %0, %1;" : "+f"(psum) : "f"(pv));                 // the denominator sums the UNMASKED probabilities
   if (drop) {
     constexpr uint32_t A = lcg_mul(I + 1), C = lcg_add(I + 1);
-    asm volatile(
+    asm(
         "{\n\t"
         ".reg .pred p;\n\t"
         ".reg .u32 t;\n\t"
@@ -165,7 +166,7 @@ __device__ __forceinline__ void exp_post_elem(float& pv, float& psum, uint32_t s
 }
 __device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
   uint32_t d;
-  asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
@@ -183,8 +184,8 @@ template <bool kDrop, int I>
 __device__ __forceinline__ void exp_step_elem(const uint32_t* s, float sl2, float nmb, float* pn, float* pp, float& psum,
                                               uint32_t seed_prev, uint32_t thr_hi, uint32_t* pk) {
   float x;
-  asm volatile("fma.rn.f32 %0, %1, %2, %3;" : "=f"(x) : "f"(__uint_as_float(s[I])), "f"(sl2), "f"(nmb));
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(pn[I]) : "f"(x));
+  asm("fma.rn.f32 %0, %1, %2, %3;" : "=f"(x) : "f"(__uint_as_float(s[I])), "f"(sl2), "f"(nmb));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pn[I]) : "f"(x));
   exp_post_elem<I>(pp[I], psum, seed_prev, thr_hi, kDrop);
   if constexpr ((I & 1) == 1) pk[I >> 1] = cvt_bf16x2(pp[I - 1], pp[I]);
 }
