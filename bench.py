@@ -453,7 +453,7 @@ def run_infer(args, c):
         dist.destroy_process_group()
 
 
-def check_dp(c, device, rank, world, curve):
+def check_dp(c, device, rank, world, curve, overlap=False):
     """Data-parallel correctness on the hardware the scaling run uses (N > 1, default on): the SAME code path as the timed
     step — GraphedStep with FusedAdamW inside the graph, gradients written into the flat bucket, bucket ranges all-reduced
     on the side stream — on a depth-2 model of the config's width with dropout off and lr = 0, then rank 0 alone runs
@@ -482,7 +482,7 @@ def check_dp(c, device, rank, world, curve):
     crit = SoftTargetCrossEntropy()
     model = build()
     D.sync_module(model)
-    opt = FusedAdamW(model.parameters(), lr=0.0, weight_decay=0.0, max_grad_norm=1.0)
+    opt = FusedAdamW(model.parameters(), lr=0.0, weight_decay=0.0, max_grad_norm=1.0, overlap=overlap, comm_buckets=4 if overlap else 1)
     xs, ts = D.shard(x, rank, world), D.shard(tgt, rank, world)
     step = GraphedStep(model, crit, xs, ts, optimizer=opt)
     loss = step(xs, ts).detach().float().clone()
@@ -571,7 +571,10 @@ def main():
     ap.add_argument("--check-dp", dest="check_dp", action="store_true", default=None,
                     help="N > 1: assert the sharded step equals the full-batch step before timing (default: on when N > 1)")
     ap.add_argument("--no-check-dp", dest="check_dp", action="store_false")
-    ap.add_argument("--no-overlap", action="store_true", help="N > 1: one all-reduce after backward instead of bucket ranges on a side stream during backward")
+    ap.add_argument("--overlap", action="store_true",
+                    help="N > 1: all-reduce 4 bucket ranges on a side stream DURING backward instead of one all-reduce after it. Measured "
+                         "slower (profiles/r2_bench_2gpu_*.json: 32.86 vs 32.49 ms, exposed 1.02 vs 0.61 ms): the persistent "
+                         "one-CTA-per-SM kernels leave NCCL no SM to run on, and its CTAs then delay the next kernel's wave")
     ap.add_argument("--no-exposed", action="store_true", help="N > 1: skip the second (collective-free) capture that measures allreduce_exposed_ms")
     args = ap.parse_args()
     c = dict(CONFIGS[args.config])
@@ -603,7 +606,7 @@ def main():
 
     dp_check = None
     if world > 1 and args.check_dp is not False:
-        dp_check = check_dp(c, device, rank, world, args.curve)
+        dp_check = check_dp(c, device, rank, world, args.curve, overlap=args.overlap)
     model = build_b200_model(c, device, args.curve)
     D.sync_module(model)
     if args.no_dropout:
@@ -613,7 +616,7 @@ def main():
             if isinstance(m, torch.nn.MultiheadAttention):
                 m.dropout = 0.0
     opt = FusedAdamW(model.parameters(), lr=3e-4, weight_decay=5e-5, max_grad_norm=1.0,   # main.py:288-289 + train.py:165
-                     overlap=not args.no_overlap, comm_buckets=1 if args.no_overlap else 4)
+                     overlap=args.overlap, comm_buckets=4 if args.overlap else 1)
     crit = SoftTargetCrossEntropy()
 
     g = torch.Generator(device=device).manual_seed(1234 + rank)

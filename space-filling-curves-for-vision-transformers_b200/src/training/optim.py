@@ -7,10 +7,13 @@ EAGERLY at construction; the nn.Parameters become views (names / shapes / state_
 gradient slice is registered with sfcvit.functional so that the wgrad GEMMs and reductions write gradients straight into
 the bucket (no packing copy). Gradients produced any other way are copied into their slice at step().
 
-Data parallel: the bucket is cut into contiguous ranges; a post-accumulate-grad hook per parameter counts a range down
-and, when its last gradient has landed, all-reduces the range on a side stream while backward continues on the main
-stream (reverse registration order == the order backward produces gradients). step() joins the side stream, reduces
-whatever is left, then runs kernel K6 (csrc/optim.cu): deterministic sum of squares -> clip coefficient on device ->
+Data parallel: by default ONE all-reduce of the whole bucket after backward (no packing copy: the gradients are already
+there). With overlap=True the bucket is cut into `comm_buckets` contiguous ranges; a post-accumulate-grad hook per
+parameter counts a range down and, when its last gradient has landed, all-reduces the range on a side stream while
+backward continues on the main stream (reverse registration order == the order backward produces gradients). On B200
+with this library's persistent one-CTA-per-SM kernels that is measured SLOWER (2 GPUs: 32.86 vs 32.49 ms per step,
+profiles/r2_bench_2gpu_*.json): NCCL's CTAs find no free SM until a kernel ends and then hold up the next kernel's wave.
+step() joins the side stream, reduces whatever is left, then runs kernel K6 (csrc/optim.cu): deterministic sum of squares -> clip coefficient on device ->
 AdamW with the 1/world averaging folded in. Learning rate and bias corrections reach the kernel through a small device
 block written in stream order, so the whole step() can sit inside a CUDA graph (src/training/graphs.py) and still follow
 a host-side scheduler.
@@ -30,7 +33,7 @@ _ALIGN = 64            # elements: every parameter starts on a 128-byte (bf16) /
 
 class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=0.0,
-                 state_dtype=None, comm_buckets=4, overlap=True):
+                 state_dtype=None, comm_buckets=1, overlap=False):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
         super().__init__(params, defaults)
         self._state_dtype = state_dtype

@@ -32,7 +32,7 @@ def _build(device):
 def _step(m, x, t, world_expected):
     from oracle.model import soft_target_cross_entropy
     from src.training.optim import FusedAdamW
-    opt = FusedAdamW(m.parameters(), lr=0.0, weight_decay=0.0, max_grad_norm=1.0, comm_buckets=3)
+    opt = FusedAdamW(m.parameters(), lr=0.0, weight_decay=0.0, max_grad_norm=1.0, comm_buckets=3, overlap=True)
     # step 1 (lr = 0) teaches the optimizer which parameters receive gradients: its ranges are reduced inside step();
     # step 2 is the overlapped path — per-parameter hooks all-reduce each range on the side stream during backward
     for it in range(2):
