@@ -242,6 +242,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + FwdBars::count);
 
+  ptx::pdl_launch_dependents();
   const int tid = threadIdx.x, warp = tid >> 5;
   const int bkv = L.bkv, nkv = L.nkv, stages = L.stages;
   const int kv_bytes = (bkv * 128 + 1023) / 1024 * 1024;
@@ -271,6 +272,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  ptx::pdl_wait();                                 // set-up done; the previous kernel's qkv is read from here on
   // TMEM region w = columns [w * 256, w * 256 + 256). Single pass: S in [0, bkv <= 208), O overwrites [0, 64).
   // Multi-tile (bkv <= 192): S in [0, 192), O RESIDENT in [192, 256) across the key tiles of an item.
   constexpr uint32_t kOCol = kSingle ? 0u : 192u;
@@ -625,6 +627,8 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // delta[b, h, n] = sum_d dO[b, n, h, d] * O[b, n, h, d]   (8 lanes per (row, head), fully coalesced)
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
                                                             float* __restrict__ delta, long long rows, int N, int H) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const long long total = rows * H * 8;
   const int lane = threadIdx.x & 31;
   // warp-uniform loop (the shuffles below need all 32 lanes)
@@ -708,6 +712,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::kBar);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + BwdBars::count);
 
+  ptx::pdl_launch_dependents();
   const int tid = threadIdx.x, warp = tid >> 5;
   const int nq = (p.N + BQ - 1) / BQ;                       // steps per item
   const int n_kvt = (p.N + bkv - 1) / bkv;
@@ -741,6 +746,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_dp = tmem_base + 256, tmem_dv = tmem_base + 384, tmem_dk = tmem_base + 448;
+  ptx::pdl_wait();                                 // set-up done; delta / qkv / dO of the previous kernels are read from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -1138,10 +1144,10 @@ extern "C" int sfc_attn_fwd(const void* qkv, void* out, float* lse, int B, int H
   const long long items = (long long)B * H * ((N + 2 * BQ - 1) / (2 * BQ));
   const int grid = (int)(items < sfc_num_sms() ? items : sfc_num_sms());
   const bool drop = drop_p > 0.f;
-  if (L.nkv == 1 && drop) attn_fwd_kernel<true, true><<<grid, kFwdThreads, L.total, stream>>>(tq, tkv, to, p, L);
-  else if (L.nkv == 1) attn_fwd_kernel<true, false><<<grid, kFwdThreads, L.total, stream>>>(tq, tkv, to, p, L);
-  else if (drop) attn_fwd_kernel<false, true><<<grid, kFwdThreads, L.total, stream>>>(tq, tkv, to, p, L);
-  else attn_fwd_kernel<false, false><<<grid, kFwdThreads, L.total, stream>>>(tq, tkv, to, p, L);
+  if (L.nkv == 1 && drop) SFC_CUDA_OK(sfc_launch_pdl(attn_fwd_kernel<true, true>, dim3(grid), dim3(kFwdThreads), (size_t)L.total, stream, tq, tkv, to, p, L));
+  else if (L.nkv == 1) SFC_CUDA_OK(sfc_launch_pdl(attn_fwd_kernel<true, false>, dim3(grid), dim3(kFwdThreads), (size_t)L.total, stream, tq, tkv, to, p, L));
+  else if (drop) SFC_CUDA_OK(sfc_launch_pdl(attn_fwd_kernel<false, true>, dim3(grid), dim3(kFwdThreads), (size_t)L.total, stream, tq, tkv, to, p, L));
+  else SFC_CUDA_OK(sfc_launch_pdl(attn_fwd_kernel<false, false>, dim3(grid), dim3(kFwdThreads), (size_t)L.total, stream, tq, tkv, to, p, L));
   SFC_LAUNCH_OK();
   return 0;
 }
@@ -1178,7 +1184,8 @@ extern "C" int sfc_attn_bwd(const void* qkv, const void* out, const void* dout, 
     long long blocks = sfc_ceil_div64(rows * H * 8, 256);
     const long long cap = 32ll * sfc_num_sms();
     if (blocks > cap) blocks = cap;
-    attn_bwd_prep_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta, rows, N, H);
+    SFC_CUDA_OK(sfc_launch_pdl(attn_bwd_prep_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout,
+                               delta, rows, N, H));
     SFC_LAUNCH_OK();
   }
   CUtensorMap tq, tkv, tdo;
@@ -1197,7 +1204,7 @@ extern "C" int sfc_attn_bwd(const void* qkv, const void* out, const void* dout, 
   }
   const long long items = (long long)B * H;                  // the CTAs stride over heads (all key tiles of a head on one CTA)
   const int grid = (int)(items < sfc_num_sms() ? items : sfc_num_sms());
-  attn_bwd_kernel<<<grid, kBwdThreads, BwdSmem::kTotal, stream>>>(tq, tkv, tdo, p, bkv);
+  SFC_CUDA_OK(sfc_launch_pdl(attn_bwd_kernel, dim3(grid), dim3(kBwdThreads), (size_t)BwdSmem::kTotal, stream, tq, tkv, tdo, p, bkv));
   SFC_LAUNCH_OK();
   if (dq_mode == 0) {
     long long blocks = sfc_ceil_div64(rows * (D / 8), 256);

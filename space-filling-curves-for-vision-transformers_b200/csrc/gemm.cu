@@ -78,6 +78,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* opnd_bar = tmem_empty + 2;         // [kEpiWarps][2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(opnd_bar + 2 * kEpiWarps);
 
+  ptx::pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int crank = CL > 1 ? (int)ptx::cluster_ctarank() : 0;
   const bool leader = crank == 0;
@@ -119,6 +120,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if constexpr (CL > 1) ptx::cluster_sync();       // peer barriers are initialised before any remote arrive / multicast commit
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  ptx::pdl_wait();                                 // set-up done; from here on global memory of the previous kernel is read
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA: its A rows and its share of the B tile) =====================
@@ -314,6 +316,8 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, long long spl
                                      long long ld_out, int M, int N, int out_fp32, int accumulate, float alpha,
                                      const __nv_bfloat16* __restrict__ bias, int act, const float* __restrict__ cs_ws,
                                      void* __restrict__ cs_out, int cs_fp32, int cs_parts) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)M * N;
   if (idx >= total) { reduce_colsum(idx - total, cs_ws, cs_parts, M, cs_out, cs_fp32); return; }
@@ -339,6 +343,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_vec4_kernel(const float4* _
                                                                  void* __restrict__ out, long long ld_out, int M, int N4, int out_fp32,
                                                                  int accumulate, const float* __restrict__ cs_ws,
                                                                  void* __restrict__ cs_out, int cs_fp32, int cs_parts) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)M * N4) { reduce_colsum(idx - (long long)M * N4, cs_ws, cs_parts, M, cs_out, cs_fp32); return; }
   const long long m = idx / N4, n = (idx % N4) * 4;
@@ -400,11 +406,13 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = L::kTotal;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = sfc_pdl_enabled() ? 2 : 1;
   SFC_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, topnd, p));
   return 0;
 }
@@ -581,13 +589,13 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
                       (reinterpret_cast<uintptr_t>(ep->out) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0;
     const long long extra = want_cs ? M : 0;                  // threads past the main range reduce the column sums
     if (vec4)
-      splitk_reduce_vec4_kernel<<<(unsigned)((total / 4 + extra + threads - 1) / threads), threads, 0, stream>>>(
+      SFC_CUDA_OK(sfc_launch_pdl(splitk_reduce_vec4_kernel, dim3((unsigned)((total / 4 + extra + threads - 1) / threads)), dim3(threads), 0, stream,
           (const float4*)workspace, (long long)M * N / 4, splits, ep->out, ep->ld_out, M, N / 4, ep->out_fp32, ep->accumulate,
-          pk.cs_ws, ep->colsum_out, ep->colsum_fp32, splits * p.num_n_tiles);
+          (const float*)pk.cs_ws, ep->colsum_out, ep->colsum_fp32, splits * p.num_n_tiles));
     else
-      splitk_reduce_kernel<<<(unsigned)((total + extra + threads - 1) / threads), threads, 0, stream>>>(
+      SFC_CUDA_OK(sfc_launch_pdl(splitk_reduce_kernel, dim3((unsigned)((total + extra + threads - 1) / threads)), dim3(threads), 0, stream,
         (const float*)workspace, (long long)M * N, splits, ep->out, ep->ld_out, M, N, ep->out_fp32, ep->accumulate, ep->alpha,
-        (const __nv_bfloat16*)ep->bias, ep->act, pk.cs_ws, ep->colsum_out, ep->colsum_fp32, splits * p.num_n_tiles);
+        (const __nv_bfloat16*)ep->bias, ep->act, (const float*)pk.cs_ws, ep->colsum_out, ep->colsum_fp32, splits * p.num_n_tiles));
     SFC_LAUNCH_OK();
   }
   return 0;

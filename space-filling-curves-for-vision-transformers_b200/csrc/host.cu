@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include <stdlib.h>
 #include "sfcvit.h"
 
 static thread_local char g_err[1024] = "";
@@ -85,6 +86,11 @@ int sfc_make_tmap_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t
   SFC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed (%d) cols=%llu rows=%llu slabs=%llu", (int)r,
               (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)slabs);
   return 0;
+}
+
+bool sfc_pdl_enabled() {
+  static const bool on = getenv("SFC_NO_PDL") == nullptr;
+  return on;
 }
 
 int sfc_num_sms() {

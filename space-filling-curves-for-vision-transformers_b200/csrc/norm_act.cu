@@ -38,6 +38,8 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
                      const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, long long rows, int D, float eps) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -99,6 +101,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      __nv_bfloat16* __restrict__ dx_drop, float drop_p, unsigned long long drop_seed,
                      const unsigned long long* __restrict__ drop_epoch,
                      float* __restrict__ part, long long rows, int D) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   extern __shared__ float sred[];            // [kLnWarps][3][D]
   const DropKey dkey = drop_key(drop_seed, drop_p, drop_epoch);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -194,6 +198,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long long rows, int N, float* __restrict__ part,
                       long long rows_per_block) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   __shared__ float sred[8][256 + 8];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col0 = (blockIdx.x * 32 + tx) * 8;
@@ -238,6 +244,8 @@ struct FinalizeOut { void* ptr[3]; };
 __global__ void __launch_bounds__(256) partial_finalize_kernel(const float* __restrict__ part, int nparts, long long stride,
                                                                long long vstride, int N, FinalizeOut outs, int out_fp32,
                                                                int accumulate) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   __shared__ float sred[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -279,6 +287,8 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __res
                                                       __nv_bfloat16* __restrict__ out, long long nvec, int mode, float alpha,
                                                       float drop_p, unsigned long long seed,
                                                       const unsigned long long* __restrict__ drop_epoch) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const DropKey dkey = drop_key(seed, drop_p, drop_epoch);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     float d[8], a[8], o[8];
@@ -315,8 +325,8 @@ extern "C" int sfc_layernorm_fwd(const void* x, const void* gamma, const void* b
   if (rows == 0) return 0;
   const unsigned grid = (unsigned)sfc_ceil_div64(rows, kLnWarps);
   const int nv = sfc_ceil_div(D / 8, 32);
-#define LN_FWD(NV) layernorm_fwd_kernel<NV><<<grid, kLnWarps * 32, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, \
-      (const __nv_bfloat16*)beta, (__nv_bfloat16*)y, mean, rstd, rows, D, eps)
+#define LN_FWD(NV) SFC_CUDA_OK(sfc_launch_pdl(layernorm_fwd_kernel<NV>, dim3(grid), dim3(kLnWarps * 32), 0, stream, (const __nv_bfloat16*)x, \
+      (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, (__nv_bfloat16*)y, mean, rstd, rows, D, eps))
   if (nv <= 1) LN_FWD(1); else if (nv <= 2) LN_FWD(2); else if (nv <= 3) LN_FWD(3); else if (nv <= 4) LN_FWD(4); else LN_FWD(8);
 #undef LN_FWD
   SFC_LAUNCH_OK();
@@ -347,9 +357,9 @@ extern "C" int sfc_layernorm_bwd(const void* dy, const void* x, const float* mea
   do {                                                                                                              \
     auto k = layernorm_bwd_kernel<NV, DR, CS>;                                                                      \
     if (smem > 48 * 1024) SFC_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k<<<blocks, kLnWarps * 32, smem, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd,       \
-                                               (const __nv_bfloat16*)gamma, (__nv_bfloat16*)dx, (__nv_bfloat16*)dx_drop, \
-                                               drop_p, drop_seed, sfc_dropout_epoch_ptr(), (float*)scratch, rows, D);                        \
+    SFC_CUDA_OK(sfc_launch_pdl(k, dim3(blocks), dim3(kLnWarps * 32), smem, stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, \
+                               (const __nv_bfloat16*)gamma, (__nv_bfloat16*)dx, (__nv_bfloat16*)dx_drop,            \
+                               drop_p, drop_seed, sfc_dropout_epoch_ptr(), (float*)scratch, rows, D));              \
   } while (0)
 #define LN_BWD(NV)                                                                  \
   do {                                                                              \
@@ -365,7 +375,7 @@ extern "C" int sfc_layernorm_bwd(const void* dy, const void* x, const float* mea
   FinalizeOut outs;
   outs.ptr[0] = dgamma; outs.ptr[1] = dbeta; outs.ptr[2] = dcolsum;
   dim3 grid(sfc_ceil_div(D, 32), csum ? 3 : 2);
-  partial_finalize_kernel<<<grid, 256, 0, stream>>>((const float*)scratch, blocks, 3ll * D, (long long)D, D, outs, param_fp32, accumulate);
+  SFC_CUDA_OK(sfc_launch_pdl(partial_finalize_kernel, grid, dim3(256), 0, stream, (const float*)scratch, blocks, 3ll * D, (long long)D, D, outs, param_fp32, accumulate));
   SFC_LAUNCH_OK();
   return 0;
 }

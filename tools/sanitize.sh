@@ -7,6 +7,6 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 TOOL=${1:-racecheck}
 python tools/sanitize_cases.py > gpurun_out/plain_sanitize.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_sanitize.log; exit 1; }
-timeout 1500 compute-sanitizer --tool $TOOL --print-limit 20 python tools/sanitize_cases.py > gpurun_out/r2_sanitizer_$TOOL.log 2>&1
+timeout ${SAN_TIMEOUT:-600} compute-sanitizer --tool $TOOL --print-limit 20 python tools/sanitize_cases.py > gpurun_out/r2_sanitizer_$TOOL.log 2>&1
 echo "compute-sanitizer $TOOL rc=$?"
 grep -E "ERROR SUMMARY|RACECHECK SUMMARY|SYNCCHECK SUMMARY|hazard|Invalid|out of bounds" gpurun_out/r2_sanitizer_$TOOL.log | head -20
