@@ -196,6 +196,45 @@ def curve_generation_table(device):
     return rows
 
 
+def patch_embed_sweep(device, peaks):
+    """BASELINE.json's second metric on the configurations where the bound really is HBM: the fused
+    curve-gather patch embed alone, fp32 NCHW input, embed-and-prune Hilbert order, CUDA events over rotating inputs
+    (> L2 in total). Algorithmic bytes = image read once + token matrix written once."""
+    from sfcvit import functional as SF
+    from sfcvit import ops
+    rows = []
+    for name, img, p, D, B in (("vit_tiny4_32", 32, 4, 192, 1024), ("vit_tiny4_32 (B 8192)", 32, 4, 192, 8192),
+                               ("vit_s16_224", 224, 16, 384, 256), ("vit_b16_224", 224, 16, 768, 256)):
+        n = img // p
+        perm, _ = ops.curve_perm("hilbert", n, n, device)
+        g = torch.Generator(device=device).manual_seed(0)
+        w = (torch.randn(D, 3 * p * p, generator=g, device=device) * 0.02).to(torch.bfloat16)
+        wk = SF.kernel_weight(w, 3, p, 1, "p1p2c")
+        bias = torch.zeros(D, dtype=torch.bfloat16, device=device)
+        nbuf = max(2, min(16, int(400e6 // (B * 3 * img * img * 4)) + 1))
+        xs = [torch.randn(B, 3, img, img, generator=g, device=device) for _ in range(nbuf)]
+        out = torch.empty(B, n * n, D, dtype=torch.bfloat16, device=device)
+        for i in range(3):
+            ops.patch_embed_fwd(xs[i % nbuf], perm, wk, bias, p, 1, out=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 20
+        e0.record()
+        for i in range(iters):
+            ops.patch_embed_fwd(xs[i % nbuf], perm, wk, bias, p, 1, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        nbytes = B * 3 * img * img * 4 + B * n * n * D * 2
+        flops = 2.0 * B * n * n * (3 * p * p) * D
+        t_roof = max(nbytes / (peaks["hbm_gbs"] * 1e9), flops / (peaks["tf_sustained"] * 1e12)) * 1e3
+        rows.append({"config": name, "batch": B, "ms": round(ms, 4), "achieved_gbs": round(nbytes / ms / 1e6, 1),
+                     "frac_hbm": round(nbytes / ms / 1e6 / peaks["hbm_gbs"], 3), "frac_of_max_hbm_tensor_roofline": round(t_roof / ms, 3),
+                     "bound": "hbm" if nbytes / (peaks["hbm_gbs"] * 1e9) > flops / (peaks["tf_sustained"] * 1e12) else "tensor"})
+        del xs
+    return rows
+
+
 def torch_gpu_throughput(c, device, batch, steps, warmup, compiled=False, infer=False):
     """INFORMATIONAL comparator: the reference's own modules (oracle port = stock torch nn.TransformerEncoder,
     SDPA, nn.Linear -> cuBLAS / cuDNN / flash kernels) on the SAME B200, bf16 autocast as the reference trains
@@ -798,6 +837,7 @@ def main():
 
     final_loss = float(loss.item())
     curve_gen = curve_generation_table(device) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    pe_sweep = patch_embed_sweep(device, peaks) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
     torch_gpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -825,7 +865,7 @@ def main():
             "gpu_launches_per_step": launches / args.steps, "clocks": clocks, "loss": final_loss,
             "allreduce_buckets_per_step": opt.last_num_buckets, "allreduce_buckets_overlapped": opt.last_overlapped_buckets,
             "allreduce_exposed_ms": allreduce_exposed_ms, "dp_check": dp_check, "torch_gpu_baseline": torch_gpu_baseline,
-            "curve_generation": curve_gen,
+            "curve_generation": curve_gen, "patch_embed_sweep": pe_sweep,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

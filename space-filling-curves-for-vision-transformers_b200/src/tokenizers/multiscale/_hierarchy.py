@@ -80,11 +80,5 @@ class HierarchicalCurveEmbedding(nn.Module):
         n_tokens = self.patch_list[0]
         # general-length case: kernel K7 resamples each stream along the token axis straight into
         # its column slice of the concat buffer (equal lengths degenerate to a copy)
-        cat = SF.concat_streams(streams, n_tokens)
-        if cat is None:                                   # feature size not a multiple of 8: torch ops on the same device
-            for i in range(len(streams)):
-                if streams[i].shape[1] != n_tokens:
-                    streams[i] = torch.nn.functional.interpolate(streams[i].transpose(1, 2), size=n_tokens, mode="linear",
-                                                                 align_corners=False).transpose(1, 2)
-            cat = torch.cat(streams, dim=-1)
+        cat = SF.concat_streams(streams, n_tokens)        # raises for per-level widths that are not multiples of 8: no torch fallback
         return SF.linear(cat, self.fusion.weight, self.fusion.bias)
