@@ -24,7 +24,6 @@ namespace {
 
 constexpr int DH = 64;
 constexpr int BQ = 128;
-constexpr int BKV = 128;
 constexpr int kTile = BQ * DH * 2;          // 16384 bytes: one 128 x 64 bf16 tile
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -47,32 +46,8 @@ struct AttnParams {
   long long* dbg;          // optional timeline buffer (sfc_debug_set_timeline), CTA 0 only
 };
 
-// write 32 consecutive P values (columns c32*32 .. +31 of row r) as bf16 into the K-major SW128 operand buffer
-__device__ __forceinline__ void store_p_chunk(uint8_t* buf, int r, int c32, const float* v) {
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int j8 = c32 * 4 + q;
-    uint4 o;
-    o.x = ptx::pack_bf16(v[q * 8 + 0], v[q * 8 + 1]); o.y = ptx::pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-    o.z = ptx::pack_bf16(v[q * 8 + 4], v[q * 8 + 5]); o.w = ptx::pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-    *reinterpret_cast<uint4*>(buf + (j8 >> 3) * kTile + r * 128 + (((j8 & 7) ^ (r & 7)) << 4)) = o;
-  }
-}
-
-// same, through a 32-bit shared-window address (st.shared.v4: no generic-address arithmetic in the exp loop)
-__device__ __forceinline__ void store_p_chunk_s32(uint32_t buf, int r, int c32, const float* v) {
-  const uint32_t row = buf + (uint32_t)((c32 >> 1) * kTile + r * 128);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int j8 = (c32 & 1) * 4 + q;                              // 16-byte slot inside the 128-byte row of this atom
-    const uint32_t x = ptx::pack_bf16(v[q * 8 + 0], v[q * 8 + 1]), y = ptx::pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-    const uint32_t z = ptx::pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), w = ptx::pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (uint32_t)((j8 ^ (r & 7)) << 4)), "r"(x), "r"(y), "r"(z), "r"(w)
-                 : "memory");
-  }
-}
-
-// 16 consecutive values (columns c16*16 .. +15 of row r) into the same layout (buf = 32-bit shared-window address)
+// 16 consecutive values (columns c16*16 .. +15 of row r) as bf16 into the K-major SW128 operand buffer (buf = 32-bit
+// shared-window address: st.shared, no generic-address arithmetic)
 __device__ __forceinline__ void store_p_half(uint32_t buf, int r, int c16, const float* v) {
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
