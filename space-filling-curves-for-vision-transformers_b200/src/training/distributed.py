@@ -7,6 +7,7 @@ then keeps `batch[rank::world]`. Gradients of the local mean loss are averaged o
 flat bucket (NCCL over NVLink on GPUs, gloo in the CPU tests) — equal shard sizes make this the full-batch gradient.
 """
 import os
+import weakref
 
 import torch
 import torch.distributed as dist
@@ -61,14 +62,14 @@ def agree(t, src=0):
     return t
 
 
-_synced = set()
+_synced = weakref.WeakSet()
 
 
 def sync_module(module, src=0, check=True):
     """Broadcast parameters and buffers from rank `src` (once per module) so the replicas start bit-identical even if
     their RNG streams diverged during construction; with check=True, also assert afterwards that a checksum agrees."""
     rank, ws = world()
-    if ws == 1 or id(module) in _synced:
+    if ws == 1 or module in _synced:
         return
     with torch.no_grad():
         tensors = [p.data for p in module.parameters()] + [b for b in module.buffers()]
@@ -83,7 +84,7 @@ def sync_module(module, src=0, check=True):
             dist.all_reduce(hi, op=dist.ReduceOp.MAX)
             if float(lo) != float(hi):
                 raise RuntimeError("data-parallel replicas differ after the initial broadcast")
-    _synced.add(id(module))
+    _synced.add(module)
 
 
 def build_buckets(tensors, bucket_bytes=BUCKET_BYTES):

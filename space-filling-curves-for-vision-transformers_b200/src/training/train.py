@@ -3,6 +3,9 @@ values: (avg_loss, avg_acc) python floats). Differences, all invisible to a sing
 the model's forward/backward run on the libsfcvit kernels, and when torch.distributed is initialised (torchrun) each
 step is batch-sharded across ranks with an NCCL gradient all-reduce between backward and the clip/optimizer step
 (reference insertion point: train.py:163-165). Rank 0 alone shows progress bars."""
+import os
+import weakref
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -50,17 +53,19 @@ def mixup_criterion(criterion, pred, y_a, y_b, lam):
 # criterion, batch shape) and every later step replays it (no Python / ctypes / tensor-map encoding per kernel). The
 # caller's optimizer, scheduler and gradient clipping stay what main.py passes in. SFC_TRAIN_GRAPH=0 turns it off; a
 # ragged last batch, CPU tensors or a failed capture fall back to launching the same kernels eagerly.
-_GRAPHS = {}
+_GRAPHS = weakref.WeakKeyDictionary()      # model -> {(criterion id, shapes, dtypes, autocast): GraphedStep | False}; dies with the model
 
 
 def _graphed_step(model, criterion, images, targets, autocast_dtype):
-    import os
     if os.environ.get("SFC_TRAIN_GRAPH", "1") == "0" or not images.is_cuda:
         return None
-    key = (id(model), id(criterion), tuple(images.shape), images.dtype, tuple(targets.shape), targets.dtype, autocast_dtype)
-    ent = _GRAPHS.get(key)
+    per_model = _GRAPHS.setdefault(model, {})
+    key = (id(criterion), tuple(images.shape), images.dtype, tuple(targets.shape), targets.dtype, autocast_dtype)
+    ent = per_model.get(key)
+    if ent is not None and ent and ent.criterion is not criterion:     # the id was recycled by another criterion object
+        ent = None
     if ent is None:
-        if sum(1 for k in _GRAPHS if k[0] == id(model)) >= 2:      # at most two captured shapes per model (activations are pinned)
+        if sum(1 for v in per_model.values() if v) >= 2:              # at most two captured shapes per model (activations are pinned)
             return None
         from .graphs import GraphedStep
         try:
@@ -69,12 +74,12 @@ def _graphed_step(model, criterion, images, targets, autocast_dtype):
             import warnings
             warnings.warn(f"sfcvit: step not capturable in a CUDA graph ({type(e).__name__}: {e}); launching eagerly")
             ent = False
-        _GRAPHS[key] = ent
+        per_model[key] = ent
     return ent or None
 
 
 def _has_graphs(model):
-    return any(k[0] == id(model) and v for k, v in _GRAPHS.items())
+    return any(bool(v) for v in _GRAPHS.get(model, {}).values())
 
 
 def _step(model, criterion, optimizer, images, targets, full_batch, autocast_dtype):
@@ -96,18 +101,18 @@ def _step(model, criterion, optimizer, images, targets, full_batch, autocast_dty
     return outputs, loss
 
 
-_NUM_CLASSES = {}
+_NUM_CLASSES = weakref.WeakKeyDictionary()
 
 
 def _num_classes(model, images):
-    n = _NUM_CLASSES.get(id(model))
+    n = _NUM_CLASSES.get(model)
     if n is None:
         was = model.training
         model.eval()
         with torch.no_grad(), torch.amp.autocast(device_type="cuda", dtype=torch.bfloat16):
             n = int(model(images[:1]).size(1))
         model.train(was)
-        _NUM_CLASSES[id(model)] = n
+        _NUM_CLASSES[model] = n
     return n
 
 
