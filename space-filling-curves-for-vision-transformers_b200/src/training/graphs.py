@@ -2,15 +2,17 @@
 
 The reference wraps its model in ``torch.compile(mode="reduce-overhead")`` (main.py:284), i.e. CUDA-graphed Inductor
 code. The B200 path has no tracing compiler: its kernels are launched through the C ABI, so the equivalent is to capture
-the ~370 launches of a step once and replay them (no Python / ctypes / tensor-map encoding on the critical path).
+the ~320 launches of a step once and replay them (no Python / ctypes / tensor-map encoding on the critical path).
+The training loops of src/training/train.py build one lazily per (model, criterion, batch shape).
 
     step = GraphedStep(model, criterion, example_images, example_targets)
     loss = step(images, targets)        # copies into the static buffers, replays, returns the static loss tensor
     optimizer.step()                    # p.grad tensors are static; do NOT zero them to None between replays
 
 or, with a FusedAdamW (src/training/optim.py), the WHOLE step in one graph — backward's wgrad kernels write into the
-optimizer's flat gradient bucket, the data-parallel all-reduce of each bucket range is captured on a side stream as soon
-as the range is complete, and grad-norm + clip + AdamW follow in the same graph:
+optimizer's flat gradient bucket, the data-parallel all-reduce of the bucket (one NCCL call after backward by default;
+bucket ranges on a side stream during backward with FusedAdamW(overlap=True)) is captured, and grad-norm + clip + AdamW
+follow in the same graph:
 
     step = GraphedStep(model, criterion, example_images, example_targets, optimizer=fused_adamw)
     loss = step(images, targets)        # advance() (lr / bias corrections -> device) + one replay; no optimizer.step()
