@@ -226,11 +226,365 @@ __global__ void __launch_bounds__(kGThreads) attn_generic_bwd_kernel(const GAttn
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Warp-MMA kernels (head_dim % 16 == 0): the same one-(image, head)-per-CTA plan with the seven matrix products on
+// mma.sync.m16n8k16 (bf16 in, fp32 accumulate). A warp owns a 16-row tile; NPAD = N rounded up to 16 / 32 / 64 / 96 / 128
+// (padding rows are zero in shared memory, padding keys are masked).
+//   X . Y^T products (Q K^T, dO V^T and their transposes K Q^T, V dO^T): both operands are read k-contiguous straight
+//     from the row-major tiles (32-bit loads; pitch dh + 8 elements = an odd number of 16-byte units, conflict-free);
+//   F . Z products (P V, dS K, P^T dO, dS^T Q): F is the probability tile converted in registers (accumulator layout ->
+//     A-fragment layout, two n-tiles per k-step), Z row-major with the contraction index on rows -> ldmatrix.trans.
+// The backward computes the transposed score tile (K Q^T) again for the key-row half instead of transposing dS through
+// shared memory, and gives the two halves (dQ | dK, dV) to different warps when NPAD <= 64.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ uint32_t lds32(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+
+// rows [0, N) x dh of a strided matrix -> smem [NPAD][ld] (16-byte stores), rows N.. zero
+__device__ __forceinline__ void load_rows_pad(__nv_bfloat16* dst, int ld, const __nv_bfloat16* src, long long row_stride, int N,
+                                              int npad, int dh) {
+  const int vec_per_row = dh / 8;
+  for (int i = threadIdx.x; i < npad * vec_per_row; i += blockDim.x) {
+    const int r = i / vec_per_row, c = (i % vec_per_row) * 8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < N) v = __ldg(reinterpret_cast<const uint4*>(src + (long long)r * row_stride + c));
+    *reinterpret_cast<uint4*>(dst + r * ld + c) = v;
+  }
+}
+
+// acc[nt] = X[m0 .. m0+15][0:dh] . Y[nt*8 .. nt*8+7][0:dh]^T
+template <int NT8>
+__device__ __forceinline__ void rowtile_nt(float (&acc)[NT8][4], const __nv_bfloat16* X, const __nv_bfloat16* Y, int m0, int ld,
+                                           int dh, int g, int t) {
+#pragma unroll
+  for (int nt = 0; nt < NT8; ++nt) { acc[nt][0] = 0.f; acc[nt][1] = 0.f; acc[nt][2] = 0.f; acc[nt][3] = 0.f; }
+  const __nv_bfloat16* xa = X + (m0 + g) * ld + 2 * t;
+  const __nv_bfloat16* yb = Y + g * ld + 2 * t;
+  for (int k0 = 0; k0 < dh; k0 += 16) {
+    uint32_t a[4];
+    a[0] = lds32(xa + k0); a[1] = lds32(xa + 8 * ld + k0); a[2] = lds32(xa + k0 + 8); a[3] = lds32(xa + 8 * ld + k0 + 8);
+#pragma unroll
+    for (int nt = 0; nt < NT8; ++nt) {
+      const uint32_t b0 = lds32(yb + nt * 8 * ld + k0), b1 = lds32(yb + nt * 8 * ld + k0 + 8);
+      mma16816(acc[nt], a, b0, b1);
+    }
+  }
+}
+
+// acc[nt] (columns d0 + nt*8 .., nt < 8) = F[16 x 16*NK] . Z[0 : 16*NK][d0 : d0+64]
+template <int NK>
+__device__ __forceinline__ void rowtile_nn(float (&acc)[8][4], const uint32_t (&f)[NK][4], const __nv_bfloat16* Z, int ld, int d0,
+                                           int dh, int lane) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = 0.f; acc[nt][1] = 0.f; acc[nt][2] = 0.f; acc[nt][3] = 0.f; }
+  const uint32_t zaddr = ptx::smem_u32(Z + (lane & 15) * ld + d0 + (lane >> 4) * 8);
+#pragma unroll
+  for (int kt = 0; kt < NK; ++kt) {
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      if (d0 + np * 16 < dh) {
+        uint32_t r0, r1, r2, r3;
+        ldsm_x4_trans(r0, r1, r2, r3, zaddr + (uint32_t)((kt * 16 * ld + np * 16) * 2));
+        mma16816(acc[2 * np], f[kt], r0, r1);
+        mma16816(acc[2 * np + 1], f[kt], r2, r3);
+      }
+    }
+  }
+}
+
+// rows m0 + g, m0 + g + 8 (< N), columns d0 + nt*8 + 2t (< dh) of a bf16 matrix with the given row stride
+__device__ __forceinline__ void store_chunk(const float (&acc)[8][4], __nv_bfloat16* dst, long long row_stride, int m0, int N,
+                                            int d0, int dh, int g, int t) {
+  const int r0 = m0 + g, r1 = r0 + 8;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int col = d0 + nt * 8 + 2 * t;
+    if (col < dh) {
+      if (r0 < N) *reinterpret_cast<uint32_t*>(dst + r0 * row_stride + col) = ptx::pack_bf16(acc[nt][0], acc[nt][1]);
+      if (r1 < N) *reinterpret_cast<uint32_t*>(dst + r1 * row_stride + col) = ptx::pack_bf16(acc[nt][2], acc[nt][3]);
+    }
+  }
+}
+
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+// LCG jump constants of position pos inside a dropout group: x_pos = seed * mul + add (== drop_keep<16>'s iteration)
+__device__ __forceinline__ void lcg_at(int pos, uint32_t& mul, uint32_t& add) {
+  uint32_t a = 1u, c = 0u;
+  for (int i = 0; i <= pos; ++i) { a *= kLcgA; c = c * kLcgA + kLcgC; }
+  mul = a; add = c;
+}
+
+template <int NPAD>
+__global__ void __launch_bounds__(NPAD * 2) attn_mma_fwd_kernel(const GAttnParams p) {
+  constexpr int NT8 = NPAD / 8, NK = NPAD / 16;
+  extern __shared__ __align__(16) uint8_t smem_g[];
+  const int N = p.N, dh = p.dh, ld = dh + 8;
+  __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smem_g);
+  __nv_bfloat16* sk = sq + NPAD * ld;
+  __nv_bfloat16* sv = sk + NPAD * ld;
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const __nv_bfloat16* base = p.qkv + (long long)b * N * 3 * p.D + h * dh;
+  load_rows_pad(sq, ld, base, 3ll * p.D, N, NPAD, dh);
+  load_rows_pad(sk, ld, base + p.D, 3ll * p.D, N, NPAD, dh);
+  load_rows_pad(sv, ld, base + 2 * p.D, 3ll * p.D, N, NPAD, dh);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, m0 = (threadIdx.x >> 5) * 16, g = lane >> 2, t = lane & 3;
+  const float sl2 = p.scale * kLog2eG;
+  float s[NT8][4];
+  rowtile_nt<NT8>(s, sq, sk, m0, ld, dh, g, t);
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < NT8; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (nt * 8 + 2 * t + (e & 1) >= N) s[nt][e] = -INFINITY;
+    }
+    mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+    mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+  }
+  mx0 = quad_max(mx0); mx1 = quad_max(mx1);
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < NT8; ++nt) {
+    s[nt][0] = exp2f((s[nt][0] - mx0) * sl2); s[nt][1] = exp2f((s[nt][1] - mx0) * sl2);
+    s[nt][2] = exp2f((s[nt][2] - mx1) * sl2); s[nt][3] = exp2f((s[nt][3] - mx1) * sl2);
+    sum0 += s[nt][0] + s[nt][1];
+    sum1 += s[nt][2] + s[nt][3];
+  }
+  sum0 = quad_sum(sum0); sum1 = quad_sum(sum1);
+  const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+  if (t == 0 && p.lse) {
+    float* lse = p.lse + ((long long)b * p.H + h) * N;
+    if (m0 + g < N) lse[m0 + g] = mx0 * p.scale + logf(sum0);
+    if (m0 + g + 8 < N) lse[m0 + g + 8] = mx1 * p.scale + logf(sum1);
+  }
+  uint32_t f[NK][4];
+  if (p.drop_p > 0.f) {
+    const DropKey dkey = drop_key(p.drop_seed, p.drop_p, p.drop_epoch);
+    const uint32_t thr_hi = dkey.thr16 << 16;
+    uint32_t mul[4], add[4];
+    lcg_at(2 * t, mul[0], add[0]); lcg_at(2 * t + 1, mul[1], add[1]);
+    lcg_at(2 * t + 8, mul[2], add[2]); lcg_at(2 * t + 9, mul[3], add[3]);
+    const unsigned long long groups = (unsigned long long)((N + 15) >> 4);
+    const unsigned long long row0 = ((unsigned long long)(b * p.H + h) * N + (unsigned long long)(m0 + g)) * groups;
+    const float k0 = inv0 * dkey.inv_keep, k1 = inv1 * dkey.inv_keep;
+#pragma unroll
+    for (int kt = 0; kt < NK; ++kt) {
+      const uint32_t h0 = drop_hash2(dkey, row0 + kt), h1 = drop_hash2(dkey, row0 + 8 * groups + kt);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int nt = 2 * kt + half;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int ci = half * 2 + (e & 1);
+          const uint32_t x = ((e >> 1) ? h1 : h0) * mul[ci] + add[ci];
+          s[nt][e] = (x >= thr_hi) ? s[nt][e] * ((e >> 1) ? k1 : k0) : 0.f;
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int nt = 0; nt < NT8; ++nt) { s[nt][0] *= inv0; s[nt][1] *= inv0; s[nt][2] *= inv1; s[nt][3] *= inv1; }
+  }
+#pragma unroll
+  for (int kt = 0; kt < NK; ++kt) {
+    f[kt][0] = ptx::pack_bf16(s[2 * kt][0], s[2 * kt][1]); f[kt][1] = ptx::pack_bf16(s[2 * kt][2], s[2 * kt][3]);
+    f[kt][2] = ptx::pack_bf16(s[2 * kt + 1][0], s[2 * kt + 1][1]); f[kt][3] = ptx::pack_bf16(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+  }
+  __nv_bfloat16* out = p.out + (long long)b * N * p.D + h * dh;
+  for (int d0 = 0; d0 < dh; d0 += 64) {
+    float o[8][4];
+    rowtile_nn<NK>(o, f, sv, ld, d0, dh, lane);
+    store_chunk(o, out, (long long)p.D, m0, N, d0, dh, g, t);
+  }
+}
+
+// kSplit: warps [0, NK) own the query-row half (dQ), warps [NK, 2 NK) the key-row half (dK, dV); otherwise every warp
+// does both in turn.
+template <int NPAD, bool kSplit>
+__global__ void __launch_bounds__(NPAD * (kSplit ? 4 : 2)) attn_mma_bwd_kernel(const GAttnParams p) {
+  constexpr int NT8 = NPAD / 8, NK = NPAD / 16;
+  extern __shared__ __align__(16) uint8_t smem_g[];
+  const int N = p.N, dh = p.dh, ld = dh + 8;
+  __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smem_g);
+  __nv_bfloat16* sk = sq + NPAD * ld;
+  __nv_bfloat16* sv = sk + NPAD * ld;
+  __nv_bfloat16* sdo = sv + NPAD * ld;
+  float* slse = reinterpret_cast<float*>(sdo + NPAD * ld);     // [NPAD] lse * log2e
+  float* sdelta = slse + NPAD;                                 // [NPAD] rowsum(dO * O)
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const __nv_bfloat16* base = p.qkv + (long long)b * N * 3 * p.D + h * dh;
+  load_rows_pad(sq, ld, base, 3ll * p.D, N, NPAD, dh);
+  load_rows_pad(sk, ld, base + p.D, 3ll * p.D, N, NPAD, dh);
+  load_rows_pad(sv, ld, base + 2 * p.D, 3ll * p.D, N, NPAD, dh);
+  load_rows_pad(sdo, ld, p.dout + (long long)b * N * p.D + h * dh, (long long)p.D, N, NPAD, dh);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  __syncthreads();
+  for (int q = warp; q < NPAD; q += nwarps) {
+    float dl = 0.f;
+    if (q < N) {
+      const __nv_bfloat16* orow = p.o + (long long)(b * N + q) * p.D + h * dh;
+      for (int d = 2 * lane; d < dh; d += 64) {
+        const uint32_t x = lds32(sdo + q * ld + d), y = __ldg(reinterpret_cast<const uint32_t*>(orow + d));
+        dl = fmaf(ptx::bf16_lo(x), ptx::bf16_lo(y), dl);
+        dl = fmaf(ptx::bf16_hi(x), ptx::bf16_hi(y), dl);
+      }
+      dl = warp_sum(dl);
+    }
+    if (lane == 0) {
+      sdelta[q] = dl;
+      slse[q] = q < N ? p.lse[((long long)b * p.H + h) * N + q] * kLog2eG : 0.f;
+    }
+  }
+  __syncthreads();
+  const int g = lane >> 2, t = lane & 3;
+  const int tile = kSplit ? warp % NK : warp, m0 = tile * 16;
+  const float sl2 = p.scale * kLog2eG;
+  const bool drop = p.drop_p > 0.f;
+  const DropKey dkey = drop_key(p.drop_seed, p.drop_p, p.drop_epoch);
+  const uint32_t thr_hi = dkey.thr16 << 16;
+  const unsigned long long groups = (unsigned long long)((N + 15) >> 4);
+  const unsigned long long bh_rows = (unsigned long long)(b * p.H + h) * N;
+  __nv_bfloat16* dq_out = p.dqkv + (long long)b * N * 3 * p.D + h * dh;
+  for (int role = kSplit ? warp / NK : 0; role < 2; role += kSplit ? 2 : 1) {
+    if (role == 0) {
+      // query rows m0 .. m0+15: dS[q][j] = P (dP' - delta_q) scale,  dQ = dS K
+      float s[NT8][4], dp[NT8][4];
+      rowtile_nt<NT8>(s, sq, sk, m0, ld, dh, g, t);
+      rowtile_nt<NT8>(dp, sdo, sv, m0, ld, dh, g, t);
+      const float l0 = slse[m0 + g], l1 = slse[m0 + g + 8], de0 = sdelta[m0 + g], de1 = sdelta[m0 + g + 8];
+      uint32_t mul[4], add[4];
+      if (drop) {
+        lcg_at(2 * t, mul[0], add[0]); lcg_at(2 * t + 1, mul[1], add[1]);
+        lcg_at(2 * t + 8, mul[2], add[2]); lcg_at(2 * t + 9, mul[3], add[3]);
+      }
+      const unsigned long long row0 = (bh_rows + (unsigned long long)(m0 + g)) * groups;
+      uint32_t fds[NK][4];
+#pragma unroll
+      for (int kt = 0; kt < NK; ++kt) {
+        uint32_t h0 = 0u, h1 = 0u;
+        if (drop) { h0 = drop_hash2(dkey, row0 + kt); h1 = drop_hash2(dkey, row0 + 8 * groups + kt); }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int nt = 2 * kt + half;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = nt * 8 + 2 * t + (e & 1);
+            const float pr = j < N ? exp2f(s[nt][e] * sl2 - ((e >> 1) ? l1 : l0)) : 0.f;
+            float d = dp[nt][e];
+            if (drop) {
+              const int ci = half * 2 + (e & 1);
+              const uint32_t x = ((e >> 1) ? h1 : h0) * mul[ci] + add[ci];
+              d = (x >= thr_hi) ? d * dkey.inv_keep : 0.f;
+            }
+            s[nt][e] = pr * (d - ((e >> 1) ? de1 : de0)) * p.scale;
+          }
+        }
+        fds[kt][0] = ptx::pack_bf16(s[2 * kt][0], s[2 * kt][1]); fds[kt][1] = ptx::pack_bf16(s[2 * kt][2], s[2 * kt][3]);
+        fds[kt][2] = ptx::pack_bf16(s[2 * kt + 1][0], s[2 * kt + 1][1]); fds[kt][3] = ptx::pack_bf16(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+      }
+      for (int d0 = 0; d0 < dh; d0 += 64) {
+        float acc[8][4];
+        rowtile_nn<NK>(acc, fds, sk, ld, d0, dh, lane);
+        store_chunk(acc, dq_out, 3ll * p.D, m0, N, d0, dh, g, t);
+      }
+    } else {
+      // key rows m0 .. m0+15 of the transposed tiles: S^T = K Q^T, dP^T = V dO^T;  dV = Pd^T dO,  dK = dS^T Q
+      float s[NT8][4], dp[NT8][4];
+      rowtile_nt<NT8>(s, sk, sq, m0, ld, dh, g, t);
+      rowtile_nt<NT8>(dp, sv, sdo, m0, ld, dh, g, t);
+      uint32_t mul[2], add[2];
+      if (drop) { lcg_at(g, mul[0], add[0]); lcg_at(g + 8, mul[1], add[1]); }
+      uint32_t fp[NK][4], fds[NK][4];
+#pragma unroll
+      for (int kt = 0; kt < NK; ++kt) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int nt = 2 * kt + half;
+          float pd[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int q = nt * 8 + 2 * t + (e & 1);
+            const float pr = q < N ? exp2f(s[nt][e] * sl2 - slse[q]) : 0.f;
+            float d = dp[nt][e];
+            pd[e] = pr;
+            if (drop) {
+              const uint32_t hq = drop_hash2(dkey, (bh_rows + (unsigned long long)q) * groups + tile);
+              const uint32_t x = hq * mul[e >> 1] + add[e >> 1];
+              const bool keep = x >= thr_hi;
+              pd[e] = keep ? pr * dkey.inv_keep : 0.f;
+              d = keep ? d * dkey.inv_keep : 0.f;
+            }
+            s[nt][e] = pr * (d - sdelta[q]) * p.scale;
+          }
+          fp[kt][2 * half] = ptx::pack_bf16(pd[0], pd[1]);
+          fp[kt][2 * half + 1] = ptx::pack_bf16(pd[2], pd[3]);
+        }
+        fds[kt][0] = ptx::pack_bf16(s[2 * kt][0], s[2 * kt][1]); fds[kt][1] = ptx::pack_bf16(s[2 * kt][2], s[2 * kt][3]);
+        fds[kt][2] = ptx::pack_bf16(s[2 * kt + 1][0], s[2 * kt + 1][1]); fds[kt][3] = ptx::pack_bf16(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+      }
+      for (int d0 = 0; d0 < dh; d0 += 64) {
+        float acc[8][4];
+        rowtile_nn<NK>(acc, fp, sdo, ld, d0, dh, lane);
+        store_chunk(acc, dq_out + 2 * p.D, 3ll * p.D, m0, N, d0, dh, g, t);
+        rowtile_nn<NK>(acc, fds, sq, ld, d0, dh, lane);
+        store_chunk(acc, dq_out + p.D, 3ll * p.D, m0, N, d0, dh, g, t);
+      }
+    }
+  }
+}
+
+int mma_npad(int N) { return N <= 16 ? 16 : N <= 32 ? 32 : N <= 64 ? 64 : N <= 96 ? 96 : 128; }
+size_t mma_smem_bytes(int N, int dh, bool bwd) {
+  const int npad = mma_npad(N);
+  return (size_t)(bwd ? 4 : 3) * npad * (dh + 8) * 2 + (bwd ? 2 * npad * 4 : 0);
+}
+// the CUDA-core kernels stay for head_dim % 16 == 8 and as the A/B comparator (SFC_ATTN_NO_MMA=1)
+bool mma_path(int N, int dh, bool bwd) {
+  const char* e = getenv("SFC_ATTN_NO_MMA");       // read per call: the tests flip it to compare the two paths
+  const bool off = e && e[0] == '1';
+  return !off && dh % 16 == 0 && N >= 1 && N <= 128 && mma_smem_bytes(N, dh, bwd) <= 220 * 1024;
+}
+
+template <int NPAD>
+int launch_mma_fwd(const GAttnParams& p, size_t smem, cudaStream_t stream) {
+  SFC_CUDA_OK(cudaFuncSetAttribute(attn_mma_fwd_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  attn_mma_fwd_kernel<NPAD><<<p.B * p.H, NPAD * 2, smem, stream>>>(p);
+  SFC_LAUNCH_OK();
+  return 0;
+}
+template <int NPAD, bool kSplit>
+int launch_mma_bwd(const GAttnParams& p, size_t smem, cudaStream_t stream) {
+  SFC_CUDA_OK(cudaFuncSetAttribute(attn_mma_bwd_kernel<NPAD, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  attn_mma_bwd_kernel<NPAD, kSplit><<<p.B * p.H, NPAD * (kSplit ? 4 : 2), smem, stream>>>(p);
+  SFC_LAUNCH_OK();
+  return 0;
+}
+
 }  // namespace
 
 // Shapes served by this path: head_dim % 8 == 0, N <= 128 and the (image, head) working set within shared memory.
 int sfc_attn_generic_supported(int N, int dh, bool bwd) {
   if (dh % 8 != 0 || dh < 8 || N < 1 || N > 32 * kMaxKeysPerLane) return 0;
+  if (mma_path(N, dh, bwd)) return 1;
   const size_t bytes = (size_t)(bwd ? 4 : 3) * N * (dh + 2) * 2 + (bwd ? 2 * N * 4 : 0);
   return bytes <= 220 * 1024;
 }
@@ -242,6 +596,16 @@ int sfc_attn_generic_fwd(const void* qkv, void* out, float* lse, int B, int H, i
   p.B = B; p.H = H; p.N = N; p.D = D; p.dh = dh; p.scale = scale; p.drop_p = drop_p; p.drop_seed = drop_seed;
   p.drop_epoch = sfc_dropout_epoch_ptr();
   p.qkv = (const __nv_bfloat16*)qkv; p.out = (__nv_bfloat16*)out; p.lse = lse;
+  if (mma_path(N, dh, false)) {
+    const size_t bytes = mma_smem_bytes(N, dh, false);
+    switch (mma_npad(N)) {
+      case 16: return launch_mma_fwd<16>(p, bytes, stream);
+      case 32: return launch_mma_fwd<32>(p, bytes, stream);
+      case 64: return launch_mma_fwd<64>(p, bytes, stream);
+      case 96: return launch_mma_fwd<96>(p, bytes, stream);
+      default: return launch_mma_fwd<128>(p, bytes, stream);
+    }
+  }
   const int smem = 3 * N * (dh + 2) * 2;
   SFC_CUDA_OK(cudaFuncSetAttribute(attn_generic_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   attn_generic_fwd_kernel<<<B * H, kGThreads, smem, stream>>>(p);
@@ -257,6 +621,16 @@ int sfc_attn_generic_bwd(const void* qkv, const void* out, const void* dout, con
   p.drop_epoch = sfc_dropout_epoch_ptr();
   p.qkv = (const __nv_bfloat16*)qkv; p.o = (const __nv_bfloat16*)out; p.dout = (const __nv_bfloat16*)dout;
   p.lse = const_cast<float*>(lse); p.dqkv = (__nv_bfloat16*)dqkv;
+  if (mma_path(N, dh, true)) {
+    const size_t bytes = mma_smem_bytes(N, dh, true);
+    switch (mma_npad(N)) {
+      case 16: return launch_mma_bwd<16, true>(p, bytes, stream);
+      case 32: return launch_mma_bwd<32, true>(p, bytes, stream);
+      case 64: return launch_mma_bwd<64, true>(p, bytes, stream);
+      case 96: return launch_mma_bwd<96, false>(p, bytes, stream);
+      default: return launch_mma_bwd<128, false>(p, bytes, stream);
+    }
+  }
   const int smem = 4 * N * (dh + 2) * 2 + 2 * N * 4;
   SFC_CUDA_OK(cudaFuncSetAttribute(attn_generic_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   attn_generic_bwd_kernel<<<B * H, kGThreads, smem, stream>>>(p);

@@ -78,11 +78,15 @@ def test_fused_clip_adamw_matches_torch(cuda_device):
     assert r["ok"], r
 
 
-@pytest.mark.parametrize("B,H,N,dh,drop", [(2, 4, 64, 192, 0.0), (3, 2, 50, 32, 0.0), (1, 3, 128, 96, 0.0), (2, 4, 64, 192, 0.1)])
-def test_attention_generic_head_dim(cuda_device, B, H, N, dh, drop):
-    """head_dim != 64 (main.py builds 768 / 4 heads = 192 on 64 tokens): CUDA-core path of attention_generic.cu."""
+@pytest.mark.parametrize("mma", [True, False])
+@pytest.mark.parametrize("B,H,N,dh,drop", [(2, 4, 64, 192, 0.0), (3, 2, 50, 32, 0.0), (1, 3, 128, 96, 0.0), (2, 4, 64, 192, 0.1),
+                                           (2, 2, 17, 16, 0.0), (1, 2, 100, 48, 0.0), (2, 1, 9, 128, 0.0), (1, 2, 40, 24, 0.0)])
+def test_attention_generic_head_dim(cuda_device, monkeypatch, mma, B, H, N, dh, drop):
+    """head_dim != 64 (main.py builds 768 / 4 heads = 192 on 64 tokens): attention_generic.cu — the warp-MMA kernels
+    (head_dim % 16 == 0) and the CUDA-core kernels (any head_dim % 8 == 0; forced with SFC_ATTN_NO_MMA=1)."""
     import torch
     from sfcvit import ops
+    monkeypatch.setenv("SFC_ATTN_NO_MMA", "0" if mma else "1")
     g = torch.Generator(device="cuda").manual_seed(3)
     D = H * dh
     qkv = torch.randn(B * N, 3 * D, generator=g, device="cuda").bfloat16()
@@ -110,6 +114,29 @@ def test_attention_generic_head_dim(cuda_device, B, H, N, dh, drop):
         lhs = float((out_dir.float() * dout.float()).sum()); rhs = float((dqkv[:, 2 * D:].float() * vdir.float()).sum())
         assert abs(lhs - rhs) / max(abs(lhs), 1e-6) < 3e-2
         assert torch.isfinite(dqkv.float()).all()
+
+
+@pytest.mark.parametrize("B,H,N,dh", [(2, 4, 64, 192), (1, 2, 100, 48), (2, 2, 128, 32), (3, 1, 23, 16)])
+def test_attention_generic_paths_share_the_dropout_mask(cuda_device, monkeypatch, B, H, N, dh):
+    """With dropout the warp-MMA and the CUDA-core kernels must draw the SAME mask (one counter-based definition,
+    indexed by (image, head, query, key)): outputs and all three gradients agree to bf16 rounding; a different mask
+    would differ by O(1)."""
+    import torch
+    from sfcvit import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    D = H * dh
+    qkv = torch.randn(B * N, 3 * D, generator=g, device="cuda").bfloat16()
+    dout = torch.randn(B * N, D, generator=g, device="cuda").bfloat16()
+    res = {}
+    for mma in ("0", "1"):
+        monkeypatch.setenv("SFC_ATTN_NO_MMA", mma)
+        out, lse = ops.attn_fwd(qkv, B, H, N, drop_p=0.25, drop_seed=99)
+        res[mma] = (out, lse, ops.attn_bwd(qkv, out, dout, lse, B, H, N, drop_p=0.25, drop_seed=99))
+    rel = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm())
+    assert rel(res["0"][0], res["1"][0]) < 1e-2
+    assert (res["0"][1] - res["1"][1]).abs().max() < 1e-4
+    for i, name in enumerate("qkv"):
+        assert rel(res["0"][2][:, i * D:(i + 1) * D], res["1"][2][:, i * D:(i + 1) * D]) < 2e-2, name
 
 
 # K7: token-axis linear resampling into a concat slice vs torch (F.interpolate(mode="linear", align_corners=False) on the
