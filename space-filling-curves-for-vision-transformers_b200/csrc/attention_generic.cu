@@ -249,35 +249,50 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t& r0, uint32_t& r1, uint32
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                : "r"(addr));
 }
-__device__ __forceinline__ uint32_t lds32(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+__device__ __forceinline__ void ldsm_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void cp_async16(const __nv_bfloat16* dst, const __nv_bfloat16* src, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(ptx::smem_u32(dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(kPending) : "memory"); }
 
-// rows [0, N) x dh of a strided matrix -> smem [NPAD][ld] (16-byte stores), rows N.. zero
-__device__ __forceinline__ void load_rows_pad(__nv_bfloat16* dst, int ld, const __nv_bfloat16* src, long long row_stride, int N,
-                                              int npad, int dh) {
+// Visits the 16-byte pieces (row r, column c) of an [npad][dh] tile, one per thread and step; the callers issue their
+// cp.async copies from it (no register staging: every copy of a tile is in flight at once; rows >= N are zero-filled
+// through src-size 0 and read nothing).
+template <typename F>
+__device__ __forceinline__ void for_each_piece(int npad, int dh, F&& f) {
   const int vec_per_row = dh / 8;
   for (int i = threadIdx.x; i < npad * vec_per_row; i += blockDim.x) {
-    const int r = i / vec_per_row, c = (i % vec_per_row) * 8;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (r < N) v = __ldg(reinterpret_cast<const uint4*>(src + (long long)r * row_stride + c));
-    *reinterpret_cast<uint4*>(dst + r * ld + c) = v;
+    const int r = i / vec_per_row;
+    f(r, (i - r * vec_per_row) * 8);
   }
 }
 
-// acc[nt] = X[m0 .. m0+15][0:dh] . Y[nt*8 .. nt*8+7][0:dh]^T
+// acc[nt] = X[m0 .. m0+15][0:dh] . Y[nt*8 .. nt*8+7][0:dh]^T; one ldmatrix.x4 per A fragment and per pair of n-tiles
 template <int NT8>
 __device__ __forceinline__ void rowtile_nt(float (&acc)[NT8][4], const __nv_bfloat16* X, const __nv_bfloat16* Y, int m0, int ld,
-                                           int dh, int g, int t) {
+                                           int dh, int lane) {
+  static_assert(NT8 % 2 == 0, "n-tiles are fetched in pairs");
 #pragma unroll
   for (int nt = 0; nt < NT8; ++nt) { acc[nt][0] = 0.f; acc[nt][1] = 0.f; acc[nt][2] = 0.f; acc[nt][3] = 0.f; }
-  const __nv_bfloat16* xa = X + (m0 + g) * ld + 2 * t;
-  const __nv_bfloat16* yb = Y + g * ld + 2 * t;
+  // A: matrices (rows +0, k +0), (rows +8, k +0), (rows +0, k +8), (rows +8, k +8) = a0..a3
+  const uint32_t xaddr = ptx::smem_u32(X + (m0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ld + (lane >> 4) * 8);
+  // B: matrices (n +0, k +0), (n +0, k +8), (n +8, k +0), (n +8, k +8) = b0, b1 of n-tile 2 np and of n-tile 2 np + 1
+  const uint32_t yaddr = ptx::smem_u32(Y + ((lane & 7) + (lane >> 4) * 8) * ld + ((lane >> 3) & 1) * 8);
   for (int k0 = 0; k0 < dh; k0 += 16) {
     uint32_t a[4];
-    a[0] = lds32(xa + k0); a[1] = lds32(xa + 8 * ld + k0); a[2] = lds32(xa + k0 + 8); a[3] = lds32(xa + 8 * ld + k0 + 8);
+    ldsm_x4(a[0], a[1], a[2], a[3], xaddr + (uint32_t)(k0 * 2));
 #pragma unroll
-    for (int nt = 0; nt < NT8; ++nt) {
-      const uint32_t b0 = lds32(yb + nt * 8 * ld + k0), b1 = lds32(yb + nt * 8 * ld + k0 + 8);
-      mma16816(acc[nt], a, b0, b1);
+    for (int np = 0; np < NT8 / 2; ++np) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4(b0, b1, b2, b3, yaddr + (uint32_t)((np * 16 * ld + k0) * 2));
+      mma16816(acc[2 * np], a, b0, b1);
+      mma16816(acc[2 * np + 1], a, b2, b3);
     }
   }
 }
@@ -289,11 +304,12 @@ __device__ __forceinline__ void rowtile_nn(float (&acc)[8][4], const uint32_t (&
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = 0.f; acc[nt][1] = 0.f; acc[nt][2] = 0.f; acc[nt][3] = 0.f; }
   const uint32_t zaddr = ptx::smem_u32(Z + (lane & 15) * ld + d0 + (lane >> 4) * 8);
+  const int npairs = min(4, (dh - d0) >> 4);
 #pragma unroll
   for (int kt = 0; kt < NK; ++kt) {
 #pragma unroll
     for (int np = 0; np < 4; ++np) {
-      if (d0 + np * 16 < dh) {
+      if (np < npairs) {
         uint32_t r0, r1, r2, r3;
         ldsm_x4_trans(r0, r1, r2, r3, zaddr + (uint32_t)((kt * 16 * ld + np * 16) * 2));
         mma16816(acc[2 * np], f[kt], r0, r1);
@@ -307,12 +323,14 @@ __device__ __forceinline__ void rowtile_nn(float (&acc)[8][4], const uint32_t (&
 __device__ __forceinline__ void store_chunk(const float (&acc)[8][4], __nv_bfloat16* dst, long long row_stride, int m0, int N,
                                             int d0, int dh, int g, int t) {
   const int r0 = m0 + g, r1 = r0 + 8;
+  __nv_bfloat16* p0 = dst + r0 * row_stride + d0 + 2 * t;
+  __nv_bfloat16* p1 = p0 + 8 * row_stride;
+  const int ntiles = min(8, (dh - d0) >> 3);
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
-    const int col = d0 + nt * 8 + 2 * t;
-    if (col < dh) {
-      if (r0 < N) *reinterpret_cast<uint32_t*>(dst + r0 * row_stride + col) = ptx::pack_bf16(acc[nt][0], acc[nt][1]);
-      if (r1 < N) *reinterpret_cast<uint32_t*>(dst + r1 * row_stride + col) = ptx::pack_bf16(acc[nt][2], acc[nt][3]);
+    if (nt < ntiles) {
+      if (r0 < N) *reinterpret_cast<uint32_t*>(p0 + nt * 8) = ptx::pack_bf16(acc[nt][0], acc[nt][1]);
+      if (r1 < N) *reinterpret_cast<uint32_t*>(p1 + nt * 8) = ptx::pack_bf16(acc[nt][2], acc[nt][3]);
     }
   }
 }
@@ -342,14 +360,24 @@ __global__ void __launch_bounds__(NPAD * 2) attn_mma_fwd_kernel(const GAttnParam
   __nv_bfloat16* sv = sk + NPAD * ld;
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
   const __nv_bfloat16* base = p.qkv + (long long)b * N * 3 * p.D + h * dh;
-  load_rows_pad(sq, ld, base, 3ll * p.D, N, NPAD, dh);
-  load_rows_pad(sk, ld, base + p.D, 3ll * p.D, N, NPAD, dh);
-  load_rows_pad(sv, ld, base + 2 * p.D, 3ll * p.D, N, NPAD, dh);
+  for_each_piece(NPAD, dh, [&](int r, int c) {
+    const bool valid = r < N;
+    const __nv_bfloat16* src = valid ? base + (long long)r * 3 * p.D + c : base;
+    cp_async16(sq + r * ld + c, src, valid);
+    cp_async16(sk + r * ld + c, src + p.D, valid);
+  });
+  cp_async_commit();
+  for_each_piece(NPAD, dh, [&](int r, int c) {                           // V lands under the score tile
+    const bool valid = r < N;
+    cp_async16(sv + r * ld + c, valid ? base + (long long)r * 3 * p.D + 2 * p.D + c : base, valid);
+  });
+  cp_async_commit();
+  cp_async_wait<1>();
   __syncthreads();
   const int lane = threadIdx.x & 31, m0 = (threadIdx.x >> 5) * 16, g = lane >> 2, t = lane & 3;
   const float sl2 = p.scale * kLog2eG;
   float s[NT8][4];
-  rowtile_nt<NT8>(s, sq, sk, m0, ld, dh, g, t);
+  rowtile_nt<NT8>(s, sq, sk, m0, ld, dh, lane);
   float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
   for (int nt = 0; nt < NT8; ++nt) {
@@ -409,6 +437,8 @@ __global__ void __launch_bounds__(NPAD * 2) attn_mma_fwd_kernel(const GAttnParam
     f[kt][0] = ptx::pack_bf16(s[2 * kt][0], s[2 * kt][1]); f[kt][1] = ptx::pack_bf16(s[2 * kt][2], s[2 * kt][3]);
     f[kt][2] = ptx::pack_bf16(s[2 * kt + 1][0], s[2 * kt + 1][1]); f[kt][3] = ptx::pack_bf16(s[2 * kt + 1][2], s[2 * kt + 1][3]);
   }
+  cp_async_wait<0>();
+  __syncthreads();
   __nv_bfloat16* out = p.out + (long long)b * N * p.D + h * dh;
   for (int d0 = 0; d0 < dh; d0 += 64) {
     float o[8][4];
@@ -432,28 +462,43 @@ __global__ void __launch_bounds__(NPAD * (kSplit ? 4 : 2)) attn_mma_bwd_kernel(c
   float* sdelta = slse + NPAD;                                 // [NPAD] rowsum(dO * O)
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
   const __nv_bfloat16* base = p.qkv + (long long)b * N * 3 * p.D + h * dh;
-  load_rows_pad(sq, ld, base, 3ll * p.D, N, NPAD, dh);
-  load_rows_pad(sk, ld, base + p.D, 3ll * p.D, N, NPAD, dh);
-  load_rows_pad(sv, ld, base + 2 * p.D, 3ll * p.D, N, NPAD, dh);
-  load_rows_pad(sdo, ld, p.dout + (long long)b * N * p.D + h * dh, (long long)p.D, N, NPAD, dh);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  __syncthreads();
-  for (int q = warp; q < NPAD; q += nwarps) {
+  const __nv_bfloat16* dobase = p.dout + (long long)b * N * p.D + h * dh;
+  for_each_piece(NPAD, dh, [&](int r, int c) {
+    const bool valid = r < N;
+    const __nv_bfloat16* src = valid ? base + (long long)r * 3 * p.D + c : base;
+    cp_async16(sq + r * ld + c, src, valid);
+    cp_async16(sk + r * ld + c, src + p.D, valid);
+    cp_async16(sv + r * ld + c, src + 2 * p.D, valid);
+    cp_async16(sdo + r * ld + c, valid ? dobase + (long long)r * p.D + c : dobase, valid);
+  });
+  cp_async_commit();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  {
+    // delta[q] = sum_d dO[q][d] O[q][d] from global memory while the tiles are in flight: kRowThreads adjacent lanes per
+    // row, 16-byte loads issued ahead of their use
+    constexpr int kRowThreads = kSplit ? 4 : 2;                 // blockDim.x / NPAD
+    const int q = threadIdx.x / kRowThreads, sub = threadIdx.x % kRowThreads;
     float dl = 0.f;
     if (q < N) {
-      const __nv_bfloat16* orow = p.o + (long long)(b * N + q) * p.D + h * dh;
-      for (int d = 2 * lane; d < dh; d += 64) {
-        const uint32_t x = lds32(sdo + q * ld + d), y = __ldg(reinterpret_cast<const uint32_t*>(orow + d));
-        dl = fmaf(ptx::bf16_lo(x), ptx::bf16_lo(y), dl);
-        dl = fmaf(ptx::bf16_hi(x), ptx::bf16_hi(y), dl);
+      const uint4* orow = reinterpret_cast<const uint4*>(p.o + (long long)(b * N + q) * p.D + h * dh);
+      const uint4* dorow = reinterpret_cast<const uint4*>(dobase + (long long)q * p.D);
+#pragma unroll 4
+      for (int c = sub; c < dh / 8; c += kRowThreads) {
+        const uint4 x = __ldg(dorow + c), y = __ldg(orow + c);
+        dl = fmaf(ptx::bf16_lo(x.x), ptx::bf16_lo(y.x), dl); dl = fmaf(ptx::bf16_hi(x.x), ptx::bf16_hi(y.x), dl);
+        dl = fmaf(ptx::bf16_lo(x.y), ptx::bf16_lo(y.y), dl); dl = fmaf(ptx::bf16_hi(x.y), ptx::bf16_hi(y.y), dl);
+        dl = fmaf(ptx::bf16_lo(x.z), ptx::bf16_lo(y.z), dl); dl = fmaf(ptx::bf16_hi(x.z), ptx::bf16_hi(y.z), dl);
+        dl = fmaf(ptx::bf16_lo(x.w), ptx::bf16_lo(y.w), dl); dl = fmaf(ptx::bf16_hi(x.w), ptx::bf16_hi(y.w), dl);
       }
-      dl = warp_sum(dl);
     }
-    if (lane == 0) {
+#pragma unroll
+    for (int o = kRowThreads / 2; o > 0; o >>= 1) dl += __shfl_xor_sync(0xffffffffu, dl, o);
+    if (sub == 0) {
       sdelta[q] = dl;
       slse[q] = q < N ? p.lse[((long long)b * p.H + h) * N + q] * kLog2eG : 0.f;
     }
   }
+  cp_async_wait<0>();
   __syncthreads();
   const int g = lane >> 2, t = lane & 3;
   const int tile = kSplit ? warp % NK : warp, m0 = tile * 16;
@@ -468,8 +513,8 @@ __global__ void __launch_bounds__(NPAD * (kSplit ? 4 : 2)) attn_mma_bwd_kernel(c
     if (role == 0) {
       // query rows m0 .. m0+15: dS[q][j] = P (dP' - delta_q) scale,  dQ = dS K
       float s[NT8][4], dp[NT8][4];
-      rowtile_nt<NT8>(s, sq, sk, m0, ld, dh, g, t);
-      rowtile_nt<NT8>(dp, sdo, sv, m0, ld, dh, g, t);
+      rowtile_nt<NT8>(s, sq, sk, m0, ld, dh, lane);
+      rowtile_nt<NT8>(dp, sdo, sv, m0, ld, dh, lane);
       const float l0 = slse[m0 + g], l1 = slse[m0 + g + 8], de0 = sdelta[m0 + g], de1 = sdelta[m0 + g + 8];
       uint32_t mul[4], add[4];
       if (drop) {
@@ -509,8 +554,8 @@ __global__ void __launch_bounds__(NPAD * (kSplit ? 4 : 2)) attn_mma_bwd_kernel(c
     } else {
       // key rows m0 .. m0+15 of the transposed tiles: S^T = K Q^T, dP^T = V dO^T;  dV = Pd^T dO,  dK = dS^T Q
       float s[NT8][4], dp[NT8][4];
-      rowtile_nt<NT8>(s, sk, sq, m0, ld, dh, g, t);
-      rowtile_nt<NT8>(dp, sv, sdo, m0, ld, dh, g, t);
+      rowtile_nt<NT8>(s, sk, sq, m0, ld, dh, lane);
+      rowtile_nt<NT8>(dp, sv, sdo, m0, ld, dh, lane);
       uint32_t mul[2], add[2];
       if (drop) { lcg_at(g, mul[0], add[0]); lcg_at(g + 8, mul[1], add[1]); }
       uint32_t fp[NK][4], fds[NK][4];
