@@ -1,10 +1,11 @@
-// K4g — generic-head-dimension attention (CUDA cores), forward and backward.
+// K4g — generic-head-dimension attention, forward and backward: warp-MMA kernels (head_dim % 16 == 0, second half of
+// this file) and the CUDA-core kernels they replaced (any head_dim % 8 == 0; comparator).
 //
 // The tcgen05 kernels of attention.cu are specialised for head_dim = 64 (every BASELINE.json model). The reference's own
 // driver, however, builds VisionTransformer1D(embed 3 x 256 = 768, n_heads = 4) -> head_dim 192 on 64 tokens
 // (/root/reference/main.py:269-282), so "main.py drives it unchanged" needs an attention for other head dimensions.
-// Those shapes are small (N <= 128 tokens), so this path keeps one (image, head) per CTA entirely in shared memory and
-// uses warp-per-row FMA code: same packed qkv layout, same lse output, same counter-based dropout as attention.cu.
+// Those shapes are small (N <= 128 tokens), so this path keeps one (image, head) per CTA entirely in shared memory:
+// same packed qkv layout, same lse output, same counter-based dropout as attention.cu. CUDA-core kernels (warp per row):
 //   forward : warp per query row: scores over keys (lanes = keys), softmax by shuffles, O = P V (lanes = features)
 //   backward: pass 1, warp per query row -> dQ;  pass 2, warp per key row -> dK, dV (P recomputed from lse; no atomics)
 #include "common.cuh"
