@@ -250,6 +250,11 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t& r0, uint32_t& r1, uint32
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                : "r"(addr));
 }
+__device__ __forceinline__ float ex2_fast(float x) {            // ex2.approx.ftz: 2^-inf = +0, no denormal rescaling code
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void ldsm_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
@@ -393,8 +398,8 @@ __global__ void __launch_bounds__(NPAD * 2) attn_mma_fwd_kernel(const GAttnParam
   float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
   for (int nt = 0; nt < NT8; ++nt) {
-    s[nt][0] = exp2f((s[nt][0] - mx0) * sl2); s[nt][1] = exp2f((s[nt][1] - mx0) * sl2);
-    s[nt][2] = exp2f((s[nt][2] - mx1) * sl2); s[nt][3] = exp2f((s[nt][3] - mx1) * sl2);
+    s[nt][0] = ex2_fast((s[nt][0] - mx0) * sl2); s[nt][1] = ex2_fast((s[nt][1] - mx0) * sl2);
+    s[nt][2] = ex2_fast((s[nt][2] - mx1) * sl2); s[nt][3] = ex2_fast((s[nt][3] - mx1) * sl2);
     sum0 += s[nt][0] + s[nt][1];
     sum1 += s[nt][2] + s[nt][3];
   }
@@ -534,7 +539,7 @@ __global__ void __launch_bounds__(NPAD * (kSplit ? 4 : 2)) attn_mma_bwd_kernel(c
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = nt * 8 + 2 * t + (e & 1);
-            const float pr = j < N ? exp2f(s[nt][e] * sl2 - ((e >> 1) ? l1 : l0)) : 0.f;
+            const float pr = j < N ? ex2_fast(fmaf(s[nt][e], sl2, -((e >> 1) ? l1 : l0))) : 0.f;
             float d = dp[nt][e];
             if (drop) {
               const int ci = half * 2 + (e & 1);
@@ -566,20 +571,27 @@ __global__ void __launch_bounds__(NPAD * (kSplit ? 4 : 2)) attn_mma_bwd_kernel(c
         for (int half = 0; half < 2; ++half) {
           const int nt = 2 * kt + half;
           float pd[4];
+          uint32_t hq[2] = {0u, 0u};
+          float lq[2], dq[2];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {                      // the two query columns this thread holds in the n-tile
+            const int q = nt * 8 + 2 * t + c;
+            lq[c] = slse[q]; dq[c] = sdelta[q];
+            if (drop) hq[c] = drop_hash2(dkey, (bh_rows + (unsigned long long)q) * groups + tile);
+          }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int q = nt * 8 + 2 * t + (e & 1);
-            const float pr = q < N ? exp2f(s[nt][e] * sl2 - slse[q]) : 0.f;
+            const float pr = q < N ? ex2_fast(fmaf(s[nt][e], sl2, -lq[e & 1])) : 0.f;
             float d = dp[nt][e];
             pd[e] = pr;
             if (drop) {
-              const uint32_t hq = drop_hash2(dkey, (bh_rows + (unsigned long long)q) * groups + tile);
-              const uint32_t x = hq * mul[e >> 1] + add[e >> 1];
+              const uint32_t x = hq[e & 1] * mul[e >> 1] + add[e >> 1];
               const bool keep = x >= thr_hi;
               pd[e] = keep ? pr * dkey.inv_keep : 0.f;
               d = keep ? d * dkey.inv_keep : 0.f;
             }
-            s[nt][e] = pr * (d - sdelta[q]) * p.scale;
+            s[nt][e] = pr * (d - dq[e & 1]) * p.scale;
           }
           fp[kt][2 * half] = ptx::pack_bf16(pd[0], pd[1]);
           fp[kt][2 * half + 1] = ptx::pack_bf16(pd[2], pd[3]);

@@ -35,6 +35,8 @@ struct PatchParams {
   const int* perm;       // [ntok * g] flat pre-patch index r*gw + c in curve order
   int B, C, H, W, p, g, gw;
   int in_fmt;            // SFC_IMG_F32_NCHW / SFC_IMG_BF16_NCHW / SFC_IMG_U8_NHWC
+  int row_split;         // p == 4 (NCHW): an 8-element chunk is two 4-element patch rows, the second `row_split` (= W)
+                         // elements after the first; 0 = the chunk is one contiguous run
   int ntok, K, Kpad;
   long long M;           // B * ntok
   int num_m_tiles, num_n_tiles, num_k_blocks;
@@ -78,13 +80,19 @@ constexpr int IN_F32 = 0, IN_BF16 = 1, IN_U8 = 2;
 struct ChunkRaw { uint4 a, b; };      // 8 consecutive K elements as loaded: fp32 a+b, bf16 a, uint8 a.x / a.y
 
 template <int IN>
-__device__ __forceinline__ void chunk_load(ChunkRaw& r, const void* img, long long off) {
+__device__ __forceinline__ void chunk_load(ChunkRaw& r, const void* img, long long off, int row_split = 0) {
   if constexpr (IN == IN_BF16) {
-    r.a = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(img) + off));
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(img) + off;
+    if (row_split == 0) {
+      r.a = __ldg(reinterpret_cast<const uint4*>(src));
+    } else {
+      const uint2 lo = __ldg(reinterpret_cast<const uint2*>(src)), hi = __ldg(reinterpret_cast<const uint2*>(src + row_split));
+      r.a = make_uint4(lo.x, lo.y, hi.x, hi.y);
+    }
   } else if constexpr (IN == IN_F32) {
-    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(img) + off);
-    r.a = __ldg(src);
-    r.b = __ldg(src + 1);
+    const float* src = reinterpret_cast<const float*>(img) + off;
+    r.a = __ldg(reinterpret_cast<const uint4*>(src));
+    r.b = __ldg(reinterpret_cast<const uint4*>(src + (row_split == 0 ? 4 : row_split)));
   } else {
     const uint2 v = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(img) + off));
     r.a.x = v.x; r.a.y = v.y;
@@ -160,7 +168,7 @@ __device__ __forceinline__ void gather_row_vec(const PatchParams& pp, bool row_o
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     off[j] = tbl[kb * 8 + j];                     // broadcast shared-memory read
-    if (row_ok && off[j] >= 0) chunk_load<IN>(raw[j], pp.img, origin + off[j]);
+    if (row_ok && off[j] >= 0) chunk_load<IN>(raw[j], pp.img, origin + off[j], pp.row_split);
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -656,7 +664,7 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const PatchParams pp,
     const int b = (int)(m / pp.ntok), t = (int)(m - (long long)b * pp.ntok);
     uint4 o = make_uint4(0, 0, 0, 0);
     if constexpr (VEC) {
-      // p % 8 == 0: the chunk is one contiguous run inside a patch row
+      // p % 8 == 0: the chunk is one contiguous run inside a patch row; p == 4: two consecutive patch rows (row_split)
       if (k0 < pp.K) {
         long long off;
         if constexpr (IN == IN_U8) {                  // K ordered (q, p1, p2, c), image NHWC
@@ -671,7 +679,7 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const PatchParams pp,
           off = ((long long)b * pp.C + c) * plane + (long long)(r * p + p1) * pp.W + cc * p + p2;
         }
         ChunkRaw raw;
-        chunk_load<IN>(raw, pp.img, off);
+        chunk_load<IN>(raw, pp.img, off, pp.row_split);
         o = chunk_pack<IN>(raw);
       }
     } else if constexpr (IN != IN_U8) {
@@ -695,12 +703,14 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const PatchParams pp,
   }
 }
 
-// vectorised gather: every 8-element K chunk is one contiguous, aligned run of the image
+// vectorised gather: every 8-element K chunk is one contiguous, aligned run of the image (p % 8 == 0) or — p == 4, NCHW —
+// two aligned 4-element patch rows one image row apart (a (q, c) plane is 16 elements, so a chunk never straddles two)
 bool pe_vec_ok(const void* img, int fmt, int C, int H, int W, int p) {
   if (fmt == SFC_IMG_U8_NHWC)
     return ((p * C) % 8 == 0) && ((p * p * C) % 64 == 0) && ((W * C) % 8 == 0) && ((reinterpret_cast<uintptr_t>(img) & 7) == 0) &&
            ((long long)H * W * C < (1ll << 31));
-  return (p % 8 == 0) && (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0) && (((long long)H * W) % 8 == 0) &&
+  const int unit = (p == 4) ? 4 : 8;
+  return (p % unit == 0) && (W % unit == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0) && (((long long)H * W) % unit == 0) &&
          ((long long)C * H * W < (1ll << 31));
 }
 
@@ -710,6 +720,7 @@ int fill_params(PatchParams& pp, const void* img, int img_bf16, int B, int C, in
   SFC_REQUIRE(img_bf16 == SFC_IMG_F32_NCHW || img_bf16 == SFC_IMG_BF16_NCHW || img_bf16 == SFC_IMG_U8_NHWC,
               "patch_embed: unknown image format %d", img_bf16);
   pp.in_fmt = img_bf16;
+  pp.row_split = (img_bf16 != SFC_IMG_U8_NHWC && p == 4) ? W : 0;
   SFC_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && p > 0 && g > 0 && D > 0, "patch_embed: bad shape");
   SFC_REQUIRE(H % p == 0 && W % p == 0, "patch_embed: image %dx%d not divisible by pre-patch size %d", H, W, p);
   const int gh = H / p, gw = W / p;
@@ -765,12 +776,13 @@ extern "C" int sfc_patch_embed_fwd(const void* img, int img_bf16, int B, int C, 
   e.alpha = 1.0f; e.act = SFC_ACT_NONE; e.aux_mode = SFC_AUX_NONE; e.out_fp32 = 0; e.drop_p = 0.f; e.drop_seed = 0; e.drop_epoch = nullptr;
   CUtensorMap tw;
   if (int err = sfc_make_tmap_2d(&tw, Wk, 2, (uint64_t)pp.Kpad, (uint64_t)D, (uint64_t)pp.Kpad * 2, BK, (uint32_t)BN, true)) return err;
-  const bool vec = pe_vec_ok(img, img_bf16, C, H, W, p) && pp.num_k_blocks <= kMaxTblKb;
+  // the fused kernels take one pre-patch origin per 64-element k-block: p == 4 (48 elements per pre-patch at C = 3) only for g == 1
+  const bool vec = pe_vec_ok(img, img_bf16, C, H, W, p) && pp.num_k_blocks <= kMaxTblKb && (pp.row_split == 0 || g == 1);
   const bool u8 = img_bf16 == SFC_IMG_U8_NHWC;
   SFC_REQUIRE(!u8 || vec, "sfc_patch_embed_fwd: uint8 NHWC input with K = %d exceeds the chunk table", pp.K);
   const bool fast = epi_fast_ok(pp.epi);
   static const bool tm_off = getenv("SFC_PE_NOTMEM") != nullptr;
-  if (vec && fast && !tm_off && pp.num_k_blocks <= kTmMaxKb && D % (2 * kTmBN) == 0 && D <= kTmMaxD) {
+  if (vec && pp.row_split == 0 && fast && !tm_off && pp.num_k_blocks <= kTmMaxKb && D % (2 * kTmBN) == 0 && D <= kTmMaxD) {
     // TMEM-resident A: gather once per token, 64-column passes over the weights
     pp.num_n_tiles = D / kTmBN;
     static const int cl = getenv("SFC_PE_CLUSTER") ? atoi(getenv("SFC_PE_CLUSTER")) : 4;

@@ -35,7 +35,10 @@ def test_attention_rejects_unsupported_shapes(cuda_device):
 @pytest.mark.parametrize("args", [(3, 3, 224, 16, 1, 768, "hilbert", "fp32"), (3, 3, 224, 16, 1, 384, "hilbert", "bf16"),
                                   (5, 3, 32, 4, 1, 192, "z", "fp32"), (5, 3, 32, 1, 16, 256, "hilbert", "fp32"),
                                   (5, 3, 32, 2, 4, 256, "peano", "fp32"), (2, 3, 64, 8, 2, 128, "moore", "bf16"),
-                                  (2, 3, 384, 16, 1, 1024, "peano", "fp32")])
+                                  (2, 3, 384, 16, 1, 1024, "peano", "fp32"),
+                                  # p == 4: 8-element chunks are two 4-element patch rows (vectorised half-row gather)
+                                  (6, 3, 32, 4, 1, 192, "hilbert", "bf16"), (3, 3, 64, 4, 4, 128, "hilbert", "fp32"),
+                                  (3, 1, 32, 4, 2, 128, "moore", "bf16"), (130, 3, 32, 4, 1, 256, "peano", "fp32")])
 def test_patch_embed(cuda_device, args):
     import kernel_selftest as ks
     r = ks.check_patch(*args)
