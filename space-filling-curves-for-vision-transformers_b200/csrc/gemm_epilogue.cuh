@@ -453,7 +453,7 @@ __device__ __forceinline__ void epi_tile_fast(const EpiParams& p, uint32_t taddr
 // ------------------------------------------------------------------------------------------------------------------
 template <class RowMap>
 __device__ __forceinline__ void epi_tile_direct(const EpiParams& p, uint32_t taddr, int n_begin, int ncols, long long m_base, long long M,
-                                                const RowMap& rm, int split, float* bias_s) {
+                                                const RowMap& rm, int split, float* bias_s, bool wide_st = false) {
   const int lane = (int)(threadIdx.x & 31);
   const bool has_res = p.residual != nullptr, has_aux = p.aux_mode != SFC_AUX_NONE;
   const bool has_drop = p.drop_p > 0.0f, f32 = p.out_fp32 != 0;
@@ -531,8 +531,13 @@ __device__ __forceinline__ void epi_tile_direct(const EpiParams& p, uint32_t tad
         for (int q = 0; q < 8; ++q) op[q] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
       } else {
         uint4* op = reinterpret_cast<uint4*>(outp + coff * 2);
+        if (wide_st) {                               // 256-bit stores: a full 32-byte sector per lane and instruction
+          ptx::stg256(op, epi_pack8(&v[0]), epi_pack8(&v[8]));
+          ptx::stg256(op + 2, epi_pack8(&v[16]), epi_pack8(&v[24]));
+        } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) op[q] = epi_pack8(&v[q * 8]);
+          for (int q = 0; q < 4; ++q) op[q] = epi_pack8(&v[q * 8]);
+        }
       }
     }
   }

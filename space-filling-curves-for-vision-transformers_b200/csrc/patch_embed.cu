@@ -35,6 +35,7 @@ struct PatchParams {
   const int* perm;       // [ntok * g] flat pre-patch index r*gw + c in curve order
   int B, C, H, W, p, g, gw;
   int in_fmt;            // SFC_IMG_F32_NCHW / SFC_IMG_BF16_NCHW / SFC_IMG_U8_NHWC
+  int wide_ld, wide_st;  // 256-bit accesses: fp32 chunk = one 32-byte load (image 32-byte aligned), output rows 32-byte aligned
   int row_split;         // p == 4 (NCHW): an 8-element chunk is two 4-element patch rows, the second `row_split` (= W)
                          // elements after the first; 0 = the chunk is one contiguous run
   int ntok, K, Kpad;
@@ -80,7 +81,7 @@ constexpr int IN_F32 = 0, IN_BF16 = 1, IN_U8 = 2;
 struct ChunkRaw { uint4 a, b; };      // 8 consecutive K elements as loaded: fp32 a+b, bf16 a, uint8 a.x / a.y
 
 template <int IN>
-__device__ __forceinline__ void chunk_load(ChunkRaw& r, const void* img, long long off, int row_split = 0) {
+__device__ __forceinline__ void chunk_load(ChunkRaw& r, const void* img, long long off, int row_split = 0, bool wide = false) {
   if constexpr (IN == IN_BF16) {
     const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(img) + off;
     if (row_split == 0) {
@@ -91,8 +92,12 @@ __device__ __forceinline__ void chunk_load(ChunkRaw& r, const void* img, long lo
     }
   } else if constexpr (IN == IN_F32) {
     const float* src = reinterpret_cast<const float*>(img) + off;
-    r.a = __ldg(reinterpret_cast<const uint4*>(src));
-    r.b = __ldg(reinterpret_cast<const uint4*>(src + (row_split == 0 ? 4 : row_split)));
+    if (wide) {                                  // warp-uniform: the 8 floats are one aligned 32-byte sector
+      ptx::ldg256(src, r.a, r.b);
+    } else {
+      r.a = __ldg(reinterpret_cast<const uint4*>(src));
+      r.b = __ldg(reinterpret_cast<const uint4*>(src + (row_split == 0 ? 4 : row_split)));
+    }
   } else {
     const uint2 v = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(img) + off));
     r.a.x = v.x; r.a.y = v.y;
@@ -168,7 +173,7 @@ __device__ __forceinline__ void gather_row_vec(const PatchParams& pp, bool row_o
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     off[j] = tbl[kb * 8 + j];                     // broadcast shared-memory read
-    if (row_ok && off[j] >= 0) chunk_load<IN>(raw[j], pp.img, origin + off[j], pp.row_split);
+    if (row_ok && off[j] >= 0) chunk_load<IN>(raw[j], pp.img, origin + off[j], pp.row_split, pp.wide_ld != 0);
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -334,7 +339,7 @@ patch_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchPa
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(ewarp * 32) << 16);
-      if constexpr (FAST_EPI) epi_tile_direct(pp.epi, taddr, n_tile * BN, BN, (long long)m_tile * BM + ewarp * 32, pp.M, rm, 0, reinterpret_cast<float*>(stage));
+      if constexpr (FAST_EPI) epi_tile_direct(pp.epi, taddr, n_tile * BN, BN, (long long)m_tile * BM + ewarp * 32, pp.M, rm, 0, reinterpret_cast<float*>(stage), pp.wide_st != 0 && (n_tile * BN * 2) % 32 == 0);
       else epi_tile(pp.epi, taddr, n_tile * BN, BN, (long long)m_tile * BM + ewarp * 32, pp.M, rm, 0, stage);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
@@ -523,7 +528,7 @@ patch_embed_tmem_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchP
     const int ewarp = warp - 4;
     const int lane = threadIdx.x & 31;
     const EpiParams& e = pp.epi;
-    const bool has_res = e.residual != nullptr;
+    const bool has_res = e.residual != nullptr, wide_st = pp.wide_st != 0;
     PeRowMap rm{pp.ntok, pp.rows_per_img, pp.tok_off};
     int pass = 0;
     for (int r = 0; r < rounds; ++r) {
@@ -551,6 +556,7 @@ patch_embed_tmem_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchP
         ptx::mbar_arrive(&d_empty[acc]);                             // the accumulator is in registers: release it now
         if (ok) {
           const float* bs = bias_s + n * kTmBN;
+          uint4 prev = make_uint4(0, 0, 0, 0);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             float v[8];
@@ -566,7 +572,10 @@ patch_embed_tmem_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchP
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] += f[i];
             }
-            outp[n * 8 + q] = epi_pack8(v);
+            const uint4 o = epi_pack8(v);
+            if (!wide_st) outp[n * 8 + q] = o;
+            else if (q & 1) ptx::stg256(outp + n * 8 + q - 1, prev, o);       // one full 32-byte sector per lane
+            else prev = o;
           }
         }
       }
@@ -592,7 +601,7 @@ patch_embed_tmem_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchP
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           off[j] = tbl[kb * 8 + j];
-          if (row_ok && off[j] >= 0) chunk_load<IN>(raw[j], pp.img, origin + off[j]);
+          if (row_ok && off[j] >= 0) chunk_load<IN>(raw[j], pp.img, origin + off[j], 0, pp.wide_ld != 0);
         }
         uint32_t packed[32];
 #pragma unroll
@@ -679,7 +688,7 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const PatchParams pp,
           off = ((long long)b * pp.C + c) * plane + (long long)(r * p + p1) * pp.W + cc * p + p2;
         }
         ChunkRaw raw;
-        chunk_load<IN>(raw, pp.img, off, pp.row_split);
+        chunk_load<IN>(raw, pp.img, off, pp.row_split, pp.wide_ld != 0);
         o = chunk_pack<IN>(raw);
       }
     } else if constexpr (IN != IN_U8) {
@@ -721,6 +730,10 @@ int fill_params(PatchParams& pp, const void* img, int img_bf16, int B, int C, in
               "patch_embed: unknown image format %d", img_bf16);
   pp.in_fmt = img_bf16;
   pp.row_split = (img_bf16 != SFC_IMG_U8_NHWC && p == 4) ? W : 0;
+  static const bool no_wide = getenv("SFC_PE_NO256") != nullptr;               // measurement switch
+  // fp32 chunks as single 32-byte loads: every chunk offset is a multiple of 8 floats when the vectorised path applies
+  pp.wide_ld = (!no_wide && img_bf16 == SFC_IMG_F32_NCHW && p % 8 == 0 && (reinterpret_cast<uintptr_t>(img) & 31) == 0) ? 1 : 0;
+  pp.wide_st = 0;
   SFC_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && p > 0 && g > 0 && D > 0, "patch_embed: bad shape");
   SFC_REQUIRE(H % p == 0 && W % p == 0, "patch_embed: image %dx%d not divisible by pre-patch size %d", H, W, p);
   const int gh = H / p, gw = W / p;
@@ -770,6 +783,7 @@ extern "C" int sfc_patch_embed_fwd(const void* img, int img_bf16, int B, int C, 
   pp.rows_per_img = rows_per_img; pp.tok_off = tok_off;
   const int BN = (D > 128) ? 256 : 128;
   pp.num_n_tiles = sfc_ceil_div(D, BN);
+  pp.wide_st = (getenv("SFC_PE_NO256") == nullptr && (reinterpret_cast<uintptr_t>(out) & 31) == 0 && (ld_out * 2) % 32 == 0 && D % 16 == 0) ? 1 : 0;
   EpiParams& e = pp.epi;
   e.N = D; e.bias = (const __nv_bfloat16*)bias; e.residual = (const __nv_bfloat16*)pos; e.aux = nullptr;
   e.out = out; e.out_pre = nullptr; e.ld_out = ld_out; e.ld_res = ld_pos; e.ld_aux = 0; e.split_stride = 0;

@@ -38,7 +38,10 @@ def test_attention_rejects_unsupported_shapes(cuda_device):
                                   (2, 3, 384, 16, 1, 1024, "peano", "fp32"),
                                   # p == 4: 8-element chunks are two 4-element patch rows (vectorised half-row gather)
                                   (6, 3, 32, 4, 1, 192, "hilbert", "bf16"), (3, 3, 64, 4, 4, 128, "hilbert", "fp32"),
-                                  (3, 1, 32, 4, 2, 128, "moore", "bf16"), (130, 3, 32, 4, 1, 256, "peano", "fp32")])
+                                  (3, 1, 32, 4, 2, 128, "moore", "bf16"), (130, 3, 32, 4, 1, 256, "peano", "fp32"),
+                                  # one k-block per tile: both warp sets of the split epilogue, 1 / 2 / 6 / 8 column chunks
+                                  (2, 3, 16, 4, 1, 32, "z", "fp32"), (40, 3, 32, 4, 1, 64, "hilbert", "fp32"),
+                                  (300, 3, 32, 4, 1, 192, "hilbert", "fp32")])
 def test_patch_embed(cuda_device, args):
     import kernel_selftest as ks
     r = ks.check_patch(*args)
@@ -50,7 +53,8 @@ def test_patch_embed(cuda_device, args):
 # embedding behind a class-token row; cluster sizes 4 / 2 / 1 and the shared-memory kernel via the env switches.
 @pytest.mark.parametrize("args", [(4, 3, 64, 8, 1, 256, "hilbert", "fp32"), (2, 1, 64, 16, 1, 128, "z", "bf16"),
                                   (1, 3, 32, 16, 1, 128, "hilbert", "fp32"), (3, 3, 64, 8, 4, 384, "moore", "fp32"),
-                                  (100, 3, 224, 16, 1, 256, "hilbert", "bf16"), (7, 3, 224, 16, 1, 768, "hilbert", "fp32")])
+                                  (100, 3, 224, 16, 1, 256, "hilbert", "bf16"), (7, 3, 224, 16, 1, 768, "hilbert", "fp32"),
+                                  (9, 3, 32, 4, 1, 192, "hilbert", "fp32"), (9, 3, 32, 4, 1, 320, "moore", "bf16")])
 def test_patch_embed_tmem_resident(cuda_device, args):
     import kernel_selftest as ks
     r = ks.check_patch(*args, pos_cls=True)
