@@ -41,6 +41,7 @@ struct AttnParams {
   __nv_bfloat16* dqkv;     // [B*N, 3D]
   float* dq_acc;           // [B*N, D] fp32, zero-initialised (more than two key tiles: red.global.add)
   __nv_bfloat16* dq_part;  // one or two key tiles: bf16 [B*N, D] partial of key tile 0 when there are two (no atomics)
+  int wide_st;             // backward read-out: 256-bit stores (dqkv and the partial buffer 32-byte aligned)
   int dq_mode;             // 0 = atomics into dq_acc, 1 = single key tile -> dqkv directly, 2 = tile 0 -> dq_part, tile 1 -> dqkv
   float* delta;            // [B, H, N] fp32 rowsum(dO * O)
   long long* dbg;          // optional timeline buffer (sfc_debug_set_timeline), CTA 0 only
@@ -874,6 +875,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             const bool second = p.dq_mode == 2 && jt != 0;
             __nv_bfloat16* part = p.dq_part + (long long)(row0 + qi) * p.D + h * DH + ch * 16;
             __nv_bfloat16* dst = first_of_two ? part : p.dqkv + (long long)(row0 + qi) * (3 * p.D) + h * DH + ch * 16;
+            uint4 o2[2];
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               float v[8];
@@ -884,11 +886,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 v[0] += ptx::bf16_lo(a.x); v[1] += ptx::bf16_hi(a.x); v[2] += ptx::bf16_lo(a.y); v[3] += ptx::bf16_hi(a.y);
                 v[4] += ptx::bf16_lo(a.z); v[5] += ptx::bf16_hi(a.z); v[6] += ptx::bf16_lo(a.w); v[7] += ptx::bf16_hi(a.w);
               }
-              uint4 o;
-              o.x = ptx::pack_bf16(v[0], v[1]); o.y = ptx::pack_bf16(v[2], v[3]);
-              o.z = ptx::pack_bf16(v[4], v[5]); o.w = ptx::pack_bf16(v[6], v[7]);
-              reinterpret_cast<uint4*>(dst)[q] = o;
+              o2[q].x = ptx::pack_bf16(v[0], v[1]); o2[q].y = ptx::pack_bf16(v[2], v[3]);
+              o2[q].z = ptx::pack_bf16(v[4], v[5]); o2[q].w = ptx::pack_bf16(v[6], v[7]);
             }
+            // the lane's 16 columns are one 32-byte sector of its row: one 256-bit store (row-per-lane 16-byte stores
+            // would touch 32 half-filled sectors per instruction, twice)
+            if (p.wide_st) ptx::stg256(dst, o2[0], o2[1]);
+            else { reinterpret_cast<uint4*>(dst)[0] = o2[0]; reinterpret_cast<uint4*>(dst)[1] = o2[1]; }
           }
         }
       }
@@ -903,14 +907,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         ptx::tmem_ld_x32(t, rr);
         ptx::tmem_ld_wait();
         if (ok) {
+          uint4 o4[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            uint4 o;
-            o.x = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 0]), __uint_as_float(rr[q * 8 + 1]));
-            o.y = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 2]), __uint_as_float(rr[q * 8 + 3]));
-            o.z = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 4]), __uint_as_float(rr[q * 8 + 5]));
-            o.w = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 6]), __uint_as_float(rr[q * 8 + 7]));
-            reinterpret_cast<uint4*>(dst)[q] = o;
+            o4[q].x = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 0]), __uint_as_float(rr[q * 8 + 1]));
+            o4[q].y = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 2]), __uint_as_float(rr[q * 8 + 3]));
+            o4[q].z = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 4]), __uint_as_float(rr[q * 8 + 5]));
+            o4[q].w = ptx::pack_bf16(__uint_as_float(rr[q * 8 + 6]), __uint_as_float(rr[q * 8 + 7]));
+          }
+          if (p.wide_st) {
+            ptx::stg256(dst, o4[0], o4[1]);
+            ptx::stg256(dst + 16, o4[2], o4[3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(dst)[q] = o4[q];
           }
         }
       }
@@ -1171,6 +1181,8 @@ extern "C" int sfc_attn_bwd(const void* qkv, const void* out, const void* dout, 
   p.B = B; p.H = H; p.N = N; p.D = D; p.scale = scale; p.drop_p = drop_p; p.drop_seed = drop_seed; p.drop_epoch = sfc_dropout_epoch_ptr();
   p.lse = const_cast<float*>(lse); p.o = (const __nv_bfloat16*)out; p.dout = (const __nv_bfloat16*)dout;
   p.dqkv = (__nv_bfloat16*)dqkv; p.dq_acc = (float*)scratch; p.dq_part = (__nv_bfloat16*)scratch; p.dq_mode = dq_mode;
+  static const bool no_wide = getenv("SFC_ATTN_NO256") != nullptr;          // measurement switch
+  p.wide_st = (!no_wide && ((reinterpret_cast<uintptr_t>(dqkv) | reinterpret_cast<uintptr_t>(scratch)) & 31) == 0) ? 1 : 0;
   p.delta = delta; p.dbg = g_attn_dbg;
   static bool configured = false;
   if (!configured) {

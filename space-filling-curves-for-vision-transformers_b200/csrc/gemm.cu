@@ -499,6 +499,8 @@ extern "C" int sfc_gemm_bf16(const void* A, int a_mn_major, long long lda, const
   e.ld_out = ep->ld_out; e.ld_res = ep->ld_res; e.ld_aux = ep->ld_aux;
   e.alpha = ep->alpha;
   e.act = ep->act; e.aux_mode = ep->aux_mode; e.out_fp32 = ep->out_fp32;
+  static const bool no_wide = getenv("SFC_GEMM_NO256") != nullptr;         // measurement switch
+  e.wide_st256 = no_wide ? 0 : 1;
   e.drop_p = ep->drop_p; e.drop_seed = ep->drop_seed; e.drop_epoch = sfc_dropout_epoch_ptr();
   e.split_stride = 0;
   SFC_REQUIRE(e.aux_mode == SFC_AUX_NONE || e.aux != nullptr, "sfc_gemm_bf16: aux_mode set but aux is null");

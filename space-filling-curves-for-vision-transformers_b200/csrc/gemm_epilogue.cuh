@@ -23,6 +23,7 @@ struct EpiParams {
   int act;                        // SFC_ACT_*
   int aux_mode;                   // SFC_AUX_*
   int out_fp32;
+  int wide_st256;                 // allow 256-bit stores where the addresses are 32-byte aligned (host switch; 0 = off)
   float drop_p;                   // dropout prob applied after activation (0 = off)
   unsigned long long drop_seed;
   const unsigned long long* drop_epoch;   // optional device counter mixed into the seed (null = none)
@@ -351,6 +352,9 @@ __device__ __forceinline__ void epi_tile_fast(const EpiParams& p, uint32_t taddr
   const int cg = lane & 3, rsub = lane >> 2;
   const bool has_bias = p.bias != nullptr, has_res = p.residual != nullptr, has_aux = p.aux_mode != SFC_AUX_NONE;
   const bool has_drop = p.drop_p > 0.0f, f32 = p.out_fp32 != 0;
+  // fp32 output (split-K partials): two 16-byte stores per lane would each half-fill 32 sectors per instruction
+  const bool wide_f32 = f32 && p.wide_st256 && (reinterpret_cast<uintptr_t>(p.out) & 31) == 0 && p.ld_out % 8 == 0 && p.split_stride % 8 == 0 &&
+                        n_begin % 8 == 0;
   const float relu_lo = p.act == SFC_ACT_RELU ? 0.0f : -INFINITY;
   const float alpha = p.alpha;
   const DropKey dkey = drop_key(p.drop_seed, p.drop_p, p.drop_epoch);
@@ -428,8 +432,13 @@ __device__ __forceinline__ void epi_tile_fast(const EpiParams& p, uint32_t taddr
         }
         if (f32) {
           float4* op = reinterpret_cast<float4*>(outp[it] + coff * 4);
-          op[0] = make_float4(v[0], v[1], v[2], v[3]);
-          op[1] = make_float4(v[4], v[5], v[6], v[7]);
+          if (wide_f32) {                          // the lane's 8 fp32 = one 32-byte sector: a single 256-bit store
+            ptx::stg256(op, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])),
+                        make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
+          } else {
+            op[0] = make_float4(v[0], v[1], v[2], v[3]);
+            op[1] = make_float4(v[4], v[5], v[6], v[7]);
+          }
         } else {
           *reinterpret_cast<uint4*>(outp[it] + coff * 2) = epi_pack8(v);
         }
