@@ -207,3 +207,50 @@ def test_curve_properties_hypothesis(host_curve_lib):
         if cid != 1 and P > 1:                               # continuity (the Z curve jumps by construction)
             assert int((np.abs(np.diff(i)) + np.abs(np.diff(j))).max()) == 1
     prop()
+
+
+def test_main_py_import_surface():
+    """Every `src.*` name the reference's driver imports (main.py:25-42) resolves in this package's mirror, with the
+    constructor / call signatures main.py uses (keyword names only — no GPU work)."""
+    import importlib
+    import inspect
+    surface = {
+        "src.tokenizers._2D.zigzag_embedding": ["ZigzagEmbedding"],
+        "src.tokenizers._1D.zigzag_embedding1D": ["RasterScan1DEmbedding"],
+        "src.tokenizers._1D.hilbert_embedding1D": ["HilbertEmbedding1D"],
+        "src.tokenizers._1D.peano_embedding1D": ["PeanoEmbedding1D"],
+        "src.tokenizers._1D.moore_embedding1D": ["MooreEmbedding1D"],
+        "src.tokenizers._1D.onion_embedding1D": ["OnionEmbedding1D"],
+        "src.tokenizers._1D.morton_embedding1D": ["MortonEmbedding1D"],
+        "src.tokenizers.multiscale.multi_morton": ["HierarchicalMortonEmbedding"],
+        "src.tokenizers.multiscale.multi_zigzag": ["HierarchicalRasterScanEmbedding"],
+        "src.tokenizers.multiscale.multi_hilbert": ["HierarchicalHilbertEmbedding", "SFCEmbedding1D"],
+        "src.tokenizers.multiscale.multi_peano": ["HierarchicalPeanoEmbedding"],
+        "src.tokenizers.multiscale.multi_moore": ["HierarchicalMooreEmbedding"],
+        "src.tokenizers.multiscale.multi_onion": ["HierarchicalOnionEmbedding"],
+        "src.tokenizers._2D.hilbert_embedding": ["HilbertEmbedding"],
+        "src.tokenizers._2D.random_embedding": ["RandomEmbedding"],
+        "src.models.vit": ["VisionTransformer1D", "VisionTransformer", "HierarchicalVisionTransformer1D", "TransformerSeqEncoder",
+                           "MixerBlock", "FactorisedLinear", "MultiLayerPredictor"],
+        "src.models.altvit": ["HilbertViT", "SimpleViT"],
+        "src.training.train": ["evaluate", "train_with_mixup_or_cutmix", "train", "train_with_scheduler", "mixup_data",
+                               "cutmix_data", "rand_bbox", "mixup_criterion"],
+        "src.training.scheduler": ["WarmupCosineScheduler"],
+        "src.curves.space_filling_curves": ["hilbert_curve", "z_curve", "peano_curve", "moore_curve", "onion_curve", "grid_size",
+                                            "embed_and_prune_sfc", "block_stitch_sfc", "refine_curve_to_hamiltonian",
+                                            "find_hamiltonian_path"],
+    }
+    for mod, names in surface.items():
+        m = importlib.import_module(mod)
+        for n in names:
+            assert hasattr(m, n), f"{mod}.{n}"
+    from src.models.vit import VisionTransformer1D
+    from src.tokenizers.multiscale.multi_morton import HierarchicalMortonEmbedding
+    from src.tokenizers._2D.zigzag_embedding import ZigzagEmbedding
+    from src.training.train import evaluate, train_with_mixup_or_cutmix
+    # main.py:255-282 (keyword construction) and :300-312 (positional calls)
+    assert {"img_size", "in_channels", "patch_size_list", "embed_dim"} <= set(inspect.signature(HierarchicalMortonEmbedding).parameters)
+    assert {"img_size", "patch_size", "in_channels", "embed_dim"} <= set(inspect.signature(ZigzagEmbedding).parameters)
+    assert {"patch_embed", "depth", "n_heads", "mlp_dim", "num_classes"} <= set(inspect.signature(VisionTransformer1D).parameters)
+    assert list(inspect.signature(train_with_mixup_or_cutmix).parameters)[:6] == ["model", "train_loader", "criterion", "optimizer", "scheduler", "device"]
+    assert list(inspect.signature(evaluate).parameters)[:4] == ["model", "test_loader", "criterion", "device"]
