@@ -238,15 +238,17 @@ colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long lo
 }
 
 // out_v[c] = (accumulate ? out_v[c] : 0) + sum_b part[b * stride + v * vstride + c]   for v < nvec output vectors.
-// grid (ceil(N / 32), nvec), block (32 columns x 8 part-lanes): the partials of a column are summed by 8 threads with
-// independent loads in flight instead of one long dependent loop.
+// grid (ceil(N / 32), nvec), block (32 columns x kFinLanes part-lanes): the partials of a column are summed by kFinLanes
+// threads with four independent loads in flight each instead of one long dependent loop (444 partials of a LayerNorm
+// backward: 4 rounds of loads per thread).
 struct FinalizeOut { void* ptr[3]; };
-__global__ void __launch_bounds__(256) partial_finalize_kernel(const float* __restrict__ part, int nparts, long long stride,
-                                                               long long vstride, int N, FinalizeOut outs, int out_fp32,
-                                                               int accumulate) {
+template <int kFinLanes>
+__global__ void __launch_bounds__(32 * kFinLanes) partial_finalize_kernel(const float* __restrict__ part, int nparts, long long stride,
+                                                                          long long vstride, int N, FinalizeOut outs, int out_fp32,
+                                                                          int accumulate) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
-  __shared__ float sred[8][33];
+  __shared__ float sred[kFinLanes][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
   const int v = blockIdx.y;
@@ -255,13 +257,13 @@ __global__ void __launch_bounds__(256) partial_finalize_kernel(const float* __re
     const float* base = part + v * vstride + c;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     int b = ty;
-    for (; b + 24 < nparts; b += 32) {
+    for (; b + 3 * kFinLanes < nparts; b += 4 * kFinLanes) {
       s0 += base[(long long)b * stride];
-      s1 += base[(long long)(b + 8) * stride];
-      s2 += base[(long long)(b + 16) * stride];
-      s3 += base[(long long)(b + 24) * stride];
+      s1 += base[(long long)(b + kFinLanes) * stride];
+      s2 += base[(long long)(b + 2 * kFinLanes) * stride];
+      s3 += base[(long long)(b + 3 * kFinLanes) * stride];
     }
-    for (; b < nparts; b += 8) s0 += base[(long long)b * stride];
+    for (; b < nparts; b += kFinLanes) s0 += base[(long long)b * stride];
     s = (s0 + s1) + (s2 + s3);
   }
   sred[ty][tx] = s;
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(256) partial_finalize_kernel(const float* __re
   if (ty == 0 && c < N) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += sred[w][tx];
+    for (int w = 0; w < kFinLanes; ++w) t += sred[w][tx];
     void* out = outs.ptr[v];
     if (out_fp32) {
       float* o = reinterpret_cast<float*>(out) + c;
@@ -375,7 +377,9 @@ extern "C" int sfc_layernorm_bwd(const void* dy, const void* x, const float* mea
   FinalizeOut outs;
   outs.ptr[0] = dgamma; outs.ptr[1] = dbeta; outs.ptr[2] = dcolsum;
   dim3 grid(sfc_ceil_div(D, 32), csum ? 3 : 2);
-  SFC_CUDA_OK(sfc_launch_pdl(partial_finalize_kernel, grid, dim3(256), 0, stream, (const float*)scratch, blocks, 3ll * D, (long long)D, D, outs, param_fp32, accumulate));
+  static const bool fin8 = getenv("SFC_FIN8") != nullptr;                 // measurement switch: the 8-lane variant
+  if (fin8) SFC_CUDA_OK(sfc_launch_pdl(partial_finalize_kernel<8>, grid, dim3(256), 0, stream, (const float*)scratch, blocks, 3ll * D, (long long)D, D, outs, param_fp32, accumulate));
+  else SFC_CUDA_OK(sfc_launch_pdl(partial_finalize_kernel<32>, grid, dim3(1024), 0, stream, (const float*)scratch, blocks, 3ll * D, (long long)D, D, outs, param_fp32, accumulate));
   SFC_LAUNCH_OK();
   return 0;
 }
@@ -399,7 +403,7 @@ extern "C" int sfc_colsum(const void* x, long long ld, long long rows, int N, vo
   SFC_LAUNCH_OK();
   FinalizeOut outs;
   outs.ptr[0] = out; outs.ptr[1] = nullptr; outs.ptr[2] = nullptr;
-  partial_finalize_kernel<<<dim3(sfc_ceil_div(N, 32), 1), 256, 0, stream>>>((const float*)scratch, rb, (long long)N, 0, N, outs, out_fp32, accumulate);
+  partial_finalize_kernel<8><<<dim3(sfc_ceil_div(N, 32), 1), 256, 0, stream>>>((const float*)scratch, rb, (long long)N, 0, N, outs, out_fp32, accumulate);
   SFC_LAUNCH_OK();
   return 0;
 }
