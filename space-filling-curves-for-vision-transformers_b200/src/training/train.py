@@ -12,6 +12,7 @@ import torch.nn.functional as F
 from tqdm import tqdm
 
 from . import distributed as D
+from ._nvtx import span
 
 
 def mixup_data(x, y, alpha=0.2):
@@ -216,21 +217,25 @@ def train_with_mixup_or_cutmix(model, train_loader, criterion, optimizer, schedu
     full_batch = None
     bar = _bar(train_loader, "Training")
     for images, labels in bar:
-        images, labels = images.to(device), labels.to(device)
-        if full_batch is None:
-            full_batch = D.shard(images, rank, ws).size(0)          # the loader's batch size (per rank): the shape that is captured
-        if np.random.rand() < mix_prob:
-            images, y_a, y_b, lam = mixup_data(images, labels, alpha=mixup_alpha)
-        else:
-            images, y_a, y_b, lam = cutmix_data(images, labels, alpha=cutmix_alpha)
-        images, y_a, y_b = D.shard(images, rank, ws), D.shard(y_a, rank, ws), D.shard(y_b, rank, ws)
-        num_classes = _num_classes(model, images)
-        soft_targets = lam * F.one_hot(y_a, num_classes).float() + (1 - lam) * F.one_hot(y_b, num_classes).float()
-        outputs, loss = _step(model, criterion, optimizer, images, soft_targets, full_batch, torch.bfloat16)
-        D.allreduce_gradients(model.parameters(), ws)
-        _clip_grad_norm(model.parameters(), 1.0)
-        optimizer.step()
-        scheduler.step()
+        with span("batch prep"):
+            images, labels = images.to(device), labels.to(device)
+            if full_batch is None:
+                full_batch = D.shard(images, rank, ws).size(0)      # the loader's batch size (per rank): the shape that is captured
+            if np.random.rand() < mix_prob:
+                images, y_a, y_b, lam = mixup_data(images, labels, alpha=mixup_alpha)
+            else:
+                images, y_a, y_b, lam = cutmix_data(images, labels, alpha=cutmix_alpha)
+            images, y_a, y_b = D.shard(images, rank, ws), D.shard(y_a, rank, ws), D.shard(y_b, rank, ws)
+            num_classes = _num_classes(model, images)
+            soft_targets = lam * F.one_hot(y_a, num_classes).float() + (1 - lam) * F.one_hot(y_b, num_classes).float()
+        with span("forward+backward"):
+            outputs, loss = _step(model, criterion, optimizer, images, soft_targets, full_batch, torch.bfloat16)
+        with span("allreduce"):
+            D.allreduce_gradients(model.parameters(), ws)
+        with span("clip+optimizer"):
+            _clip_grad_norm(model.parameters(), 1.0)
+            optimizer.step()
+            scheduler.step()
         preds = outputs.argmax(dim=1)
         total_correct += (lam * (preds == y_a).float() + (1 - lam) * (preds == y_b).float()).sum().item()
         total_loss += loss.item() * images.size(0)

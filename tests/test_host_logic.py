@@ -254,3 +254,11 @@ def test_main_py_import_surface():
     assert {"patch_embed", "depth", "n_heads", "mlp_dim", "num_classes"} <= set(inspect.signature(VisionTransformer1D).parameters)
     assert list(inspect.signature(train_with_mixup_or_cutmix).parameters)[:6] == ["model", "train_loader", "criterion", "optimizer", "scheduler", "device"]
     assert list(inspect.signature(evaluate).parameters)[:4] == ["model", "test_loader", "criterion", "device"]
+
+
+def test_nvtx_spans_are_inert_by_default():
+    """SFC_NVTX is opt-in: without it (and on a box without CUDA) the span context manager does nothing."""
+    from src.training import _nvtx
+    assert not _nvtx.enabled()
+    with _nvtx.span("x"):
+        pass
